@@ -1,0 +1,178 @@
+/*
+ * pixelbox_b200.h -- C ABI of the B200-native similarity-search library for PixelBox.
+ *
+ * This is the drop-in boundary for ONE path of the reference (JosephCatrambone/pixelbox): the
+ * brute-force cosine-distance scan + top-k over the u8-quantized hashes of the SQLite
+ * `semantic_hashes` table.  The reference has no FFI for this path today; each entry point
+ * below names the reference code it replaces (paths relative to the reference checkout) and
+ * INTEGRATION.md shows the Rust `extern "C"` block and the engine.rs patch that binds them.
+ *
+ * Conventions
+ *   - plain C, no C++ types, no exceptions across the boundary; every call returns PBX_OK (0)
+ *     or a negative PBX_E_* code; pbx_last_error() gives a thread-local message.
+ *   - the caller owns every input and output buffer; the library copies inputs before it returns.
+ *   - a pbx_corpus is one device-resident shard of the table on ONE B200 (sm_100).  There is
+ *     no CPU fallback: without an sm_100 device pbx_corpus_create fails with PBX_E_NO_DEVICE.
+ *   - results are the reference's: rows with (f64)dist < max_dist, ordered by (dist asc,
+ *     image_id asc), at most k of them (src/engine.rs:379-381), where dist is the reference's
+ *     f32 cosine_distance (src/engine.rs:572-588) reproduced bit for bit.
+ */
+#ifndef PIXELBOX_B200_H
+#define PIXELBOX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define PBX_API __declspec(dllexport)
+#else
+#define PBX_API __attribute__((visibility("default")))
+#endif
+
+#define PBX_OK 0
+#define PBX_E_INVALID (-1)     /* null pointer, k == 0 where not allowed, bad sizes            */
+#define PBX_E_DIM (-2)         /* dim == 0 or dim > PBX_MAX_DIM                                  */
+#define PBX_E_OOM (-3)         /* host or device allocation failed                              */
+#define PBX_E_CUDA (-4)        /* a CUDA runtime call or kernel failed                          */
+#define PBX_E_NO_DEVICE (-5)   /* no sm_100 (B200) device: there is no CPU fallback             */
+#define PBX_E_CAPACITY (-6)    /* more than PBX_MAX_ROWS rows in one shard                      */
+#define PBX_E_K (-7)           /* k > PBX_MAX_K                                                  */
+#define PBX_E_INTERNAL (-8)    /* an internal invariant failed (a bug; never a silent wrong answer) */
+
+#define PBX_MAX_DIM 16384u
+#define PBX_MAX_K 2048u
+#define PBX_MAX_ROWS 0xFFFFFFF0ull
+
+/* DEFAULT_MAX_QUERY_DISTANCE and the literal LIMIT of the reference (src/engine.rs:23, :381). */
+#define PBX_DEFAULT_MAX_DIST 1e3
+#define PBX_DEFAULT_K 100u
+
+typedef struct pbx_corpus pbx_corpus;
+
+/* One result row.  image_id / dist are what src/engine.rs:384-387 reads back from SQLite
+ * (row.get(0), row.get(7)); dot / norm2 are the exact integer terms of SURVEY.md section 8a:
+ * dot = sum c(q_i) c(r_i), norm2 = sum c(r_i)^2 with c(v) = 2v - 255.
+ * Also the record the shards exchange (one NCCL all-gather of k of these per query). */
+typedef struct pbx_hit {
+    int64_t image_id;
+    float dist;
+    int32_t dot;
+    int32_t norm2;
+    uint32_t flags; /* bit 0: produced by the exact (tie-resolving) pass */
+} pbx_hit;
+
+typedef struct pbx_stats {
+    uint64_t rows;             /* committed rows                                   */
+    uint64_t capacity_rows;    /* allocated rows                                   */
+    uint32_t dim;
+    uint32_t row_pitch;        /* bytes between rows in HBM (dim rounded up to 16) */
+    uint64_t queries;          /* queries answered since create                    */
+    uint64_t exact_passes;     /* queries that needed the exact tie-resolving pass */
+    float last_search_ms;      /* device time of the last pbx_search (CUDA events) */
+    float last_scan_ms;        /* ... of its scan kernels alone                    */
+    uint64_t last_bytes_scanned; /* rows * dim * nq of the last pbx_search         */
+    int32_t device;
+    int32_t sm_count;
+    int32_t scan_grid;         /* CTAs of the persistent scan kernel               */
+    int32_t reserved;
+} pbx_stats;
+
+/* ---- lifecycle -------------------------------------------------------------------------
+ * Replaces: the table itself, `CREATE TABLE semantic_hashes (image_id INTEGER PRIMARY KEY,
+ * hash BLOB)` (src/engine.rs:48, :109), as the thing the scan reads.  `device` is a CUDA
+ * ordinal; capacity_hint rows are reserved up front (the corpus still grows on append). */
+PBX_API int pbx_corpus_create(uint32_t dim, uint64_t capacity_hint, int device, pbx_corpus** out);
+PBX_API void pbx_corpus_destroy(pbx_corpus* c);
+
+/* Replaces: nothing upstream does this explicitly -- SQLite pages the table in during every
+ * scan.  Hook: Engine::open after src/engine.rs:129, fed by
+ * `SELECT image_id, hash FROM semantic_hashes ORDER BY image_id`.  Discards previous contents.
+ * hashes is [n][dim] row-major u8.  Rows whose blob length != dim cannot be expressed here;
+ * the caller must reject them (the reference would zip-truncate, src/engine.rs:585). */
+PBX_API int pbx_corpus_load(pbx_corpus* c, const int64_t* image_ids, const uint8_t* hashes, uint64_t n);
+
+/* Replaces: the hash INSERT of src/engine.rs:251-256 as seen by later scans.  Hook: the writer
+ * loop src/engine.rs:188-200, after the INSERT reports a changed row.  Safe to call while
+ * another thread is inside pbx_search: a search sees a committed prefix of the rows. */
+PBX_API int pbx_corpus_append(pbx_corpus* c, const int64_t* image_ids, const uint8_t* hashes, uint64_t n);
+
+/* Bench/test only: fills the shard on the device with rows [first_row, first_row + n) of the
+ * counter-based synthetic corpus (pixelbox_b200/synth.py), image_id = global row + 1. */
+PBX_API int pbx_corpus_fill_synthetic(pbx_corpus* c, uint64_t n, uint64_t seed, uint64_t first_row);
+
+PBX_API int pbx_corpus_size(const pbx_corpus* c, uint64_t* n_rows);
+PBX_API int pbx_corpus_dim(const pbx_corpus* c, uint32_t* dim);
+
+/* Copies rows [first, first + n) back to the host (tests, and result hydration of
+ * IndexedImage.visual_hash, src/engine.rs:385).  Either output may be NULL. */
+PBX_API int pbx_corpus_read_rows(const pbx_corpus* c, uint64_t first, uint64_t n, int64_t* image_ids, uint8_t* hashes);
+
+/* ---- search ----------------------------------------------------------------------------
+ * Replaces: the SQL statement of Engine::query_by_image_hash_from_image,
+ *   SELECT ..., cosine_distance(?, semantic_hashes.hash) AS dist FROM semantic_hashes ...
+ *   WHERE dist < ? ORDER BY dist ASC LIMIT 100            (src/engine.rs:375-383)
+ * together with the scalar UDF it calls per row (src/engine.rs:608-622) and the distance
+ * function itself (src/engine.rs:572-588).  queries is [nq][dim] u8 (IndexedImage.visual_hash,
+ * src/indexed_image.rs:28); k replaces the literal LIMIT; max_dist is
+ * Engine.max_distance_from_query (src/engine.rs:92), compared as `(f64)dist < max_dist`.
+ * Outputs are [nq][k]; out_count[q] <= k rows are valid for query q; any of out_dist, out_dot,
+ * out_norm2 may be NULL.  Synchronous: host buffers in, host buffers out. */
+PBX_API int pbx_search(pbx_corpus* c, const uint8_t* queries, uint32_t nq, uint32_t k, double max_dist,
+                       int64_t* out_ids, float* out_dist, int32_t* out_dot, int32_t* out_norm2,
+                       uint32_t* out_count);
+
+/* Same search, but as the per-shard half of a row-sharded corpus: leaves [nq][k] pbx_hit
+ * records (unused tail slots have image_id = INT64_MAX, dist = +inf) and [nq] counts in host
+ * memory, ready for the all-gather. */
+PBX_API int pbx_search_hits(pbx_corpus* c, const uint8_t* queries, uint32_t nq, uint32_t k, double max_dist,
+                            pbx_hit* out_hits, uint32_t* out_count);
+
+/* Device-resident, asynchronous variant: d_queries [nq][dim], d_hits [nq][k] and d_count [nq]
+ * are DEVICE pointers on the corpus' device; the work is enqueued on `cuda_stream` (a
+ * cudaStream_t; NULL = the corpus' own stream) and the call returns without waiting.  This is
+ * what a pipeline (or the multi-GPU driver, which all-gathers d_hits with NCCL on the same
+ * stream) uses; no host synchronisation happens inside. */
+PBX_API int pbx_search_device(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, uint32_t k, double max_dist,
+                              pbx_hit* d_hits, uint32_t* d_count, void* cuda_stream);
+
+/* Merge step after the all-gather: gathered is [n_shards][nq][k] hits and
+ * counts is [n_shards][nq], both in HOST memory; every shard list is already ordered by
+ * (dist, image_id).  Writes the global first k per query under the same order.  Pure host
+ * logic (a k-way merge of <= n_shards*k records), usable without a GPU. */
+PBX_API int pbx_merge_hits(const pbx_hit* gathered, const uint32_t* counts, uint32_t n_shards, uint32_t nq, uint32_t k,
+                           pbx_hit* out_hits, uint32_t* out_count);
+
+/* Device-side form of the same merge for pipelines that keep the gathered records in HBM (the
+ * buffer an NCCL all-gather of the pbx_search_device outputs produces): all pointers are DEVICE
+ * pointers, the kernel is enqueued on `cuda_stream` (NULL = the legacy default stream) of
+ * `device` and the call does not wait. */
+PBX_API int pbx_merge_hits_device(int device, const pbx_hit* d_gathered, const uint32_t* d_counts, uint32_t n_shards,
+                                  uint32_t nq, uint32_t k, pbx_hit* d_out_hits, uint32_t* d_out_count, void* cuda_stream);
+
+/* ---- the scalar function, for external users of the DB -----------------------------------
+ * Replaces: `pub fn cosine_distance(&Vec<u8>, &Vec<u8>) -> f32` (src/engine.rs:572-588) for a
+ * batch of pairs: a and b are [n][dim] u8 in host memory; out_dist[n] receives the reference's
+ * f32 value bit for bit, out_dot / out_norm2_a / out_norm2_b (optional) the exact integers.
+ * Runs on the GPU of `device`. */
+PBX_API int pbx_cosine_distance_pairs(int device, const uint8_t* a, const uint8_t* b, uint64_t n, uint32_t dim,
+                                      float* out_dist, int32_t* out_dot, int32_t* out_norm2_a, int32_t* out_norm2_b);
+
+/* ---- diagnostics ------------------------------------------------------------------------- */
+PBX_API int pbx_get_stats(const pbx_corpus* c, pbx_stats* out);
+/* Tuning knob for tests: candidate slack of the fast pass (candidates = k + slack); 0 restores
+ * the default.  A tiny slack forces the exact pass and must not change any result. */
+PBX_API int pbx_set_candidate_slack(pbx_corpus* c, uint32_t slack);
+/* CTAs per SM of the persistent scan kernel (0 = default). */
+PBX_API int pbx_set_scan_ctas_per_sm(pbx_corpus* c, uint32_t ctas_per_sm);
+PBX_API const char* pbx_last_error(void);
+PBX_API const char* pbx_version(void);
+PBX_API int pbx_device_count(void); /* number of sm_100 devices visible; 0 if none */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIXELBOX_B200_H */

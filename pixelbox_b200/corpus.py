@@ -1,0 +1,164 @@
+"""Corpus: one device-resident shard of the `semantic_hashes` table (src/engine.rs:48) on one B200.
+
+Thin host wrapper over the C ABI (include/pixelbox_b200.h); all compute is in the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, NamedTuple, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as nat
+
+
+class SearchResult(NamedTuple):
+    """Rows of one query, ordered by (dist asc, image_id asc) -- what src/engine.rs:384-387 maps."""
+    ids: np.ndarray     # int64
+    dist: np.ndarray    # float32: the reference's f32 cosine_distance, bit for bit
+    dot: np.ndarray     # int32: sum c(q) c(r), c(v) = 2v - 255
+    norm2: np.ndarray   # int32: sum c(r)^2
+
+
+def _as_u8_2d(a, dim: int, what: str) -> np.ndarray:
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.uint8))
+    if a.ndim == 1:
+        a = a.reshape(1, -1) if a.size else a.reshape(0, dim)
+    if a.ndim != 2 or a.shape[1] != dim:
+        # the reference would zip-truncate a length mismatch (src/engine.rs:585); the device
+        # corpus cannot represent one, so it is an error here
+        raise nat.PbxError(-2, f"{what}: expected [n][{dim}] bytes, got shape {tuple(a.shape)}")
+    return a
+
+
+class Corpus:
+    def __init__(self, dim: int, capacity_hint: int = 0, device: int = 0):
+        self._h = ctypes.c_void_p(0)
+        self.dim = int(dim)
+        self.device = int(device)
+        nat.check(nat.lib().pbx_corpus_create(self.dim, int(capacity_hint), self.device, ctypes.byref(self._h)))
+
+    # -- lifecycle ---------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            nat.lib().pbx_corpus_destroy(self._h)
+            self._h = ctypes.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __len__(self) -> int:
+        n = ctypes.c_uint64(0)
+        nat.check(nat.lib().pbx_corpus_size(self._h, ctypes.byref(n)))
+        return int(n.value)
+
+    @property
+    def handle(self) -> ctypes.c_void_p:
+        return self._h
+
+    # -- contents ----------------------------------------------------------------------------
+    def load(self, image_ids, hashes) -> None:
+        hashes = _as_u8_2d(hashes, self.dim, "load")
+        ids = np.ascontiguousarray(np.asarray(image_ids, dtype=np.int64))
+        if ids.shape != (hashes.shape[0],):
+            raise nat.PbxError(-1, "load: one image_id per hash row required")
+        nat.check(nat.lib().pbx_corpus_load(self._h, nat.ptr(ids), nat.ptr(hashes), hashes.shape[0]))
+
+    def append(self, image_ids, hashes) -> None:
+        hashes = _as_u8_2d(hashes, self.dim, "append")
+        ids = np.ascontiguousarray(np.asarray(image_ids, dtype=np.int64)).reshape(-1)
+        if ids.shape != (hashes.shape[0],):
+            raise nat.PbxError(-1, "append: one image_id per hash row required")
+        nat.check(nat.lib().pbx_corpus_append(self._h, nat.ptr(ids), nat.ptr(hashes), hashes.shape[0]))
+
+    def fill_synthetic(self, n: int, seed: int, first_row: int = 0) -> None:
+        nat.check(nat.lib().pbx_corpus_fill_synthetic(self._h, int(n), int(seed), int(first_row)))
+
+    def read_rows(self, first: int, n: int) -> Tuple[np.ndarray, np.ndarray]:
+        ids = np.zeros(n, np.int64)
+        rows = np.zeros((n, self.dim), np.uint8)
+        nat.check(nat.lib().pbx_corpus_read_rows(self._h, int(first), int(n), nat.ptr(ids), nat.ptr(rows)))
+        return ids, rows
+
+    # -- search ------------------------------------------------------------------------------
+    def search(self, queries, k: int = nat.DEFAULT_K, max_dist: float = nat.DEFAULT_MAX_DIST) -> List[SearchResult]:
+        """pbx_search: host buffers in, host buffers out; one SearchResult per query."""
+        q = _as_u8_2d(queries, self.dim, "search")
+        nq = q.shape[0]
+        ids = np.zeros((nq, k), np.int64)
+        dist = np.zeros((nq, k), np.float32)
+        dot = np.zeros((nq, k), np.int32)
+        n2 = np.zeros((nq, k), np.int32)
+        cnt = np.zeros(nq, np.uint32)
+        nat.check(nat.lib().pbx_search(self._h, nat.ptr(q), nq, int(k), float(max_dist), nat.ptr(ids), nat.ptr(dist),
+                                       nat.ptr(dot), nat.ptr(n2), nat.ptr(cnt)))
+        return [SearchResult(ids[i, :cnt[i]].copy(), dist[i, :cnt[i]].copy(), dot[i, :cnt[i]].copy(), n2[i, :cnt[i]].copy())
+                for i in range(nq)]
+
+    def search_hits(self, queries, k: int = nat.DEFAULT_K, max_dist: float = nat.DEFAULT_MAX_DIST) -> Tuple[np.ndarray, np.ndarray]:
+        """pbx_search_hits: ([nq][k] pbx_hit records, [nq] counts) -- the per-shard half of a sharded search."""
+        q = _as_u8_2d(queries, self.dim, "search_hits")
+        nq = q.shape[0]
+        hits = np.zeros((nq, k), nat.HIT_DTYPE)
+        cnt = np.zeros(nq, np.uint32)
+        nat.check(nat.lib().pbx_search_hits(self._h, nat.ptr(q), nq, int(k), float(max_dist), nat.ptr(hits), nat.ptr(cnt)))
+        return hits, cnt
+
+    def search_device(self, d_queries_ptr: int, nq: int, k: int, max_dist: float, d_hits_ptr: int, d_count_ptr: int,
+                      stream: int = 0) -> None:
+        """pbx_search_device: raw device pointers, enqueued on `stream` (a cudaStream_t value), no host sync."""
+        nat.check(nat.lib().pbx_search_device(self._h, ctypes.c_void_p(d_queries_ptr), int(nq), int(k), float(max_dist),
+                                              ctypes.c_void_p(d_hits_ptr), ctypes.c_void_p(d_count_ptr),
+                                              ctypes.c_void_p(stream)))
+
+    # -- diagnostics -------------------------------------------------------------------------
+    def stats(self) -> nat.PbxStats:
+        s = nat.PbxStats()
+        nat.check(nat.lib().pbx_get_stats(self._h, ctypes.byref(s)))
+        return s
+
+    def set_candidate_slack(self, slack: int) -> None:
+        nat.check(nat.lib().pbx_set_candidate_slack(self._h, int(slack)))
+
+    def set_scan_ctas_per_sm(self, n: int) -> None:
+        nat.check(nat.lib().pbx_set_scan_ctas_per_sm(self._h, int(n)))
+
+
+def merge_hits(gathered: np.ndarray, counts: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
+    """pbx_merge_hits: gathered [n_shards][nq][k] records + counts [n_shards][nq] -> global ([nq][k], [nq])."""
+    gathered = np.ascontiguousarray(gathered, dtype=nat.HIT_DTYPE)
+    counts = np.ascontiguousarray(counts, dtype=np.uint32)
+    n_shards, nq = counts.shape
+    assert gathered.shape == (n_shards, nq, k), (gathered.shape, (n_shards, nq, k))
+    out = np.zeros((nq, k), nat.HIT_DTYPE)
+    cnt = np.zeros(nq, np.uint32)
+    nat.check(nat.lib().pbx_merge_hits(nat.ptr(gathered), nat.ptr(counts), n_shards, nq, int(k), nat.ptr(out), nat.ptr(cnt)))
+    return out, cnt
+
+
+def cosine_distance_pairs(a, b, device: int = 0):
+    """pbx_cosine_distance_pairs: the reference's cosine_distance (src/engine.rs:572-588) on the GPU for
+    explicit pairs; returns (dist f32, dot i32, norm2_a i32, norm2_b i32)."""
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.uint8))
+    b = np.ascontiguousarray(np.asarray(b, dtype=np.uint8))
+    if a.ndim == 1:
+        a, b = a.reshape(1, -1), b.reshape(1, -1)
+    if a.shape != b.shape:
+        raise nat.PbxError(-2, f"pair shapes differ: {a.shape} vs {b.shape}")
+    n, d = a.shape
+    dist = np.zeros(n, np.float32)
+    dot = np.zeros(n, np.int32)
+    na = np.zeros(n, np.int32)
+    nb = np.zeros(n, np.int32)
+    nat.check(nat.lib().pbx_cosine_distance_pairs(int(device), nat.ptr(a), nat.ptr(b), n, d, nat.ptr(dist), nat.ptr(dot),
+                                                  nat.ptr(na), nat.ptr(nb)))
+    return dist, dot, na, nb

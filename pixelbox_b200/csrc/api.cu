@@ -1,0 +1,757 @@
+// api.cu -- the C ABI of include/pixelbox_b200.h: device-resident corpus shard, append, search.
+// Host side of the hot path; the kernels are in scan.cuh / finalize.cuh.
+#include <atomic>
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <new>
+#include <type_traits>
+#include <vector>
+
+#include "finalize.cuh"
+
+using namespace pbx;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU_TRY(expr)                                                                               \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(e__ == cudaErrorMemoryAllocation ? PBX_E_OOM : PBX_E_CUDA, "%s failed: %s (%s:%d)", #expr, \
+                        cudaGetErrorString(e__), __FILE__, __LINE__);                              \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// corpus
+// ------------------------------------------------------------------------------------------------
+struct pbx_corpus {
+    int device = 0;
+    int sm_count = 0;
+    uint32_t dim = 0, pitch = 0, pitch16 = 0;
+    std::atomic<uint64_t> n{0};       // committed rows (searches see a prefix)
+    uint64_t capacity = 0;            // allocated rows, multiple of kTileRows
+    uint8_t* d_rows = nullptr;
+    float* d_inv = nullptr;
+    int64_t* d_ids = nullptr;
+
+    cudaStream_t stream = nullptr;    // default search stream
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_chain = nullptr;   // serialises searches enqueued on different streams
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;   // around the last fast-pass scan kernel of a timed search
+    float last_scan_ms = 0.f;
+    bool chain_valid = false;
+
+    // per-batch query scratch
+    uint32_t max_nq = 0;
+    uint8_t* d_queries = nullptr;
+    int16_t* d_q16 = nullptr;
+    uint8_t* d_qbytes = nullptr;
+    QueryHeader* d_qh = nullptr;
+    SearchStatus* d_status = nullptr;
+    pbx_hit* d_hits = nullptr;
+    uint32_t* d_counts = nullptr;
+    size_t hits_cap = 0;
+    // scan scratch
+    void* d_cand = nullptr;
+    size_t cand_bytes = 0;
+    uint32_t* d_cand_cnt = nullptr;
+    uint32_t* d_tile_counter = nullptr;
+    unsigned long long* d_exact_passes = nullptr;
+    // pinned staging
+    uint8_t* h_queries = nullptr;
+    size_t h_queries_cap = 0;
+    pbx_hit* h_hits = nullptr;
+    uint32_t* h_counts = nullptr;
+    size_t h_hits_cap = 0;
+    uint8_t* h_stage = nullptr;       // append staging
+    size_t h_stage_cap = 0;
+
+    std::mutex mu;                    // searches and structural changes
+    std::mutex append_mu;             // appends among themselves
+
+    uint32_t slack = 0;               // 0 = default
+    uint32_t ctas_per_sm = 0;         // 0 = default
+    uint64_t queries = 0;
+    float last_search_ms = 0.f;
+    uint64_t last_bytes = 0;
+    int last_grid = 0;
+};
+
+static uint32_t default_keep(uint32_t k, uint32_t slack) {
+    uint32_t s = slack ? slack : std::max<uint32_t>(156u, k / 4u);
+    uint32_t keep = k + s;
+    if (!slack) keep = (keep + 31u) & ~31u;
+    return std::min<uint32_t>(keep, 4096u);
+}
+
+static float certificate_margin(uint32_t dim) {
+    // 2 * (eps_d + 5u) + 2^-21 with eps_d = (2d + 1600) u, u = 2^-24   
+    return (float)((4.0 * dim + 3232.0) * std::ldexp(1.0, -24));
+}
+
+static int free_corpus_buffers(pbx_corpus* c) {
+    cudaFree(c->d_rows); cudaFree(c->d_inv); cudaFree(c->d_ids);
+    c->d_rows = nullptr; c->d_inv = nullptr; c->d_ids = nullptr;
+    c->capacity = 0;
+    return PBX_OK;
+}
+
+// (re)allocates row storage for at least `rows` rows, keeping the committed prefix.  Caller holds mu.
+static int reserve_rows(pbx_corpus* c, uint64_t rows) {
+    if (rows <= c->capacity) return PBX_OK;
+    if (rows > PBX_MAX_ROWS) return fail(PBX_E_CAPACITY, "shard would hold %llu rows (max %llu)", (unsigned long long)rows, (unsigned long long)PBX_MAX_ROWS);
+    uint64_t want = std::max<uint64_t>(rows, c->capacity + c->capacity / 2);
+    want = (want + kTileRows - 1) / kTileRows * kTileRows;
+    uint8_t* nr = nullptr; float* ni = nullptr; int64_t* nid = nullptr;
+    cudaError_t e = cudaMalloc(&nr, want * c->pitch);
+    if (e == cudaSuccess) e = cudaMalloc(&ni, want * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&nid, want * sizeof(int64_t));
+    if (e != cudaSuccess && want > rows) {          // retry without growth head-room
+        cudaFree(nr); cudaFree(ni); cudaFree(nid); nr = nullptr; ni = nullptr; nid = nullptr;
+        cudaGetLastError();
+        want = (rows + kTileRows - 1) / kTileRows * kTileRows;
+        e = cudaMalloc(&nr, want * c->pitch);
+        if (e == cudaSuccess) e = cudaMalloc(&ni, want * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&nid, want * sizeof(int64_t));
+    }
+    if (e != cudaSuccess) {
+        cudaFree(nr); cudaFree(ni); cudaFree(nid);
+        cudaGetLastError();
+        return fail(PBX_E_OOM, "cannot allocate %llu rows x %u bytes on device %d: %s", (unsigned long long)want, c->pitch, c->device, cudaGetErrorString(e));
+    }
+    const uint64_t n = c->n.load();
+    CU_TRY(cudaDeviceSynchronize());                // nothing may still read the old buffers
+    if (n) {
+        CU_TRY(cudaMemcpyAsync(nr, c->d_rows, n * c->pitch, cudaMemcpyDeviceToDevice, c->stream));
+        CU_TRY(cudaMemcpyAsync(ni, c->d_inv, n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+        CU_TRY(cudaMemcpyAsync(nid, c->d_ids, n * sizeof(int64_t), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    // rows beyond the committed prefix are read (and ignored) by whole-tile loads: keep them defined
+    CU_TRY(cudaMemsetAsync(nr + n * c->pitch, 0, (want - n) * c->pitch, c->stream));
+    CU_TRY(cudaMemsetAsync(ni + n, 0, (want - n) * sizeof(float), c->stream));
+    CU_TRY(cudaMemsetAsync(nid + n, 0, (want - n) * sizeof(int64_t), c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_rows); cudaFree(c->d_inv); cudaFree(c->d_ids);
+    c->d_rows = nr; c->d_inv = ni; c->d_ids = nid;
+    c->capacity = want;
+    return PBX_OK;
+}
+
+static int ensure_query_scratch(pbx_corpus* c, uint32_t nq) {
+    if (nq <= c->max_nq) return PBX_OK;
+    CU_TRY(cudaDeviceSynchronize());
+    cudaFree(c->d_queries); cudaFree(c->d_q16); cudaFree(c->d_qbytes); cudaFree(c->d_qh); cudaFree(c->d_status);
+    c->d_queries = nullptr; c->d_q16 = nullptr; c->d_qbytes = nullptr; c->d_qh = nullptr; c->d_status = nullptr;
+    c->max_nq = 0;
+    uint32_t want = std::max<uint32_t>(nq, 64u);
+    CU_TRY(cudaMalloc(&c->d_queries, (size_t)want * c->dim));
+    CU_TRY(cudaMalloc(&c->d_q16, (size_t)want * c->pitch * sizeof(int16_t)));
+    CU_TRY(cudaMalloc(&c->d_qbytes, (size_t)want * c->pitch));
+    CU_TRY(cudaMalloc(&c->d_qh, (size_t)want * sizeof(QueryHeader)));
+    CU_TRY(cudaMalloc(&c->d_status, (size_t)want * sizeof(SearchStatus)));
+    c->max_nq = want;
+    return PBX_OK;
+}
+
+static int ensure_hits(pbx_corpus* c, size_t n_hits, uint32_t nq) {
+    if (n_hits > c->hits_cap) {
+        CU_TRY(cudaDeviceSynchronize());
+        cudaFree(c->d_hits); c->d_hits = nullptr; c->hits_cap = 0;
+        cudaFree(c->d_counts); c->d_counts = nullptr;
+        CU_TRY(cudaMalloc(&c->d_hits, n_hits * sizeof(pbx_hit)));
+        CU_TRY(cudaMalloc(&c->d_counts, std::max<size_t>(n_hits, 1024) * sizeof(uint32_t)));
+        c->hits_cap = n_hits;
+    }
+    if (n_hits > c->h_hits_cap) {
+        cudaFreeHost(c->h_hits); cudaFreeHost(c->h_counts);
+        c->h_hits = nullptr; c->h_counts = nullptr; c->h_hits_cap = 0;
+        CU_TRY(cudaMallocHost(&c->h_hits, n_hits * sizeof(pbx_hit)));
+        CU_TRY(cudaMallocHost(&c->h_counts, std::max<size_t>(n_hits, 1024) * sizeof(uint32_t)));
+        c->h_hits_cap = n_hits;
+    }
+    (void)nq;
+    return PBX_OK;
+}
+
+static int ensure_cand(pbx_corpus* c, size_t bytes) {
+    if (bytes <= c->cand_bytes) return PBX_OK;
+    CU_TRY(cudaDeviceSynchronize());
+    cudaFree(c->d_cand); c->d_cand = nullptr; c->cand_bytes = 0;
+    CU_TRY(cudaMalloc(&c->d_cand, bytes));
+    c->cand_bytes = bytes;
+    return PBX_OK;
+}
+
+extern "C" int pbx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ok++;
+    }
+    return ok;
+}
+
+extern "C" const char* pbx_last_error(void) { return g_err; }
+extern "C" const char* pbx_version(void) { return "pixelbox_b200 0.1.0 (sm_100a)"; }
+
+extern "C" int pbx_corpus_create(uint32_t dim, uint64_t capacity_hint, int device, pbx_corpus** out) {
+    if (!out) return fail(PBX_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (dim == 0 || dim > PBX_MAX_DIM) return fail(PBX_E_DIM, "dim %u outside [1, %u]", dim, PBX_MAX_DIM);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(PBX_E_NO_DEVICE, "no CUDA device visible: pixelbox_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(PBX_E_INVALID, "device %d out of range (have %d)", device, ndev);
+    int major = 0, minor = 0;
+    CU_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    CU_TRY(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+    if (major != 10) return fail(PBX_E_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, major, minor);
+    CU_TRY(cudaSetDevice(device));
+    pbx_corpus* c = new (std::nothrow) pbx_corpus();
+    if (!c) return fail(PBX_E_OOM, "host allocation failed");
+    c->device = device;
+    c->dim = dim;
+    c->pitch = (dim + 15u) & ~15u;
+    c->pitch16 = c->pitch / 16u;
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_chain, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev_t0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev_t1);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev_s0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev_s1);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_cand_cnt, kMaxScanGrid * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_tile_counter, 256);
+    if (e == cudaSuccess) e = cudaMemset(c->d_tile_counter, 0, 256);
+    if (e == cudaSuccess) { c->d_exact_passes = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(c->d_tile_counter) + 128); }
+    if (e != cudaSuccess) {
+        int rc = fail(PBX_E_CUDA, "corpus setup failed: %s", cudaGetErrorString(e));
+        pbx_corpus_destroy(c);
+        return rc;
+    }
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        int rc = reserve_rows(c, std::max<uint64_t>(capacity_hint, 1));
+        if (rc != PBX_OK) { pbx_corpus_destroy(c); return rc; }
+    }
+    *out = c;
+    return PBX_OK;
+}
+
+extern "C" void pbx_corpus_destroy(pbx_corpus* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    free_corpus_buffers(c);
+    cudaFree(c->d_queries); cudaFree(c->d_q16); cudaFree(c->d_qbytes); cudaFree(c->d_qh); cudaFree(c->d_status);
+    cudaFree(c->d_hits); cudaFree(c->d_counts); cudaFree(c->d_cand); cudaFree(c->d_cand_cnt); cudaFree(c->d_tile_counter);
+    cudaFreeHost(c->h_queries); cudaFreeHost(c->h_hits); cudaFreeHost(c->h_counts); cudaFreeHost(c->h_stage);
+    if (c->ev_chain) cudaEventDestroy(c->ev_chain);
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+    if (c->ev_s0) cudaEventDestroy(c->ev_s0);
+    if (c->ev_s1) cudaEventDestroy(c->ev_s1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    cudaGetLastError();
+    delete c;
+}
+
+extern "C" int pbx_corpus_size(const pbx_corpus* c, uint64_t* n_rows) {
+    if (!c || !n_rows) return fail(PBX_E_INVALID, "NULL argument");
+    *n_rows = c->n.load();
+    return PBX_OK;
+}
+extern "C" int pbx_corpus_dim(const pbx_corpus* c, uint32_t* dim) {
+    if (!c || !dim) return fail(PBX_E_INVALID, "NULL argument");
+    *dim = c->dim;
+    return PBX_OK;
+}
+
+// copies n host rows to device rows [at, at+n) through pinned staging and computes their metadata
+static int upload_rows(pbx_corpus* c, uint64_t at, const int64_t* ids, const uint8_t* hashes, uint64_t n) {
+    const size_t stage_rows = std::max<size_t>(1, (size_t)(8u << 20) / c->pitch);
+    const size_t per_row = (size_t)c->pitch + sizeof(int64_t);
+    if (c->h_stage_cap < stage_rows * per_row * 2) {
+        cudaFreeHost(c->h_stage); c->h_stage = nullptr; c->h_stage_cap = 0;
+        CU_TRY(cudaMallocHost(&c->h_stage, stage_rows * per_row * 2));
+        c->h_stage_cap = stage_rows * per_row * 2;
+    }
+    cudaEvent_t done[2];
+    CU_TRY(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
+    int rc = PBX_OK;
+    uint64_t off = 0;
+    int slot = 0;
+    bool used[2] = {false, false};
+    while (off < n && rc == PBX_OK) {
+        const uint64_t m = std::min<uint64_t>(stage_rows, n - off);
+        uint8_t* hs = c->h_stage + (size_t)slot * stage_rows * per_row;
+        int64_t* hid = reinterpret_cast<int64_t*>(hs + stage_rows * c->pitch);
+        if (used[slot]) cudaEventSynchronize(done[slot]);
+        if (c->pitch == c->dim) {
+            memcpy(hs, hashes + off * c->dim, m * c->dim);
+        } else {
+            memset(hs, 0, m * c->pitch);
+            for (uint64_t r = 0; r < m; ++r) memcpy(hs + r * c->pitch, hashes + (off + r) * c->dim, c->dim);
+        }
+        memcpy(hid, ids + off, m * sizeof(int64_t));
+        cudaError_t e = cudaMemcpyAsync(c->d_rows + (at + off) * c->pitch, hs, m * c->pitch, cudaMemcpyHostToDevice, c->copy_stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_ids + at + off, hid, m * sizeof(int64_t), cudaMemcpyHostToDevice, c->copy_stream);
+        if (e == cudaSuccess) {
+            const unsigned warps_per_block = 8;
+            const unsigned blocks = (unsigned)((m + warps_per_block - 1) / warps_per_block);
+            row_meta_kernel<<<blocks, warps_per_block * 32, 0, c->copy_stream>>>(reinterpret_cast<const uint4*>(c->d_rows), c->pitch16, c->dim,
+                                                                                at + off, m, c->d_inv);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(done[slot], c->copy_stream);
+        if (e != cudaSuccess) rc = fail(PBX_E_CUDA, "row upload failed: %s", cudaGetErrorString(e));
+        used[slot] = true;
+        slot ^= 1;
+        off += m;
+    }
+    cudaError_t e = cudaStreamSynchronize(c->copy_stream);
+    if (rc == PBX_OK && e != cudaSuccess) rc = fail(PBX_E_CUDA, "row upload failed: %s", cudaGetErrorString(e));
+    cudaEventDestroy(done[0]);
+    cudaEventDestroy(done[1]);
+    return rc;
+}
+
+extern "C" int pbx_corpus_append(pbx_corpus* c, const int64_t* image_ids, const uint8_t* hashes, uint64_t n) {
+    if (!c) return fail(PBX_E_INVALID, "corpus is NULL");
+    if (n == 0) return PBX_OK;
+    if (!image_ids || !hashes) return fail(PBX_E_INVALID, "NULL ids or hashes with n > 0");
+    std::lock_guard<std::mutex> alk(c->append_mu);
+    CU_TRY(cudaSetDevice(c->device));
+    const uint64_t at = c->n.load();
+    if (at + n > c->capacity) {
+        std::lock_guard<std::mutex> lk(c->mu);      // growth moves the buffers: no search may be running
+        int rc = reserve_rows(c, at + n);
+        if (rc != PBX_OK) return rc;
+    }
+    // rows beyond the committed prefix are invisible to concurrent searches until n is published
+    int rc = upload_rows(c, at, image_ids, hashes, n);
+    if (rc != PBX_OK) return rc;
+    c->n.store(at + n);
+    return PBX_OK;
+}
+
+extern "C" int pbx_corpus_load(pbx_corpus* c, const int64_t* image_ids, const uint8_t* hashes, uint64_t n) {
+    if (!c) return fail(PBX_E_INVALID, "corpus is NULL");
+    if (n && (!image_ids || !hashes)) return fail(PBX_E_INVALID, "NULL ids or hashes with n > 0");
+    {
+        std::lock_guard<std::mutex> alk(c->append_mu);
+        std::lock_guard<std::mutex> lk(c->mu);
+        CU_TRY(cudaSetDevice(c->device));
+        CU_TRY(cudaDeviceSynchronize());
+        c->n.store(0);
+    }
+    return pbx_corpus_append(c, image_ids, hashes, n);
+}
+
+extern "C" int pbx_corpus_fill_synthetic(pbx_corpus* c, uint64_t n, uint64_t seed, uint64_t first_row) {
+    if (!c) return fail(PBX_E_INVALID, "corpus is NULL");
+    std::lock_guard<std::mutex> alk(c->append_mu);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaDeviceSynchronize());
+    c->n.store(0);
+    int rc = reserve_rows(c, std::max<uint64_t>(n, 1));
+    if (rc != PBX_OK) return rc;
+    if (n == 0) return PBX_OK;
+    const uint64_t step = 1ull << 24;               // rows per launch
+    for (uint64_t off = 0; off < n; off += step) {
+        const uint64_t m = std::min<uint64_t>(step, n - off);
+        synth_fill_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_rows, c->pitch, c->dim, off, m, seed, first_row + off, c->d_ids);
+        const unsigned blocks = (unsigned)((m + 7) / 8);
+        row_meta_kernel<<<blocks, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_rows), c->pitch16, c->dim, off, m, c->d_inv);
+    }
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    c->n.store(n);
+    return PBX_OK;
+}
+
+extern "C" int pbx_corpus_read_rows(const pbx_corpus* cc, uint64_t first, uint64_t n, int64_t* image_ids, uint8_t* hashes) {
+    pbx_corpus* c = const_cast<pbx_corpus*>(cc);
+    if (!c) return fail(PBX_E_INVALID, "corpus is NULL");
+    if (first + n > c->n.load()) return fail(PBX_E_INVALID, "rows [%llu, %llu) outside the corpus", (unsigned long long)first, (unsigned long long)(first + n));
+    if (n == 0) return PBX_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU_TRY(cudaSetDevice(c->device));
+    if (image_ids) CU_TRY(cudaMemcpy(image_ids, c->d_ids + first, n * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (hashes) CU_TRY(cudaMemcpy2D(hashes, c->dim, c->d_rows + first * c->pitch, c->pitch, c->dim, n, cudaMemcpyDeviceToHost));
+    return PBX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// search
+// ------------------------------------------------------------------------------------------------
+__global__ void empty_result_kernel(pbx_hit* hits, uint32_t* counts, uint32_t nq, uint32_t k) {
+    const uint32_t total = nq * k;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        pbx_hit h; h.image_id = INT64_MAX; h.dist = __int_as_float(0x7f800000); h.dot = 0; h.norm2 = 0; h.flags = 0;
+        hits[i] = h;
+    }
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x) counts[i] = 0;
+}
+
+template <bool EXACT>
+static cudaError_t launch_scan(const pbx_corpus* c, const ScanParams& p, int grid, size_t smem, cudaStream_t s) {
+#define PBX_SCAN_CASE(LL, CC)                                                                                   \
+    {                                                                                                           \
+        auto kern = scan_kernel<LL, CC, EXACT>;                                                                 \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        kern<<<grid, kScanThreads, smem, s>>>(p);                                                               \
+        return cudaGetLastError();                                                                              \
+    }
+    switch (c->pitch16) {
+        case 1: PBX_SCAN_CASE(1, 1)
+        case 2: PBX_SCAN_CASE(2, 1)
+        case 4: PBX_SCAN_CASE(4, 1)
+        case 8: PBX_SCAN_CASE(8, 1)
+        case 16: PBX_SCAN_CASE(16, 1)
+        case 32: PBX_SCAN_CASE(32, 1)
+        case 64: PBX_SCAN_CASE(32, 2)
+        case 128: PBX_SCAN_CASE(32, 4)
+        default: {
+            auto kern = scan_generic_kernel<EXACT>;
+            size_t sm = smem + (size_t)c->pitch16 * 32;
+            if (sm > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            kern<<<grid, kScanThreads, sm, s>>>(p);
+            return cudaGetLastError();
+        }
+    }
+#undef PBX_SCAN_CASE
+}
+
+static int scan_grid(const pbx_corpus* c) {
+    uint32_t per_sm = c->ctas_per_sm ? c->ctas_per_sm : ((c->pitch16 >= 16) ? 2u : 4u);
+    int g = c->sm_count * (int)per_sm;
+    return std::min<int>(g, (int)kMaxScanGrid);
+}
+
+// Enqueues the whole search for nq queries already on the device.  Caller holds c->mu.
+static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, uint32_t k, double max_dist, pbx_hit* d_hits,
+                          uint32_t* d_count, cudaStream_t s, bool timed) {
+    const uint32_t n = (uint32_t)c->n.load();
+    if (c->chain_valid) CU_TRY(cudaStreamWaitEvent(s, c->ev_chain, 0));
+    if (timed) CU_TRY(cudaEventRecord(c->ev_t0, s));
+    if (n == 0) {
+        empty_result_kernel<<<64, 256, 0, s>>>(d_hits, d_count, nq, k);
+        CU_TRY(cudaGetLastError());
+    } else {
+        int rc = ensure_query_scratch(c, nq);
+        if (rc != PBX_OK) return rc;
+        const int grid = scan_grid(c);
+        const uint32_t keep = std::min<uint32_t>(default_keep(k, c->slack), 4096u);
+        const uint32_t cap_scan = next_pow2(keep + kTileRows);
+        const uint32_t cap_scan_x = next_pow2(k + kTileRows);
+        const uint32_t cap_merge = next_pow2(keep + kMergeChunk);
+        const uint32_t cap_merge_x = next_pow2(k + kMergeChunk);
+        rc = ensure_cand(c, (size_t)std::max<uint32_t>(keep, k) * grid * sizeof(KeyX));
+        if (rc != PBX_OK) return rc;
+        const float margin = certificate_margin(c->dim);
+        const size_t fin_smem = std::max<size_t>((size_t)cap_merge * sizeof(u64), (size_t)next_pow2(keep) * sizeof(RerankEntry) + (size_t)keep * 12);
+        const size_t finx_smem = (size_t)cap_merge_x * sizeof(KeyX);
+        if (fin_smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+        if (finx_smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(finalize_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)finx_smem));
+
+        prep_query_kernel<<<nq, 256, 0, s>>>(d_queries, c->dim, c->pitch, c->d_q16, c->d_qbytes, c->d_qh);
+        CU_TRY(cudaGetLastError());
+        for (uint32_t q = 0; q < nq; ++q) {
+            ScanParams sp;
+            sp.rows = reinterpret_cast<const uint4*>(c->d_rows);
+            sp.inv_norm = c->d_inv;
+            sp.ids = c->d_ids;
+            sp.n = n;
+            sp.pitch16 = c->pitch16;
+            sp.dim = c->dim;
+            sp.q16 = c->d_q16 + (size_t)q * c->pitch;
+            sp.qbytes = c->d_qbytes + (size_t)q * c->pitch;
+            sp.qh = c->d_qh + q;
+            sp.keep = keep;
+            sp.cap = cap_scan;
+            sp.cand = c->d_cand;
+            sp.cand_cnt = c->d_cand_cnt;
+            sp.tile_counter = c->d_tile_counter;
+            sp.status = c->d_status + q;
+            sp.max_dist = max_dist;
+            const bool time_scan = timed && q + 1 == nq;
+            if (time_scan) CU_TRY(cudaEventRecord(c->ev_s0, s));
+            CU_TRY(launch_scan<false>(c, sp, grid, (size_t)cap_scan * sizeof(u64), s));
+            if (time_scan) CU_TRY(cudaEventRecord(c->ev_s1, s));
+
+            FinalizeParams fp;
+            fp.cand = reinterpret_cast<const u64*>(c->d_cand);
+            fp.cand_cnt = c->d_cand_cnt;
+            fp.grid = (uint32_t)grid;
+            fp.keep = keep;
+            fp.cap = cap_merge;
+            fp.k = k;
+            fp.n = n;
+            fp.dim = c->dim;
+            fp.pitch = c->pitch;
+            fp.rows = c->d_rows;
+            fp.ids = c->d_ids;
+            fp.qbytes = sp.qbytes;
+            fp.qh = c->d_qh + q;
+            fp.max_dist = max_dist;
+            fp.margin = margin;
+            fp.hits = d_hits + (size_t)q * k;
+            fp.count = d_count + q;
+            fp.status = c->d_status + q;
+            fp.tile_counter = c->d_tile_counter;
+            finalize_kernel<<<1, kFinalThreads, fin_smem, s>>>(fp);
+            CU_TRY(cudaGetLastError());
+
+            // exact pass: both kernels return at once unless status->need_exact was raised
+            sp.keep = k;
+            sp.cap = cap_scan_x;
+            CU_TRY(launch_scan<true>(c, sp, grid, (size_t)cap_scan_x * sizeof(KeyX), s));
+            FinalizeExactParams xp;
+            xp.cand = reinterpret_cast<const KeyX*>(c->d_cand);
+            xp.cand_cnt = c->d_cand_cnt;
+            xp.grid = (uint32_t)grid;
+            xp.k = k;
+            xp.cap = cap_merge_x;
+            xp.dim = c->dim;
+            xp.pitch = c->pitch;
+            xp.rows = c->d_rows;
+            xp.qbytes = sp.qbytes;
+            xp.hits = fp.hits;
+            xp.count = fp.count;
+            xp.status = c->d_status + q;
+            xp.tile_counter = c->d_tile_counter;
+            xp.exact_passes = c->d_exact_passes;
+            finalize_exact_kernel<<<1, kFinalThreads, finx_smem, s>>>(xp);
+            CU_TRY(cudaGetLastError());
+        }
+        c->last_grid = grid;
+    }
+    if (timed) CU_TRY(cudaEventRecord(c->ev_t1, s));
+    CU_TRY(cudaEventRecord(c->ev_chain, s));
+    c->chain_valid = true;
+    c->queries += nq;
+    c->last_bytes = (uint64_t)n * c->dim * nq;
+    return PBX_OK;
+}
+
+static int check_search_args(const pbx_corpus* c, const void* queries, uint32_t nq, uint32_t k) {
+    if (!c) return fail(PBX_E_INVALID, "corpus is NULL");
+    if (nq && !queries) return fail(PBX_E_INVALID, "queries is NULL");
+    if (k == 0) return fail(PBX_E_INVALID, "k must be >= 1");
+    if (k > PBX_MAX_K) return fail(PBX_E_K, "k = %u exceeds PBX_MAX_K = %u", k, PBX_MAX_K);
+    return PBX_OK;
+}
+
+extern "C" int pbx_search_device(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, uint32_t k, double max_dist, pbx_hit* d_hits,
+                                 uint32_t* d_count, void* cuda_stream) {
+    int rc = check_search_args(c, d_queries, nq, k);
+    if (rc != PBX_OK) return rc;
+    if (nq == 0) return PBX_OK;
+    if (!d_hits || !d_count) return fail(PBX_E_INVALID, "NULL output");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->stream;
+    return enqueue_search(c, d_queries, nq, k, max_dist, d_hits, d_count, s, false);
+}
+
+extern "C" int pbx_search_hits(pbx_corpus* c, const uint8_t* queries, uint32_t nq, uint32_t k, double max_dist, pbx_hit* out_hits,
+                               uint32_t* out_count) {
+    int rc = check_search_args(c, queries, nq, k);
+    if (rc != PBX_OK) return rc;
+    if (nq == 0) return PBX_OK;
+    if (!out_hits || !out_count) return fail(PBX_E_INVALID, "NULL output");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU_TRY(cudaSetDevice(c->device));
+    const uint32_t batch_max = 1024;
+    float total_ms = 0.f;
+    uint64_t total_bytes = 0;
+    for (uint32_t q0 = 0; q0 < nq; q0 += batch_max) {
+        const uint32_t b = std::min<uint32_t>(batch_max, nq - q0);
+        rc = ensure_query_scratch(c, b);
+        if (rc != PBX_OK) return rc;
+        rc = ensure_hits(c, (size_t)b * k, b);
+        if (rc != PBX_OK) return rc;
+        const size_t qbytes = (size_t)b * c->dim;
+        if (qbytes > c->h_queries_cap) {
+            cudaFreeHost(c->h_queries); c->h_queries = nullptr; c->h_queries_cap = 0;
+            CU_TRY(cudaMallocHost(&c->h_queries, std::max<size_t>(qbytes, 64 * 1024)));
+            c->h_queries_cap = std::max<size_t>(qbytes, 64 * 1024);
+        }
+        memcpy(c->h_queries, queries + (size_t)q0 * c->dim, qbytes);
+        CU_TRY(cudaMemcpyAsync(c->d_queries, c->h_queries, qbytes, cudaMemcpyHostToDevice, c->stream));
+        rc = enqueue_search(c, c->d_queries, b, k, max_dist, c->d_hits, c->d_counts, c->stream, true);
+        if (rc != PBX_OK) return rc;
+        CU_TRY(cudaMemcpyAsync(c->h_hits, c->d_hits, (size_t)b * k * sizeof(pbx_hit), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaMemcpyAsync(c->h_counts, c->d_counts, (size_t)b * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1) == cudaSuccess) total_ms += ms;
+        if (c->n.load() == 0 || cudaEventElapsedTime(&c->last_scan_ms, c->ev_s0, c->ev_s1) != cudaSuccess) { c->last_scan_ms = 0.f; cudaGetLastError(); }
+        total_bytes += c->last_bytes;
+        memcpy(out_hits + (size_t)q0 * k, c->h_hits, (size_t)b * k * sizeof(pbx_hit));
+        memcpy(out_count + q0, c->h_counts, (size_t)b * sizeof(uint32_t));
+    }
+    c->last_search_ms = total_ms;
+    c->last_bytes = total_bytes;
+    return PBX_OK;
+}
+
+extern "C" int pbx_search(pbx_corpus* c, const uint8_t* queries, uint32_t nq, uint32_t k, double max_dist, int64_t* out_ids,
+                          float* out_dist, int32_t* out_dot, int32_t* out_norm2, uint32_t* out_count) {
+    int rc = check_search_args(c, queries, nq, k);
+    if (rc != PBX_OK) return rc;
+    if (nq == 0) return PBX_OK;
+    if (!out_ids || !out_count) return fail(PBX_E_INVALID, "NULL output");
+    std::vector<pbx_hit> hits;
+    try { hits.resize((size_t)nq * k); } catch (...) { return fail(PBX_E_OOM, "host allocation failed"); }
+    rc = pbx_search_hits(c, queries, nq, k, max_dist, hits.data(), out_count);
+    if (rc != PBX_OK) return rc;
+    for (size_t i = 0; i < hits.size(); ++i) {
+        const bool valid = (i % k) < out_count[i / k];
+        out_ids[i] = valid ? hits[i].image_id : 0;
+        if (out_dist) out_dist[i] = valid ? hits[i].dist : 0.f;
+        if (out_dot) out_dot[i] = valid ? hits[i].dot : 0;
+        if (out_norm2) out_norm2[i] = valid ? hits[i].norm2 : 0;
+    }
+    return PBX_OK;
+}
+
+extern "C" int pbx_merge_hits(const pbx_hit* gathered, const uint32_t* counts, uint32_t n_shards, uint32_t nq, uint32_t k,
+                              pbx_hit* out_hits, uint32_t* out_count) {
+    if (!gathered || !counts || !out_hits || !out_count) return fail(PBX_E_INVALID, "NULL argument");
+    if (k == 0 || n_shards == 0) return fail(PBX_E_INVALID, "k and n_shards must be >= 1");
+    std::vector<uint32_t> head;
+    try { head.resize(n_shards); } catch (...) { return fail(PBX_E_OOM, "host allocation failed"); }
+    for (uint32_t q = 0; q < nq; ++q) {
+        std::fill(head.begin(), head.end(), 0u);
+        uint32_t out = 0;
+        while (out < k) {
+            int best = -1;
+            const pbx_hit* bh = nullptr;
+            for (uint32_t s = 0; s < n_shards; ++s) {
+                const uint32_t cnt = std::min<uint32_t>(counts[(size_t)s * nq + q], k);
+                if (head[s] >= cnt) continue;
+                const pbx_hit* h = gathered + ((size_t)s * nq + q) * k + head[s];
+                // (dist as f64, image_id) ascending: the ORDER BY of src/engine.rs:380 with ties by id
+                if (!bh || (double)h->dist < (double)bh->dist || ((double)h->dist == (double)bh->dist && h->image_id < bh->image_id)) {
+                    bh = h;
+                    best = (int)s;
+                }
+            }
+            if (best < 0) break;
+            out_hits[(size_t)q * k + out++] = *bh;
+            head[best]++;
+        }
+        out_count[q] = out;
+        for (uint32_t i = out; i < k; ++i) {
+            pbx_hit h; h.image_id = INT64_MAX; h.dist = std::numeric_limits<float>::infinity(); h.dot = 0; h.norm2 = 0; h.flags = 0;
+            out_hits[(size_t)q * k + i] = h;
+        }
+    }
+    return PBX_OK;
+}
+
+extern "C" int pbx_merge_hits_device(int device, const pbx_hit* d_gathered, const uint32_t* d_counts, uint32_t n_shards, uint32_t nq,
+                                     uint32_t k, pbx_hit* d_out_hits, uint32_t* d_out_count, void* cuda_stream) {
+    if (!d_gathered || !d_counts || !d_out_hits || !d_out_count) return fail(PBX_E_INVALID, "NULL argument");
+    if (k == 0 || n_shards == 0) return fail(PBX_E_INVALID, "k and n_shards must be >= 1");
+    if (nq == 0) return PBX_OK;
+    CU_TRY(cudaSetDevice(device));
+    merge_hits_kernel<<<nq, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(d_gathered, d_counts, n_shards, nq, k, d_out_hits, d_out_count);
+    CU_TRY(cudaGetLastError());
+    return PBX_OK;
+}
+
+extern "C" int pbx_cosine_distance_pairs(int device, const uint8_t* a, const uint8_t* b, uint64_t n, uint32_t dim, float* out_dist,
+                                         int32_t* out_dot, int32_t* out_norm2_a, int32_t* out_norm2_b) {
+    if (dim == 0 || dim > PBX_MAX_DIM) return fail(PBX_E_DIM, "dim %u outside [1, %u]", dim, PBX_MAX_DIM);
+    if (n == 0) return PBX_OK;
+    if (!a || !b || !out_dist) return fail(PBX_E_INVALID, "NULL argument");
+    if (pbx_device_count() == 0) return fail(PBX_E_NO_DEVICE, "no sm_100 device: pixelbox_b200 has no CPU fallback");
+    CU_TRY(cudaSetDevice(device));
+    uint8_t *da = nullptr, *db = nullptr;
+    float* dd = nullptr;
+    int* di = nullptr;
+    int rc = PBX_OK;
+    cudaError_t e = cudaMalloc(&da, n * dim);
+    if (e == cudaSuccess) e = cudaMalloc(&db, n * dim);
+    if (e == cudaSuccess) e = cudaMalloc(&dd, n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&di, 3 * n * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(da, a, n * dim, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(db, b, n * dim, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        pair_distance_kernel<<<(unsigned)((n + 127) / 128), 128>>>(da, db, n, dim, dd, di, di + n, di + 2 * n);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out_dist, dd, n * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && out_dot) e = cudaMemcpy(out_dot, di, n * sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && out_norm2_a) e = cudaMemcpy(out_norm2_a, di + n, n * sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && out_norm2_b) e = cudaMemcpy(out_norm2_b, di + 2 * n, n * sizeof(int), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(e == cudaErrorMemoryAllocation ? PBX_E_OOM : PBX_E_CUDA, "pair distance failed: %s", cudaGetErrorString(e));
+    cudaFree(da); cudaFree(db); cudaFree(dd); cudaFree(di);
+    return rc;
+}
+
+extern "C" int pbx_get_stats(const pbx_corpus* cc, pbx_stats* out) {
+    pbx_corpus* c = const_cast<pbx_corpus*>(cc);
+    if (!c || !out) return fail(PBX_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    memset(out, 0, sizeof(*out));
+    out->rows = c->n.load();
+    out->capacity_rows = c->capacity;
+    out->dim = c->dim;
+    out->row_pitch = c->pitch;
+    out->queries = c->queries;
+    unsigned long long xp = 0;
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaMemcpy(&xp, c->d_exact_passes, sizeof(xp), cudaMemcpyDeviceToHost));
+    out->exact_passes = xp;
+    out->last_search_ms = c->last_search_ms;
+    out->last_scan_ms = c->last_scan_ms;
+    out->last_bytes_scanned = c->last_bytes;
+    out->device = c->device;
+    out->sm_count = c->sm_count;
+    out->scan_grid = c->last_grid ? c->last_grid : scan_grid(c);
+    return PBX_OK;
+}
+
+extern "C" int pbx_set_candidate_slack(pbx_corpus* c, uint32_t slack) {
+    if (!c) return fail(PBX_E_INVALID, "corpus is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->slack = slack;
+    return PBX_OK;
+}
+
+extern "C" int pbx_set_scan_ctas_per_sm(pbx_corpus* c, uint32_t ctas_per_sm) {
+    if (!c) return fail(PBX_E_INVALID, "corpus is NULL");
+    if (ctas_per_sm > 8) return fail(PBX_E_INVALID, "ctas_per_sm must be <= 8");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->ctas_per_sm = ctas_per_sm;
+    return PBX_OK;
+}

@@ -1,0 +1,443 @@
+// finalize.cuh -- everything around the scan: query preparation, the merge of the per-CTA
+// candidate lists, kernel C (bit-exact f32 replay of the reference distance on the candidates,
+// ordering by (dist, image_id), the `dist < max_dist` filter, LIMIT k) and the certificate that
+// decides whether the exact pass must run.  Reference: src/engine.rs:375-383 (filter / order /
+// limit), :572-588 (distance), :608-622 (f32 -> f64 widening before the comparison).
+#pragma once
+#include "scan.cuh"
+#include "../../include/pixelbox_b200.h"
+
+namespace pbx {
+
+// ---- query preparation: one CTA per query -----------------------------------------------------
+// Writes the centred 16-bit query (zero in the row padding), a padded byte copy and the header.
+__global__ void prep_query_kernel(const uint8_t* __restrict__ queries, uint32_t dim, uint32_t pitch,
+                                  int16_t* __restrict__ q16, uint8_t* __restrict__ qbytes, QueryHeader* __restrict__ qh) {
+    const uint32_t qi = blockIdx.x;
+    const uint8_t* src = queries + (size_t)qi * dim;
+    int16_t* d16 = q16 + (size_t)qi * pitch;
+    uint8_t* db = qbytes + (size_t)qi * pitch;
+    int s = 0, n2 = 0;
+    for (uint32_t i = threadIdx.x; i < pitch; i += blockDim.x) {
+        if (i < dim) {
+            uint32_t v = src[i];
+            int c = centre(v);
+            d16[i] = (int16_t)c;
+            db[i] = (uint8_t)v;
+            s += c;
+            n2 += c * c;
+        } else {
+            d16[i] = 0;
+            db[i] = 0;
+        }
+    }
+    __shared__ int ss[32], sn[32];
+    for (int off = 16; off; off >>= 1) { s += __shfl_xor_sync(~0u, s, off); n2 += __shfl_xor_sync(~0u, n2, off); }
+    if ((threadIdx.x & 31) == 0) { ss[threadIdx.x >> 5] = s; sn[threadIdx.x >> 5] = n2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int S = 0, N = 0;
+        for (uint32_t w = 0; w < (blockDim.x + 31) / 32; ++w) { S += ss[w]; N += sn[w]; }
+        QueryHeader h;
+        h.sum_cq = S;
+        h.norm2_q = N;
+        h.inv_q = (float)(1.0 / sqrt((double)N));
+        h.sa = 0.0f;
+        qh[qi] = h;
+    }
+}
+
+// ---- per-row metadata: inv_norm[r] = 1/sqrt(sum c(r_i)^2), one warp per row ----------------------
+__global__ void row_meta_kernel(const uint4* __restrict__ rows, uint32_t pitch16, uint32_t dim, uint64_t first, uint64_t n,
+                                float* __restrict__ inv_norm) {
+    const uint64_t r = first + (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= first + n) return;
+    unsigned s1 = 0, s2 = 0;
+    for (uint32_t c = lane; c < pitch16; c += 32) {
+        uint4 v = __ldg(rows + r * pitch16 + c);
+        s1 = dp4a_uu(v.x, 0x01010101u, s1); s1 = dp4a_uu(v.y, 0x01010101u, s1);
+        s1 = dp4a_uu(v.z, 0x01010101u, s1); s1 = dp4a_uu(v.w, 0x01010101u, s1);
+        s2 = dp4a_uu(v.x, v.x, s2); s2 = dp4a_uu(v.y, v.y, s2);
+        s2 = dp4a_uu(v.z, v.z, s2); s2 = dp4a_uu(v.w, v.w, s2);
+    }
+    for (int off = 16; off; off >>= 1) { s1 += __shfl_xor_sync(~0u, s1, off); s2 += __shfl_xor_sync(~0u, s2, off); }
+    if (lane == 0) {
+        // sum (2v-255)^2 = 4 sum v^2 - 1020 sum v + 65025 d   (padding bytes are zero and excluded through d)
+        long long n2 = 4ll * s2 - 1020ll * s1 + 65025ll * dim;
+        inv_norm[r] = (float)(1.0 / sqrt((double)n2));
+    }
+}
+
+// ---- synthetic corpus (bench/tests): same function as pixelbox_b200/synth.py ---------------------
+__device__ __forceinline__ u64 splitmix64(u64 z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void synth_fill_kernel(uint8_t* __restrict__ rows, uint32_t pitch, uint32_t dim, uint64_t dst_row0, uint64_t n,
+                                  u64 seed, u64 first_row, int64_t* __restrict__ ids) {
+    const uint32_t chunks = pitch / 8;       // pitch is a multiple of 16
+    const u64 total = n * chunks;
+    for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (u64)gridDim.x * blockDim.x) {
+        const u64 r = t / chunks;
+        const uint32_t c = (uint32_t)(t % chunks);
+        const u64 grow = first_row + r;
+        const u64 rk = splitmix64(seed ^ (grow * 0xD1342543DE82EF95ull));
+        u64 x = splitmix64(rk + c);
+        const uint32_t b0 = c * 8;
+        if (b0 >= dim) x = 0;
+        else if (b0 + 8 > dim) x &= (~0ull) >> (8 * (b0 + 8 - dim));
+        *reinterpret_cast<u64*>(rows + (dst_row0 + r) * pitch + b0) = x;
+        if (c == 0) ids[dst_row0 + r] = (int64_t)(grow + 1);
+    }
+}
+
+// ---- merge + kernel C ----------------------------------------------------------------------------
+struct FinalizeParams {
+    const u64* cand;            // [keep][grid] rank-major, each CTA list sorted best first
+    const uint32_t* cand_cnt;   // [grid]
+    uint32_t grid;              // scan CTAs
+    uint32_t keep;              // k + slack
+    uint32_t cap;               // merge buffer capacity: power of two >= keep + kMergeChunk
+    uint32_t k;
+    uint32_t n;                 // rows searched
+    uint32_t dim;
+    uint32_t pitch;             // bytes
+    const uint8_t* rows;
+    const int64_t* ids;
+    const uint8_t* qbytes;      // this query, padded
+    QueryHeader* qh;            // sa is filled in here
+    double max_dist;
+    float margin;               // certificate margin on kappa
+    pbx_hit* hits;              // [k] this query
+    uint32_t* count;            // this query
+    SearchStatus* status;       // this query
+    uint32_t* tile_counter;     // reset for the next scan
+};
+
+struct RerankEntry {            // sort record of kernel C: (ord(dist), image_id) ascending
+    uint32_t od;
+    uint32_t slot;
+    int64_t id;
+};
+__device__ __forceinline__ bool rerank_before(const RerankEntry& a, const RerankEntry& b) {
+    if (a.od != b.od) return a.od < b.od;
+    if (a.id != b.id) return a.id < b.id;
+    return a.slot < b.slot;
+}
+__device__ void block_sort_rerank(RerankEntry* e, uint32_t n2) {
+    for (uint32_t k = 2; k <= n2; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+                uint32_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;
+                bool asc = (lo & k) == 0;
+                RerankEntry a = e[lo], b = e[hi];
+                if (rerank_before(b, a) == asc) { e[lo] = b; e[hi] = a; }
+            }
+            __syncthreads();
+        }
+}
+
+// shared memory layout (dynamic): [cap] u64 merge buffer, later reused:
+//   RerankEntry ent[n2] | int dots[keep] | int norms[keep] | float dists[keep]
+__global__ void __launch_bounds__(kFinalThreads, 1)
+finalize_kernel(const FinalizeParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64* buf = reinterpret_cast<u64*>(smem_raw);
+    __shared__ uint32_t s_cnt, s_pushed, s_maxcnt, s_nonplateau;
+    __shared__ u64 s_tau;
+    __shared__ float s_lut[256];
+    __shared__ float s_kappa_k, s_kappa_last;
+    __shared__ uint32_t s_listcnt[kMaxScanGrid];
+
+    if (threadIdx.x < 256) s_lut[threadIdx.x] = ref_decode(threadIdx.x);
+    if (threadIdx.x == 0) { s_cnt = 0; s_tau = 0ull; s_maxcnt = 0; s_nonplateau = 0; s_pushed = 0; }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < p.grid; b += blockDim.x) {
+        uint32_t c = p.cand_cnt[b];
+        s_listcnt[b] = c;
+        atomicMax(&s_maxcnt, c);
+    }
+    __syncthreads();
+
+    // ---- merge: best `keep` of the union of the CTA lists.  Elements are visited rank-major, so
+    // the strongest entries of every list come first and the threshold tightens immediately.
+    TopBuf<u64> tb{buf, &s_cnt, &s_tau, p.cap, p.keep};
+    const uint32_t total = s_maxcnt * p.grid;
+    for (uint32_t base = 0; base < total; base += kMergeChunk) {
+        if (s_cnt + kMergeChunk > p.cap) tb.compact();      // uniform (read after a barrier)
+        const u64 tau = s_tau;
+        __syncthreads();
+        if (threadIdx.x == 0) s_pushed = 0;
+        __syncthreads();
+        bool any = false;
+#pragma unroll
+        for (int x = 0; x < kMergeChunk / kFinalThreads; ++x) {
+            const uint32_t e = base + x * kFinalThreads + threadIdx.x;
+            bool pass = false;
+            u64 key = 0;
+            if (e < total) {
+                const uint32_t rank = e / p.grid, b = e - rank * p.grid;
+                if (rank < s_listcnt[b]) { key = p.cand[e]; pass = key > tau; }
+            }
+            tb.push_warp(pass, key);
+            any |= pass;
+        }
+        if (any) s_pushed = 1;
+        __syncthreads();
+        // lists are sorted: a chunk that spans at least one complete rank and pushed nothing
+        // proves every remaining element is below the threshold
+        if (s_pushed == 0 && kMergeChunk >= 2 * p.grid && s_cnt >= p.keep) break;
+    }
+    __syncthreads();
+    tb.compact();
+    const uint32_t nc = s_cnt < p.keep ? s_cnt : p.keep;     // candidates, sorted by (kappa desc, row asc)
+    if (threadIdx.x == 0) {
+        s_kappa_k = (nc >= p.k && p.k > 0) ? key64_kappa(buf[p.k - 1]) : 0.0f;
+        s_kappa_last = nc > 0 ? key64_kappa(buf[nc - 1]) : 0.0f;
+    }
+    __syncthreads();
+
+    // ---- kernel C: replay the reference arithmetic on the candidates -----------------------------
+    // candidate rows move to registers before the buffer is reused
+    uint32_t my_rows[4];
+    const uint32_t per = (nc + kFinalThreads - 1) / kFinalThreads;     // <= 4 for keep <= 4096
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+        uint32_t c = threadIdx.x + x * kFinalThreads;
+        my_rows[x] = (c < nc) ? key64_row(buf[c]) : 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    const uint32_t n2 = next_pow2(nc < 2 ? 2 : nc);
+    RerankEntry* ent = reinterpret_cast<RerankEntry*>(smem_raw);
+    int* dots = reinterpret_cast<int*>(smem_raw + (size_t)n2 * sizeof(RerankEntry));
+    int* norms = dots + p.keep;
+    float* dists = reinterpret_cast<float*>(norms + p.keep);
+
+    // the query's own norm fold (engine.rs:580) by the last thread, which rarely owns a candidate
+    if (threadIdx.x == kFinalThreads - 1) {
+        float sa = 0.0f;
+        for (uint32_t i = 0; i < p.dim; ++i) { float a = s_lut[p.qbytes[i]]; sa = ref_fold(sa, a, a); }
+        p.qh->sa = sa;
+    }
+    float my_sb[4], my_dot[4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+        if (x < (int)per && my_rows[x] != 0xFFFFFFFFu) {
+            int idot, inorm;
+            replay_row(p.rows + (size_t)my_rows[x] * p.pitch, p.qbytes, p.dim, s_lut, my_sb[x], my_dot[x], idot, inorm);
+            uint32_t c = threadIdx.x + x * kFinalThreads;
+            dots[c] = idot;
+            norms[c] = inorm;
+        }
+    }
+    __threadfence_block();
+    __syncthreads();
+    const float sa = p.qh->sa;
+    uint32_t nonplateau = 0;
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+        uint32_t c = threadIdx.x + x * kFinalThreads;
+        if (x < (int)per && my_rows[x] != 0xFFFFFFFFu) {
+            float dist = ref_distance(sa, my_sb[x], my_dot[x]);
+            dists[c] = dist;
+            RerankEntry e;
+            e.od = ord_f32(dist);
+            e.slot = c;
+            e.id = p.ids[my_rows[x]];
+            ent[c] = e;
+            if (dist < PBX_PLATEAU_DIST) nonplateau++;
+        }
+    }
+    for (uint32_t c = nc + threadIdx.x; c < n2; c += blockDim.x) {
+        RerankEntry e; e.od = 0xFFFFFFFFu; e.slot = 0xFFFFFFFFu; e.id = INT64_MAX;
+        ent[c] = e;
+    }
+    if (nonplateau) atomicAdd(&s_nonplateau, nonplateau);
+    __syncthreads();
+    block_sort_rerank(ent, n2);
+
+    // ---- WHERE dist < ? ORDER BY dist ASC LIMIT k  (engine.rs:379-381) ----------------------------
+    // ascending order makes the passing rows a prefix
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    uint32_t local = 0;
+    for (uint32_t c = threadIdx.x; c < nc; c += blockDim.x) {
+        const RerankEntry e = ent[c];
+        const float dist = dists[e.slot];
+        const bool ok = (double)dist < p.max_dist;
+        if (ok) local++;
+        if (c < p.k) {
+            pbx_hit h;
+            if (ok) { h.image_id = e.id; h.dist = dist; h.dot = dots[e.slot]; h.norm2 = norms[e.slot]; h.flags = 0; }
+            else { h.image_id = INT64_MAX; h.dist = __int_as_float(0x7f800000); h.dot = 0; h.norm2 = 0; h.flags = 0; }
+            p.hits[c] = h;
+        }
+    }
+    for (uint32_t c = nc + threadIdx.x; c < p.k; c += blockDim.x) {
+        pbx_hit h; h.image_id = INT64_MAX; h.dist = __int_as_float(0x7f800000); h.dot = 0; h.norm2 = 0; h.flags = 0;
+        p.hits[c] = h;
+    }
+    if (local) atomicAdd(&s_cnt, local);
+    __syncthreads();
+
+    // ---- certificate ---------------------------------------------------------
+    if (threadIdx.x == 0) {
+        const uint32_t passing = s_cnt;
+        *p.count = passing < p.k ? passing : p.k;
+        SearchStatus st;
+        st.n_candidates = nc;
+        st.reserved = 0;
+        st.need_exact = 0;
+        st.theta = 0.0f;
+        if (p.n > nc) {                                   // some rows are not candidates
+            const bool plateau_reachable = p.max_dist > (double)PBX_PLATEAU_DIST && s_nonplateau < p.k;
+            const bool separated = (double)s_kappa_last < (double)s_kappa_k - (double)p.margin;
+            if (plateau_reachable) { st.need_exact = 1; st.theta = -__int_as_float(0x7f800000); }
+            else if (!separated) { st.need_exact = 1; st.theta = (float)((double)s_kappa_k - (double)p.margin - 1e-7); }
+        }
+        *p.status = st;
+        *p.tile_counter = 0;
+    }
+}
+
+// ---- exact pass: merge of the per-CTA (dist, id) lists and output ----------------------------------
+struct FinalizeExactParams {
+    const KeyX* cand;           // [k][grid] rank-major
+    const uint32_t* cand_cnt;
+    uint32_t grid;
+    uint32_t k;
+    uint32_t cap;               // power of two >= k + kMergeChunk
+    uint32_t dim;
+    uint32_t pitch;
+    const uint8_t* rows;
+    const uint8_t* qbytes;
+    pbx_hit* hits;
+    uint32_t* count;
+    const SearchStatus* status;
+    uint32_t* tile_counter;
+    unsigned long long* exact_passes;
+};
+
+__global__ void __launch_bounds__(kFinalThreads, 1)
+finalize_exact_kernel(const FinalizeExactParams p) {
+    if (p.status->need_exact == 0) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    KeyX* buf = reinterpret_cast<KeyX*>(smem_raw);
+    __shared__ uint32_t s_cnt, s_maxcnt;
+    __shared__ KeyX s_tau;
+    __shared__ uint32_t s_listcnt[kMaxScanGrid];
+    if (threadIdx.x == 0) { s_cnt = 0; s_tau = KeyOps<KeyX>::lowest(); s_maxcnt = 0; }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < p.grid; b += blockDim.x) {
+        uint32_t c = p.cand_cnt[b];
+        s_listcnt[b] = c;
+        atomicMax(&s_maxcnt, c);
+    }
+    __syncthreads();
+    TopBuf<KeyX> tb{buf, &s_cnt, &s_tau, p.cap, p.k};
+    const uint32_t total = s_maxcnt * p.grid;
+    for (uint32_t base = 0; base < total; base += kMergeChunk) {
+        if (s_cnt + kMergeChunk > p.cap) tb.compact();
+        const KeyX tau = s_tau;
+        __syncthreads();
+#pragma unroll
+        for (int x = 0; x < kMergeChunk / kFinalThreads; ++x) {
+            const uint32_t e = base + x * kFinalThreads + threadIdx.x;
+            bool pass = false;
+            KeyX key = KeyOps<KeyX>::lowest();
+            if (e < total) {
+                const uint32_t rank = e / p.grid, b = e - rank * p.grid;
+                if (rank < s_listcnt[b]) { key = p.cand[e]; pass = keyx_gt(key, tau); }
+            }
+            tb.push_warp(pass, key);
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    tb.compact();
+    const uint32_t nc = s_cnt < p.k ? s_cnt : p.k;
+    for (uint32_t c = threadIdx.x; c < p.k; c += blockDim.x) {
+        pbx_hit h;
+        if (c < nc) {
+            const KeyX key = buf[c];
+            int idot = 0, inorm = 0;
+            const uint8_t* row = p.rows + (size_t)key.row * p.pitch;
+            for (uint32_t i = 0; i < p.dim; ++i) { int cr = centre(row[i]), cq = centre(p.qbytes[i]); idot += cq * cr; inorm += cr * cr; }
+            h.image_id = keyx_id(key); h.dist = keyx_dist(key); h.dot = idot; h.norm2 = inorm; h.flags = 1;
+        } else {
+            h.image_id = INT64_MAX; h.dist = __int_as_float(0x7f800000); h.dot = 0; h.norm2 = 0; h.flags = 0;
+        }
+        p.hits[c] = h;
+    }
+    if (threadIdx.x == 0) {
+        *p.count = nc;
+        *p.tile_counter = 0;
+        atomicAdd(p.exact_passes, 1ull);
+    }
+}
+
+// ---- merge after the all-gather, device side ----------------------------------------
+// gathered: [n_shards][nq][k] hits, counts: [n_shards][nq]; every shard list is ordered by
+// (dist, image_id).  One thread per gathered element computes its global rank as the number of
+// elements of all lists that precede it under (dist, image_id, shard) -- a binary search per list --
+// and writes itself to out[rank] if rank < k.  n_shards * k is at most a few thousand.
+__device__ __forceinline__ bool hit_before(const pbx_hit& a, uint32_t sa, const pbx_hit& b, uint32_t sb) {
+    if (a.dist != b.dist) return a.dist < b.dist;
+    if (a.image_id != b.image_id) return a.image_id < b.image_id;
+    return sa < sb;
+}
+__global__ void merge_hits_kernel(const pbx_hit* __restrict__ gathered, const uint32_t* __restrict__ counts, uint32_t n_shards,
+                                  uint32_t nq, uint32_t k, pbx_hit* __restrict__ out, uint32_t* __restrict__ out_count) {
+    const uint32_t q = blockIdx.x;
+    uint32_t total = 0;
+    for (uint32_t s = 0; s < n_shards; ++s) total += min(counts[s * nq + q], k);
+    const uint32_t n_out = min(total, k);
+    for (uint32_t e = threadIdx.x; e < n_shards * k; e += blockDim.x) {
+        const uint32_t s = e / k, i = e - s * k;
+        if (i >= min(counts[s * nq + q], k)) continue;
+        const pbx_hit me = gathered[((size_t)s * nq + q) * k + i];
+        uint32_t rank = 0;
+        for (uint32_t t = 0; t < n_shards; ++t) {
+            const pbx_hit* list = gathered + ((size_t)t * nq + q) * k;
+            uint32_t lo = 0, hi = min(counts[t * nq + q], k);
+            while (lo < hi) {                       // first element of list t that does not precede `me`
+                const uint32_t mid = (lo + hi) >> 1;
+                if (hit_before(list[mid], t, me, s)) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < k) out[(size_t)q * k + rank] = me;
+    }
+    for (uint32_t i = n_out + threadIdx.x; i < k; i += blockDim.x) {
+        pbx_hit h; h.image_id = INT64_MAX; h.dist = __int_as_float(0x7f800000); h.dot = 0; h.norm2 = 0; h.flags = 0;
+        out[(size_t)q * k + i] = h;
+    }
+    if (threadIdx.x == 0) out_count[q] = n_out;
+}
+
+// ---- cosine_distance for explicit pairs (src/engine.rs:572-588 as a batch) -------------------------
+__global__ void pair_distance_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint64_t n, uint32_t dim,
+                                     float* __restrict__ out_dist, int* __restrict__ out_dot, int* __restrict__ out_na,
+                                     int* __restrict__ out_nb) {
+    __shared__ float lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = ref_decode(i);
+    __syncthreads();
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint8_t* pa = a + t * dim;
+    const uint8_t* pb = b + t * dim;
+    float sa = 0.0f, sb = 0.0f, dot = 0.0f;
+    int idot = 0, ina = 0, inb = 0;
+    for (uint32_t i = 0; i < dim; ++i) { float x = lut[pa[i]]; sa = ref_fold(sa, x, x); int c = centre(pa[i]); ina += c * c; }
+    for (uint32_t i = 0; i < dim; ++i) { float y = lut[pb[i]]; sb = ref_fold(sb, y, y); int c = centre(pb[i]); inb += c * c; }
+    for (uint32_t i = 0; i < dim; ++i) { dot = ref_fold(dot, lut[pa[i]], lut[pb[i]]); idot += centre(pa[i]) * centre(pb[i]); }
+    out_dist[t] = ref_distance(sa, sb, dot);
+    if (out_dot) out_dot[t] = idot;
+    if (out_na) out_na[t] = ina;
+    if (out_nb) out_nb[t] = inb;
+}
+
+}  // namespace pbx

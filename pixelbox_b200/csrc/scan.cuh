@@ -1,0 +1,292 @@
+// scan.cuh -- kernel A: the HBM-bound single-query scan (replaces the per-row SQLite -> UDF ->
+// cosine_distance loop of src/engine.rs:375-383 / :608-622 / :572-588 in the reference).
+//
+// One persistent CTA grid streams the row-major u8 corpus once.  L lanes share a row (16-byte
+// coalesced ld.global.nc per lane), the query lives in registers as centred 16-bit values
+// c(q) = 2q - 255, and IDP.2A (dp2a) accumulates  acc = sum c(q_i) * r_i  exactly in int32, so
+//     dot_i = sum c(q_i) c(r_i) = 2 * acc - 255 * sum c(q_i)
+// needs no per-row sum.  A transposing butterfly (L-1 shuffles per L rows) leaves one finished
+// row per lane; the ranking key is kappa = dot_i / sqrt(norm2_q * norm2_r) in f32 using the
+// per-row 1/sqrt(norm2_r) precomputed at load time (4 bytes per row, the only metadata read).
+// Rows that beat the CTA's running threshold are pushed into a shared-memory buffer; the buffer
+// is sorted and cut back to `keep` entries when it runs out of headroom (rare after warm-up).
+//
+// EXACT = false: fast pass, key = (kappa, row), keep = k + slack candidates per CTA.
+// EXACT = true : tie-resolving pass.  Rows with kappa >= theta are replayed with the
+//                reference's f32 arithmetic in-kernel and ranked by the exact (dist, image_id);
+//                launched after every fast pass and exits at once unless the fast pass could
+//                not certify its answer (status->need_exact).
+#pragma once
+#include "common.cuh"
+
+namespace pbx {
+
+struct QueryHeader {            // written by prep_query_kernel (+ sa by the finalize kernel)
+    int sum_cq;                 // sum c(q_i), i < dim
+    int norm2_q;                // sum c(q_i)^2
+    float inv_q;                // 1/sqrt(norm2_q), f32-rounded from f64
+    float sa;                   // reference's sequential f32 fold of the decoded query (engine.rs:580)
+};
+
+struct SearchStatus {           // one per query, written by the finalize kernel
+    uint32_t need_exact;        // 1: the certificate failed, the exact pass must run
+    float theta;                // exact pass replays rows with kappa >= theta
+    uint32_t n_candidates;
+    uint32_t reserved;
+};
+
+struct ScanParams {
+    const uint4* rows;          // [capacity][pitch16] u8 rows, zero padded to a multiple of 16 bytes
+    const float* inv_norm;      // [capacity] 1/sqrt(norm2_r)
+    const int64_t* ids;         // [capacity]
+    uint32_t n;                 // committed rows visible to this search
+    uint32_t pitch16;           // row pitch in 16-byte chunks
+    uint32_t dim;
+    const int16_t* q16;         // [pitch] centred query, zero in the padding
+    const uint8_t* qbytes;      // [pitch] raw query bytes
+    const QueryHeader* qh;
+    uint32_t keep;              // entries kept per CTA (k + slack, or k for EXACT)
+    uint32_t cap;               // shared buffer capacity, power of two >= keep + kTileRows
+    void* cand;                 // [keep][grid] keys, rank-major (u64 or KeyX)
+    uint32_t* cand_cnt;         // [grid]
+    uint32_t* tile_counter;     // dynamic tile scheduler (reset by the finalize kernel)
+    const SearchStatus* status; // EXACT only
+    double max_dist;            // EXACT only
+};
+
+// 16 corpus bytes against 16 centred query values: 8 x IDP.2A
+__device__ __forceinline__ int dot16(const uint4& v, const int* q, int acc) {
+    acc = dp2a_lo(q[0], v.x, acc); acc = dp2a_hi(q[1], v.x, acc);
+    acc = dp2a_lo(q[2], v.y, acc); acc = dp2a_hi(q[3], v.y, acc);
+    acc = dp2a_lo(q[4], v.z, acc); acc = dp2a_hi(q[5], v.z, acc);
+    acc = dp2a_lo(q[6], v.w, acc); acc = dp2a_hi(q[7], v.w, acc);
+    return acc;
+}
+
+// L lanes each hold L partial sums (one per row); afterwards lane j holds the full sum of row j.
+template <int L>
+__device__ __forceinline__ int transpose_reduce(int (&acc)[L], int j) {
+#pragma unroll
+    for (int off = L / 2; off >= 1; off >>= 1) {
+        const bool up = (j & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            int send = up ? acc[i] : acc[i + off];
+            int keep = up ? acc[i + off] : acc[i];
+            acc[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, off);
+        }
+    }
+    return acc[0];
+}
+
+// Bit-exact replay of the reference's row norm and dot folds for one row (src/engine.rs:580, :585).
+__device__ __forceinline__ void replay_row(const uint8_t* __restrict__ row, const uint8_t* __restrict__ q, uint32_t dim,
+                                           const float* lut, float& sb, float& dot, int& idot, int& inorm) {
+    float s = 0.0f, d = 0.0f;
+    int id_ = 0, in_ = 0;
+    const uint32_t* row32 = reinterpret_cast<const uint32_t*>(row);
+    const uint32_t* q32 = reinterpret_cast<const uint32_t*>(q);
+    uint32_t words = dim >> 2;
+    for (uint32_t w = 0; w < words; ++w) {
+        uint32_t rv = __ldg(row32 + w), qv = __ldg(q32 + w);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            uint32_t rb = (rv >> (8 * b)) & 255u, qb = (qv >> (8 * b)) & 255u;
+            float fb = lut[rb], fa = lut[qb];
+            s = ref_fold(s, fb, fb);
+            d = ref_fold(d, fa, fb);
+            int cr = centre(rb), cq = centre(qb);
+            id_ += cq * cr;
+            in_ += cr * cr;
+        }
+    }
+    for (uint32_t i = words << 2; i < dim; ++i) {
+        uint32_t rb = row[i], qb = q[i];
+        float fb = lut[rb], fa = lut[qb];
+        s = ref_fold(s, fb, fb);
+        d = ref_fold(d, fa, fb);
+        int cr = centre(rb), cq = centre(qb);
+        id_ += cq * cr;
+        in_ += cr * cr;
+    }
+    sb = s; dot = d; idot = id_; inorm = in_;
+}
+
+template <typename K, bool EXACT>
+struct ScanShared {
+    uint32_t cnt;
+    uint32_t tile;
+    K tau;
+    float lut[EXACT ? 256 : 1];
+};
+
+// Fast shapes: pitch16 == L * C, L lanes per row, C chunks per lane.
+template <int L, int C, bool EXACT>
+__global__ void __launch_bounds__(kScanThreads, (L * C >= 16) ? 2 : 4)
+scan_kernel(const ScanParams p) {
+    using K = typename std::conditional<EXACT, KeyX, u64>::type;
+    constexpr int G = 32 / L;                 // rows handled by one warp-wide load
+    constexpr int P16 = L * C;                // row pitch in chunks (compile time for fast shapes)
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    K* buf = reinterpret_cast<K*>(smem_raw);
+    __shared__ ScanShared<K, EXACT> sh;
+
+    if constexpr (EXACT) {
+        if (p.status->need_exact == 0) return;
+        sh.lut[threadIdx.x & 255] = ref_decode(threadIdx.x & 255);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / L, j = lane % L;
+
+    // centred query chunks of this lane: chunk index j + c*L, 16 values = 8 packed registers each
+    int q[C][8];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int4* src = reinterpret_cast<const int4*>(p.q16 + (size_t)(j + c * L) * 16);
+        int4 a = __ldg(src), b = __ldg(src + 1);
+        q[c][0] = a.x; q[c][1] = a.y; q[c][2] = a.z; q[c][3] = a.w;
+        q[c][4] = b.x; q[c][5] = b.y; q[c][6] = b.z; q[c][7] = b.w;
+    }
+    const QueryHeader qh = *p.qh;
+    const int bias = -255 * qh.sum_cq;
+    float theta = 0.0f;
+    if constexpr (EXACT) theta = p.status->theta;
+
+    if (threadIdx.x == 0) { sh.cnt = 0; sh.tau = KeyOps<K>::lowest(); }
+    TopBuf<K> tb{buf, &sh.cnt, &sh.tau, p.cap, p.keep};
+    const uint32_t n_tiles = (p.n + kTileRows - 1) / kTileRows;
+
+    for (;;) {
+        __syncthreads();                                   // pushes of the previous tile are complete
+        if (threadIdx.x == 0) sh.tile = atomicAdd(p.tile_counter, 1u);
+        if (sh.cnt + kTileRows > p.cap) tb.compact();      // uniform: cnt was read after the barrier
+        __syncthreads();
+        const uint32_t tile = sh.tile;
+        if (tile >= n_tiles) break;
+        const K tau = sh.tau;
+        const uint32_t tile_row0 = tile * kTileRows;
+
+        constexpr int UNR = (L * C >= 16) ? 1 : kItersPerTile;
+#pragma unroll UNR
+        for (int it = 0; it < kItersPerTile; ++it) {
+            const uint32_t row0 = tile_row0 + (uint32_t)(it * kScanWarps + warp) * kRowsPerWarpIter;
+            const uint32_t my_row = row0 + (uint32_t)(j * G + g);
+            const float inv_r = __ldg(p.inv_norm + my_row);      // capacity is padded to whole tiles
+            const uint4* base = p.rows + (size_t)row0 * P16 + (size_t)g * P16 + j;
+            int acc[L];
+#pragma unroll
+            for (int r = 0; r < L; ++r) {
+                int a = 0;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    uint4 v = ldg_stream(base + (r * G) * P16 + c * L);
+                    a = dot16(v, q[c], a);
+                }
+                acc[r] = a;
+            }
+            const int s = transpose_reduce<L>(acc, j);
+            const int dot_i = 2 * s + bias;
+            const float kappa = __fmul_rn(__fmul_rn((float)dot_i, inv_r), qh.inv_q);
+            if constexpr (!EXACT) {
+                const u64 key = make_key64(kappa, my_row);
+                tb.push_warp(my_row < p.n && key > tau, key);
+            } else {
+                bool pass = false;
+                KeyX key = KeyOps<KeyX>::lowest();
+                if (my_row < p.n && kappa >= theta) {
+                    float sb, dotf; int idot, inorm;
+                    replay_row(reinterpret_cast<const uint8_t*>(p.rows) + (size_t)my_row * (P16 * 16), p.qbytes, p.dim,
+                               sh.lut, sb, dotf, idot, inorm);
+                    float dist = ref_distance(qh.sa, sb, dotf);
+                    if ((double)dist < p.max_dist) {
+                        key = make_keyx(dist, __ldg(p.ids + my_row), my_row);
+                        pass = keyx_gt(key, tau);
+                    }
+                }
+                tb.push_warp(pass, key);
+            }
+        }
+    }
+
+    // final cut: best `keep` of this CTA, written rank-major so the merge reads coalesced
+    tb.compact();
+    const uint32_t c = sh.cnt < p.keep ? sh.cnt : p.keep;
+    K* out = reinterpret_cast<K*>(p.cand);
+    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) out[(size_t)i * gridDim.x + blockIdx.x] = buf[i];
+    if (threadIdx.x == 0) p.cand_cnt[blockIdx.x] = c;
+}
+
+// Any other pitch: one lane per row, query chunks from shared memory.  Correctness path for odd
+// dims (the reference's BLOB column is length-agnostic, src/engine.rs:48); not tuned.
+template <bool EXACT>
+__global__ void __launch_bounds__(kScanThreads, 2)
+scan_generic_kernel(const ScanParams p) {
+    using K = typename std::conditional<EXACT, KeyX, u64>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    K* buf = reinterpret_cast<K*>(smem_raw);
+    int4* sq = reinterpret_cast<int4*>(smem_raw + (size_t)p.cap * sizeof(K));   // [pitch16][2] int4
+    __shared__ ScanShared<K, EXACT> sh;
+
+    if constexpr (EXACT) {
+        if (p.status->need_exact == 0) return;
+        sh.lut[threadIdx.x & 255] = ref_decode(threadIdx.x & 255);
+    }
+    for (uint32_t i = threadIdx.x; i < p.pitch16 * 2; i += blockDim.x) sq[i] = __ldg(reinterpret_cast<const int4*>(p.q16) + i);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const QueryHeader qh = *p.qh;
+    const int bias = -255 * qh.sum_cq;
+    float theta = 0.0f;
+    if constexpr (EXACT) theta = p.status->theta;
+    if (threadIdx.x == 0) { sh.cnt = 0; sh.tau = KeyOps<K>::lowest(); }
+    TopBuf<K> tb{buf, &sh.cnt, &sh.tau, p.cap, p.keep};
+    const uint32_t n_tiles = (p.n + kTileRows - 1) / kTileRows;
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) sh.tile = atomicAdd(p.tile_counter, 1u);
+        if (sh.cnt + kTileRows > p.cap) tb.compact();
+        __syncthreads();
+        const uint32_t tile = sh.tile;
+        if (tile >= n_tiles) break;
+        const K tau = sh.tau;
+        for (int it = 0; it < kItersPerTile; ++it) {
+            const uint32_t my_row = tile * kTileRows + (uint32_t)(it * kScanWarps + warp) * kRowsPerWarpIter + lane;
+            const float inv_r = __ldg(p.inv_norm + my_row);
+            const uint4* rp = p.rows + (size_t)my_row * p.pitch16;
+            int s = 0;
+            for (uint32_t c = 0; c < p.pitch16; ++c) {
+                uint4 v = __ldg(rp + c);
+                int4 a = sq[2 * c], b = sq[2 * c + 1];
+                int qq[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                s = dot16(v, qq, s);
+            }
+            const int dot_i = 2 * s + bias;
+            const float kappa = __fmul_rn(__fmul_rn((float)dot_i, inv_r), qh.inv_q);
+            if constexpr (!EXACT) {
+                const u64 key = make_key64(kappa, my_row);
+                tb.push_warp(my_row < p.n && key > tau, key);
+            } else {
+                bool pass = false;
+                KeyX key = KeyOps<KeyX>::lowest();
+                if (my_row < p.n && kappa >= theta) {
+                    float sb, dotf; int idot, inorm;
+                    replay_row(reinterpret_cast<const uint8_t*>(p.rows) + (size_t)my_row * ((size_t)p.pitch16 * 16), p.qbytes,
+                               p.dim, sh.lut, sb, dotf, idot, inorm);
+                    float dist = ref_distance(qh.sa, sb, dotf);
+                    if ((double)dist < p.max_dist) {
+                        key = make_keyx(dist, __ldg(p.ids + my_row), my_row);
+                        pass = keyx_gt(key, tau);
+                    }
+                }
+                tb.push_warp(pass, key);
+            }
+        }
+    }
+    tb.compact();
+    const uint32_t c = sh.cnt < p.keep ? sh.cnt : p.keep;
+    K* out = reinterpret_cast<K*>(p.cand);
+    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) out[(size_t)i * gridDim.x + blockIdx.x] = buf[i];
+    if (threadIdx.x == 0) p.cand_cnt[blockIdx.x] = c;
+}
+
+}  // namespace pbx
