@@ -46,6 +46,7 @@ extern "C" {
 #define PBX_MAX_DIM 16384u
 #define PBX_MAX_K 2048u
 #define PBX_MAX_ROWS 0xFFFFFFF0ull
+#define PBX_MAX_SHARDS 64u
 
 /* DEFAULT_MAX_QUERY_DISTANCE and the literal LIMIT of the reference (src/engine.rs:23, :381). */
 #define PBX_DEFAULT_MAX_DIST 1e3
@@ -111,6 +112,9 @@ PBX_API int pbx_corpus_dim(const pbx_corpus* c, uint32_t* dim);
  * IndexedImage.visual_hash, src/engine.rs:385).  Either output may be NULL. */
 PBX_API int pbx_corpus_read_rows(const pbx_corpus* c, uint64_t first, uint64_t n, int64_t* image_ids, uint8_t* hashes);
 
+/* Waits for everything enqueued on the corpus' own stream (pbx_search_device with a NULL stream). */
+PBX_API int pbx_corpus_synchronize(pbx_corpus* c);
+
 /* ---- search ----------------------------------------------------------------------------
  * Replaces: the SQL statement of Engine::query_by_image_hash_from_image,
  *   SELECT ..., cosine_distance(?, semantic_hashes.hash) AS dist FROM semantic_hashes ...
@@ -148,7 +152,8 @@ PBX_API int pbx_merge_hits(const pbx_hit* gathered, const uint32_t* counts, uint
 
 /* Device-side form of the same merge for pipelines that keep the gathered records in HBM (the
  * buffer an NCCL all-gather of the pbx_search_device outputs produces): all pointers are DEVICE
- * pointers, the kernel is enqueued on `cuda_stream` (NULL = the legacy default stream) of
+ * pointers; d_counts may be NULL, in which case each list's length is the number of leading slots
+ * with a finite dist (so only the hit records need to be exchanged).  The kernel is enqueued on `cuda_stream` (NULL = the legacy default stream) of
  * `device` and the call does not wait. */
 PBX_API int pbx_merge_hits_device(int device, const pbx_hit* d_gathered, const uint32_t* d_counts, uint32_t n_shards,
                                   uint32_t nq, uint32_t k, pbx_hit* d_out_hits, uint32_t* d_out_count, void* cuda_stream);

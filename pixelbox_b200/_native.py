@@ -26,7 +26,7 @@ DEFAULT_K = 100          # the literal LIMIT of src/engine.rs:381
 # every symbol include/pixelbox_b200.h declares (tests check the library exports exactly these)
 EXPORTS = [
     "pbx_corpus_create", "pbx_corpus_destroy", "pbx_corpus_load", "pbx_corpus_append", "pbx_corpus_fill_synthetic",
-    "pbx_corpus_size", "pbx_corpus_dim", "pbx_corpus_read_rows", "pbx_search", "pbx_search_hits", "pbx_search_device",
+    "pbx_corpus_size", "pbx_corpus_dim", "pbx_corpus_read_rows", "pbx_corpus_synchronize", "pbx_search", "pbx_search_hits", "pbx_search_device",
     "pbx_merge_hits", "pbx_merge_hits_device", "pbx_cosine_distance_pairs", "pbx_get_stats", "pbx_set_candidate_slack",
     "pbx_set_scan_ctas_per_sm", "pbx_last_error", "pbx_version", "pbx_device_count",
 ]
@@ -74,6 +74,7 @@ def lib() -> ctypes.CDLL:
         "pbx_corpus_size": (i32, [vp, ctypes.POINTER(u64)]),
         "pbx_corpus_dim": (i32, [vp, ctypes.POINTER(u32)]),
         "pbx_corpus_read_rows": (i32, [vp, u64, u64, vp, u8p]),
+        "pbx_corpus_synchronize": (i32, [vp]),
         "pbx_search": (i32, [vp, u8p, u32, u32, f64, vp, vp, vp, vp, vp]),
         "pbx_search_hits": (i32, [vp, u8p, u32, u32, f64, vp, vp]),
         "pbx_search_device": (i32, [vp, vp, u32, u32, f64, vp, vp, vp]),

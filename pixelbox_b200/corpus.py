@@ -114,11 +114,23 @@ class Corpus:
         return hits, cnt
 
     def search_device(self, d_queries_ptr: int, nq: int, k: int, max_dist: float, d_hits_ptr: int, d_count_ptr: int,
-                      stream: int = 0) -> None:
-        """pbx_search_device: raw device pointers, enqueued on `stream` (a cudaStream_t value), no host sync."""
+                      stream: Optional[int] = None) -> None:
+        """pbx_search_device: raw device pointers, enqueued on `stream`, no host sync.
+
+        `stream` is a cudaStream_t value (e.g. torch.cuda.current_stream().cuda_stream); 0 means the
+        legacy default stream, as it does in torch; None means the corpus' own stream (wait for it
+        with synchronize())."""
+        if stream is None:
+            stream = 0                      # NULL -> the corpus' own stream
+        elif stream == 0:
+            stream = 1                      # cudaStreamLegacy
         nat.check(nat.lib().pbx_search_device(self._h, ctypes.c_void_p(d_queries_ptr), int(nq), int(k), float(max_dist),
                                               ctypes.c_void_p(d_hits_ptr), ctypes.c_void_p(d_count_ptr),
                                               ctypes.c_void_p(stream)))
+
+    def synchronize(self) -> None:
+        """Waits for everything enqueued on the corpus' own stream."""
+        nat.check(nat.lib().pbx_corpus_synchronize(self._h))
 
     # -- diagnostics -------------------------------------------------------------------------
     def stats(self) -> nat.PbxStats:

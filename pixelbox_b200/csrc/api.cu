@@ -284,6 +284,12 @@ extern "C" int pbx_corpus_size(const pbx_corpus* c, uint64_t* n_rows) {
     *n_rows = c->n.load();
     return PBX_OK;
 }
+extern "C" int pbx_corpus_synchronize(pbx_corpus* c) {
+    if (!c) return fail(PBX_E_INVALID, "corpus is NULL");
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return PBX_OK;
+}
 extern "C" int pbx_corpus_dim(const pbx_corpus* c, uint32_t* dim) {
     if (!c || !dim) return fail(PBX_E_INVALID, "NULL argument");
     *dim = c->dim;
@@ -679,8 +685,8 @@ extern "C" int pbx_merge_hits(const pbx_hit* gathered, const uint32_t* counts, u
 
 extern "C" int pbx_merge_hits_device(int device, const pbx_hit* d_gathered, const uint32_t* d_counts, uint32_t n_shards, uint32_t nq,
                                      uint32_t k, pbx_hit* d_out_hits, uint32_t* d_out_count, void* cuda_stream) {
-    if (!d_gathered || !d_counts || !d_out_hits || !d_out_count) return fail(PBX_E_INVALID, "NULL argument");
-    if (k == 0 || n_shards == 0) return fail(PBX_E_INVALID, "k and n_shards must be >= 1");
+    if (!d_gathered || !d_out_hits || !d_out_count) return fail(PBX_E_INVALID, "NULL argument");
+    if (k == 0 || n_shards == 0 || n_shards > PBX_MAX_SHARDS) return fail(PBX_E_INVALID, "k >= 1 and 1 <= n_shards <= %u required", PBX_MAX_SHARDS);
     if (nq == 0) return PBX_OK;
     CU_TRY(cudaSetDevice(device));
     merge_hits_kernel<<<nq, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(d_gathered, d_counts, n_shards, nq, k, d_out_hits, d_out_count);

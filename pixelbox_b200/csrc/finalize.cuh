@@ -392,17 +392,33 @@ __device__ __forceinline__ bool hit_before(const pbx_hit& a, uint32_t sa, const 
 __global__ void merge_hits_kernel(const pbx_hit* __restrict__ gathered, const uint32_t* __restrict__ counts, uint32_t n_shards,
                                   uint32_t nq, uint32_t k, pbx_hit* __restrict__ out, uint32_t* __restrict__ out_count) {
     const uint32_t q = blockIdx.x;
-    uint32_t total = 0;
-    for (uint32_t s = 0; s < n_shards; ++s) total += min(counts[s * nq + q], k);
-    const uint32_t n_out = min(total, k);
+    __shared__ uint32_t s_cnt[PBX_MAX_SHARDS];
+    __shared__ uint32_t s_total;
+    if (threadIdx.x == 0) s_total = 0;
+    __syncthreads();
+    for (uint32_t s = threadIdx.x; s < n_shards; s += blockDim.x) {
+        uint32_t c;
+        if (counts) {
+            c = min(counts[s * nq + q], k);
+        } else {                                    // unused tail slots carry dist = +inf: count the finite prefix
+            const pbx_hit* list = gathered + ((size_t)s * nq + q) * k;
+            uint32_t lo = 0, hi = k;
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (list[mid].dist < __int_as_float(0x7f800000)) lo = mid + 1; else hi = mid; }
+            c = lo;
+        }
+        s_cnt[s] = c;
+        atomicAdd(&s_total, c);
+    }
+    __syncthreads();
+    const uint32_t n_out = min(s_total, k);
     for (uint32_t e = threadIdx.x; e < n_shards * k; e += blockDim.x) {
         const uint32_t s = e / k, i = e - s * k;
-        if (i >= min(counts[s * nq + q], k)) continue;
+        if (i >= s_cnt[s]) continue;
         const pbx_hit me = gathered[((size_t)s * nq + q) * k + i];
         uint32_t rank = 0;
         for (uint32_t t = 0; t < n_shards; ++t) {
             const pbx_hit* list = gathered + ((size_t)t * nq + q) * k;
-            uint32_t lo = 0, hi = min(counts[t * nq + q], k);
+            uint32_t lo = 0, hi = s_cnt[t];
             while (lo < hi) {                       // first element of list t that does not precede `me`
                 const uint32_t mid = (lo + hi) >> 1;
                 if (hit_before(list[mid], t, me, s)) lo = mid + 1; else hi = mid;
