@@ -199,6 +199,30 @@ static int ensure_cand(pbx_corpus* c, size_t bytes) {
     return PBX_OK;
 }
 
+// Dynamic shared memory limits are per function and per device, and static shared memory counts
+// against the 48 KB default as well: raise every kernel's cap once, when a corpus is created on a device.
+template <typename Kern>
+static cudaError_t allow_smem(Kern kern, size_t bytes) {
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+static cudaError_t init_kernel_attributes() {
+    const size_t scan_cap = 8192 * sizeof(KeyX) + PBX_MAX_DIM * 2 + 1024;       // largest cap (keep 4096 + tile) + generic query stage
+    const size_t fin_cap = 200 * 1024;
+    cudaError_t e = cudaSuccess;
+#define PBX_ALLOW(LL, CC)                                                          \
+    if (e == cudaSuccess) e = allow_smem(scan_kernel<LL, CC, false>, scan_cap);    \
+    if (e == cudaSuccess) e = allow_smem(scan_kernel<LL, CC, true>, scan_cap);
+    PBX_ALLOW(1, 1) PBX_ALLOW(2, 1) PBX_ALLOW(4, 1) PBX_ALLOW(8, 1) PBX_ALLOW(16, 1) PBX_ALLOW(32, 1) PBX_ALLOW(32, 2) PBX_ALLOW(32, 4)
+#undef PBX_ALLOW
+    if (e == cudaSuccess) e = allow_smem(scan_kernel<16, 1, false, 3>, scan_cap);
+    if (e == cudaSuccess) e = allow_smem(scan_kernel<16, 1, false, 4>, scan_cap);
+    if (e == cudaSuccess) e = allow_smem(scan_generic_kernel<false>, scan_cap);
+    if (e == cudaSuccess) e = allow_smem(scan_generic_kernel<true>, scan_cap);
+    if (e == cudaSuccess) e = allow_smem(finalize_kernel, fin_cap);
+    if (e == cudaSuccess) e = allow_smem(finalize_exact_kernel, fin_cap);
+    return e;
+}
+
 extern "C" int pbx_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -242,6 +266,7 @@ extern "C" int pbx_corpus_create(uint32_t dim, uint64_t capacity_hint, int devic
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_t1);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_s0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_s1);
+    if (e == cudaSuccess) e = init_kernel_attributes();
     if (e == cudaSuccess) e = cudaMalloc(&c->d_cand_cnt, kMaxScanGrid * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_tile_counter, 256);
     if (e == cudaSuccess) e = cudaMemset(c->d_tile_counter, 0, 256);
@@ -430,7 +455,6 @@ static cudaError_t launch_scan(const pbx_corpus* c, const ScanParams& p, int gri
 #define PBX_SCAN_CASE(LL, CC)                                                                                   \
     {                                                                                                           \
         auto kern = scan_kernel<LL, CC, EXACT>;                                                                 \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         kern<<<grid, kScanThreads, smem, s>>>(p);                                                               \
         return cudaGetLastError();                                                                              \
     }
@@ -439,14 +463,18 @@ static cudaError_t launch_scan(const pbx_corpus* c, const ScanParams& p, int gri
         case 2: PBX_SCAN_CASE(2, 1)
         case 4: PBX_SCAN_CASE(4, 1)
         case 8: PBX_SCAN_CASE(8, 1)
-        case 16: PBX_SCAN_CASE(16, 1)
+        case 16:
+            if constexpr (!EXACT) {                  // occupancy variants of the d=256 fast pass (pbx_set_scan_ctas_per_sm)
+                if (c->ctas_per_sm == 3) { auto kern = scan_kernel<16, 1, false, 3>; kern<<<grid, kScanThreads, smem, s>>>(p); return cudaGetLastError(); }
+                if (c->ctas_per_sm >= 4) { auto kern = scan_kernel<16, 1, false, 4>; kern<<<grid, kScanThreads, smem, s>>>(p); return cudaGetLastError(); }
+            }
+            PBX_SCAN_CASE(16, 1)
         case 32: PBX_SCAN_CASE(32, 1)
         case 64: PBX_SCAN_CASE(32, 2)
         case 128: PBX_SCAN_CASE(32, 4)
         default: {
             auto kern = scan_generic_kernel<EXACT>;
             size_t sm = smem + (size_t)c->pitch16 * 32;
-            if (sm > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
             kern<<<grid, kScanThreads, sm, s>>>(p);
             return cudaGetLastError();
         }
@@ -476,15 +504,16 @@ static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, 
         const uint32_t keep = std::min<uint32_t>(default_keep(k, c->slack), 4096u);
         const uint32_t cap_scan = next_pow2(keep + kTileRows);
         const uint32_t cap_scan_x = next_pow2(k + kTileRows);
-        const uint32_t cap_merge = next_pow2(keep + kMergeChunk);
+        // merge round size: one element per thread, more only when a round must span a complete rank (2 * grid)
+        const uint32_t chunk = std::min<uint32_t>(4u, std::max<uint32_t>(1u, (2u * (uint32_t)grid + kFinalThreads - 1) / kFinalThreads)) * kFinalThreads;
+        const uint32_t cap_merge = next_pow2(keep + chunk);
         const uint32_t cap_merge_x = next_pow2(k + kMergeChunk);
         rc = ensure_cand(c, (size_t)std::max<uint32_t>(keep, k) * grid * sizeof(KeyX));
         if (rc != PBX_OK) return rc;
         const float margin = certificate_margin(c->dim);
-        const size_t fin_smem = std::max<size_t>((size_t)cap_merge * sizeof(u64), (size_t)next_pow2(keep) * sizeof(RerankEntry) + (size_t)keep * 12);
+        const size_t fin_main = (std::max<size_t>((size_t)cap_merge * sizeof(u64), (size_t)next_pow2(keep) * sizeof(RerankEntry) + (size_t)keep * 12) + 15) & ~(size_t)15;
+        const size_t fin_smem = fin_main + (size_t)c->pitch * 3;
         const size_t finx_smem = (size_t)cap_merge_x * sizeof(KeyX);
-        if (fin_smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
-        if (finx_smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(finalize_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)finx_smem));
 
         prep_query_kernel<<<nq, 256, 0, s>>>(d_queries, c->dim, c->pitch, c->d_q16, c->d_qbytes, c->d_qh);
         CU_TRY(cudaGetLastError());
@@ -524,6 +553,9 @@ static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, 
             fp.rows = c->d_rows;
             fp.ids = c->d_ids;
             fp.qbytes = sp.qbytes;
+            fp.q16 = sp.q16;
+            fp.chunk = chunk;
+            fp.q_off = (uint32_t)fin_main;
             fp.qh = c->d_qh + q;
             fp.max_dist = max_dist;
             fp.margin = margin;

@@ -108,7 +108,10 @@ struct FinalizeParams {
     const uint8_t* rows;
     const int64_t* ids;
     const uint8_t* qbytes;      // this query, padded
+    const int16_t* q16;         // this query, centred, padded
     QueryHeader* qh;            // sa is filled in here
+    uint32_t chunk;             // merge elements per round: a multiple of kFinalThreads, >= 2 * grid when possible
+    uint32_t q_off;             // byte offset of the staged query inside dynamic shared memory
     double max_dist;
     float margin;               // certificate margin on kappa
     pbx_hit* hits;              // [k] this query
@@ -152,9 +155,17 @@ finalize_kernel(const FinalizeParams p) {
     __shared__ float s_kappa_k, s_kappa_last;
     __shared__ uint32_t s_listcnt[kMaxScanGrid];
 
+    // the query is staged once: raw bytes for the f32 replay, centred s16 for the exact integers
+    uint8_t* s_q = smem_raw + p.q_off;
+    int16_t* s_q16 = reinterpret_cast<int16_t*>(smem_raw + p.q_off + p.pitch);
+    for (uint32_t i = threadIdx.x; i < p.pitch / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(s_q)[i] = __ldg(reinterpret_cast<const uint4*>(p.qbytes) + i);
+    for (uint32_t i = threadIdx.x; i < p.pitch / 8; i += blockDim.x)
+        reinterpret_cast<uint4*>(s_q16)[i] = __ldg(reinterpret_cast<const uint4*>(p.q16) + i);
     if (threadIdx.x < 256) s_lut[threadIdx.x] = ref_decode(threadIdx.x);
     if (threadIdx.x == 0) { s_cnt = 0; s_tau = 0ull; s_maxcnt = 0; s_nonplateau = 0; s_pushed = 0; }
     __syncthreads();
+    const int sum_cq = p.qh->sum_cq;
     for (uint32_t b = threadIdx.x; b < p.grid; b += blockDim.x) {
         uint32_t c = p.cand_cnt[b];
         s_listcnt[b] = c;
@@ -166,15 +177,14 @@ finalize_kernel(const FinalizeParams p) {
     // the strongest entries of every list come first and the threshold tightens immediately.
     TopBuf<u64> tb{buf, &s_cnt, &s_tau, p.cap, p.keep};
     const uint32_t total = s_maxcnt * p.grid;
-    for (uint32_t base = 0; base < total; base += kMergeChunk) {
-        if (s_cnt + kMergeChunk > p.cap) tb.compact();      // uniform (read after a barrier)
+    for (uint32_t base = 0; base < total; base += p.chunk) {
+        if (s_cnt + p.chunk > p.cap) tb.compact();          // uniform (read after a barrier)
         const u64 tau = s_tau;
         __syncthreads();
         if (threadIdx.x == 0) s_pushed = 0;
         __syncthreads();
         bool any = false;
-#pragma unroll
-        for (int x = 0; x < kMergeChunk / kFinalThreads; ++x) {
+        for (uint32_t x = 0; x < p.chunk / kFinalThreads; ++x) {
             const uint32_t e = base + x * kFinalThreads + threadIdx.x;
             bool pass = false;
             u64 key = 0;
@@ -189,7 +199,7 @@ finalize_kernel(const FinalizeParams p) {
         __syncthreads();
         // lists are sorted: a chunk that spans at least one complete rank and pushed nothing
         // proves every remaining element is below the threshold
-        if (s_pushed == 0 && kMergeChunk >= 2 * p.grid && s_cnt >= p.keep) break;
+        if (s_pushed == 0 && p.chunk >= 2 * p.grid) break;
     }
     __syncthreads();
     tb.compact();
@@ -219,18 +229,19 @@ finalize_kernel(const FinalizeParams p) {
     // the query's own norm fold (engine.rs:580) by the last thread, which rarely owns a candidate
     if (threadIdx.x == kFinalThreads - 1) {
         float sa = 0.0f;
-        for (uint32_t i = 0; i < p.dim; ++i) { float a = s_lut[p.qbytes[i]]; sa = ref_fold(sa, a, a); }
+        for (uint32_t i = 0; i < p.dim; ++i) { float a = s_lut[s_q[i]]; sa = ref_fold(sa, a, a); }
         p.qh->sa = sa;
     }
     float my_sb[4], my_dot[4];
 #pragma unroll
     for (int x = 0; x < 4; ++x) {
         if (x < (int)per && my_rows[x] != 0xFFFFFFFFu) {
-            int idot, inorm;
-            replay_row(p.rows + (size_t)my_rows[x] * p.pitch, p.qbytes, p.dim, s_lut, my_sb[x], my_dot[x], idot, inorm);
+            const ReplayOut ro = replay_row<true>(p.rows + (size_t)my_rows[x] * p.pitch, s_q, s_q16, p.dim, sum_cq, s_lut);
+            my_sb[x] = ro.sb;
+            my_dot[x] = ro.dot;
             uint32_t c = threadIdx.x + x * kFinalThreads;
-            dots[c] = idot;
-            norms[c] = inorm;
+            dots[c] = ro.idot;
+            norms[c] = ro.inorm;
         }
     }
     __threadfence_block();

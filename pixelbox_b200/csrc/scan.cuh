@@ -79,50 +79,94 @@ __device__ __forceinline__ int transpose_reduce(int (&acc)[L], int j) {
     return acc[0];
 }
 
-// Bit-exact replay of the reference's row norm and dot folds for one row (src/engine.rs:580, :585).
-__device__ __forceinline__ void replay_row(const uint8_t* __restrict__ row, const uint8_t* __restrict__ q, uint32_t dim,
-                                           const float* lut, float& sb, float& dot, int& idot, int& inorm) {
-    float s = 0.0f, d = 0.0f;
-    int id_ = 0, in_ = 0;
-    const uint32_t* row32 = reinterpret_cast<const uint32_t*>(row);
-    const uint32_t* q32 = reinterpret_cast<const uint32_t*>(q);
-    uint32_t words = dim >> 2;
-    for (uint32_t w = 0; w < words; ++w) {
-        uint32_t rv = __ldg(row32 + w), qv = __ldg(q32 + w);
+// Bit-exact replay of the reference's row norm and dot folds for one row (src/engine.rs:580, :585),
+// strictly in element order.  The row is read with 16-byte loads, one batch of four prefetched ahead
+// of the arithmetic; q (raw bytes) and q16 (centred s16) may live in shared or global memory.
+// The exact integers come from the same bytes: dot_i = 2 * sum c(q) r - 255 * sum c(q),
+// norm2 = 4 sum r^2 - 1020 sum r + 65025 d (row padding is zero, q16 padding is zero).
+struct ReplayOut {
+    float sb, dot;
+    int idot, inorm;
+};
+
+__device__ __forceinline__ void replay_bytes(uint32_t rv, uint32_t qv, int nbytes, const float* lut, float& s, float& d) {
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            uint32_t rb = (rv >> (8 * b)) & 255u, qb = (qv >> (8 * b)) & 255u;
-            float fb = lut[rb], fa = lut[qb];
+    for (int b = 0; b < 4; ++b) {
+        if (b < nbytes) {
+            const float fb = lut[(rv >> (8 * b)) & 255u], fa = lut[(qv >> (8 * b)) & 255u];
             s = ref_fold(s, fb, fb);
             d = ref_fold(d, fa, fb);
-            int cr = centre(rb), cq = centre(qb);
-            id_ += cq * cr;
-            in_ += cr * cr;
         }
     }
-    for (uint32_t i = words << 2; i < dim; ++i) {
-        uint32_t rb = row[i], qb = q[i];
-        float fb = lut[rb], fa = lut[qb];
-        s = ref_fold(s, fb, fb);
-        d = ref_fold(d, fa, fb);
-        int cr = centre(rb), cq = centre(qb);
-        id_ += cq * cr;
-        in_ += cr * cr;
+}
+
+template <bool WITH_INTS>
+__device__ __forceinline__ ReplayOut replay_row(const uint8_t* __restrict__ row, const uint8_t* q, const int16_t* q16, uint32_t dim,
+                                                int sum_cq, const float* lut) {
+    const uint4* r4 = reinterpret_cast<const uint4*>(row);
+    const uint32_t* q32 = reinterpret_cast<const uint32_t*>(q);
+    const int4* q16v = reinterpret_cast<const int4*>(q16);
+    const uint32_t full = dim >> 4, chunks = (dim + 15) >> 4;
+    float s = 0.0f, d = 0.0f;
+    int acc = 0;
+    unsigned s1 = 0, s2 = 0;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    uint4 cur[4], nxt[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cur[i] = ((uint32_t)i < chunks) ? __ldg(r4 + i) : zero;
+    for (uint32_t c = 0; c < chunks; c += 4) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) nxt[i] = (c + 4 + i < chunks) ? __ldg(r4 + c + 4 + i) : zero;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t ci = c + i;
+            if (ci < chunks) {
+                const uint4 v = cur[i];
+                if (ci < full) {
+                    replay_bytes(v.x, q32[4 * ci + 0], 4, lut, s, d);
+                    replay_bytes(v.y, q32[4 * ci + 1], 4, lut, s, d);
+                    replay_bytes(v.z, q32[4 * ci + 2], 4, lut, s, d);
+                    replay_bytes(v.w, q32[4 * ci + 3], 4, lut, s, d);
+                } else {                            // ragged tail: dim is not a multiple of 16
+                    const int rem = (int)(dim - (ci << 4));
+                    replay_bytes(v.x, q32[4 * ci + 0], rem, lut, s, d);
+                    replay_bytes(v.y, q32[4 * ci + 1], rem - 4, lut, s, d);
+                    replay_bytes(v.z, q32[4 * ci + 2], rem - 8, lut, s, d);
+                    replay_bytes(v.w, q32[4 * ci + 3], rem - 12, lut, s, d);
+                }
+                if constexpr (WITH_INTS) {
+                    const int4 a = q16v[2 * ci], b = q16v[2 * ci + 1];
+                    const int qq[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                    acc = dot16(v, qq, acc);
+                    s1 = dp4a_uu(v.x, 0x01010101u, s1); s1 = dp4a_uu(v.y, 0x01010101u, s1);
+                    s1 = dp4a_uu(v.z, 0x01010101u, s1); s1 = dp4a_uu(v.w, 0x01010101u, s1);
+                    s2 = dp4a_uu(v.x, v.x, s2); s2 = dp4a_uu(v.y, v.y, s2);
+                    s2 = dp4a_uu(v.z, v.z, s2); s2 = dp4a_uu(v.w, v.w, s2);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
     }
-    sb = s; dot = d; idot = id_; inorm = in_;
+    ReplayOut o;
+    o.sb = s;
+    o.dot = d;
+    o.idot = 2 * acc - 255 * sum_cq;
+    o.inorm = (int)(4u * s2 - 1020u * s1 + 65025u * dim);
+    return o;
 }
 
 template <typename K, bool EXACT>
 struct ScanShared {
     uint32_t cnt;
-    uint32_t tile;
+    uint32_t tile[2];           // double-buffered: the next tile index is fetched one tile ahead
     K tau;
     float lut[EXACT ? 256 : 1];
 };
 
 // Fast shapes: pitch16 == L * C, L lanes per row, C chunks per lane.
-template <int L, int C, bool EXACT>
-__global__ void __launch_bounds__(kScanThreads, (L * C >= 16) ? 2 : 4)
+template <int L, int C, bool EXACT, int MINB = ((L * C >= 16) ? 2 : 4)>
+__global__ void __launch_bounds__(kScanThreads, MINB)
 scan_kernel(const ScanParams p) {
     using K = typename std::conditional<EXACT, KeyX, u64>::type;
     constexpr int G = 32 / L;                 // rows handled by one warp-wide load
@@ -156,12 +200,14 @@ scan_kernel(const ScanParams p) {
     TopBuf<K> tb{buf, &sh.cnt, &sh.tau, p.cap, p.keep};
     const uint32_t n_tiles = (p.n + kTileRows - 1) / kTileRows;
 
-    for (;;) {
+    // dynamic tile scheduler: the atomic for tile t+1 is in flight while tile t is processed
+    if (threadIdx.x == 0) sh.tile[0] = atomicAdd(p.tile_counter, 1u);
+    for (uint32_t ph = 0;; ph ^= 1u) {
         __syncthreads();                                   // pushes of the previous tile are complete
-        if (threadIdx.x == 0) sh.tile = atomicAdd(p.tile_counter, 1u);
+        const uint32_t tile = sh.tile[ph];
+        uint32_t next_tile = 0;
+        if (threadIdx.x == 0) next_tile = atomicAdd(p.tile_counter, 1u);
         if (sh.cnt + kTileRows > p.cap) tb.compact();      // uniform: cnt was read after the barrier
-        __syncthreads();
-        const uint32_t tile = sh.tile;
         if (tile >= n_tiles) break;
         const K tau = sh.tau;
         const uint32_t tile_row0 = tile * kTileRows;
@@ -194,10 +240,9 @@ scan_kernel(const ScanParams p) {
                 bool pass = false;
                 KeyX key = KeyOps<KeyX>::lowest();
                 if (my_row < p.n && kappa >= theta) {
-                    float sb, dotf; int idot, inorm;
-                    replay_row(reinterpret_cast<const uint8_t*>(p.rows) + (size_t)my_row * (P16 * 16), p.qbytes, p.dim,
-                               sh.lut, sb, dotf, idot, inorm);
-                    float dist = ref_distance(qh.sa, sb, dotf);
+                    const ReplayOut ro = replay_row<false>(reinterpret_cast<const uint8_t*>(p.rows) + (size_t)my_row * (P16 * 16),
+                                                           p.qbytes, p.q16, p.dim, qh.sum_cq, sh.lut);
+                    float dist = ref_distance(qh.sa, ro.sb, ro.dot);
                     if ((double)dist < p.max_dist) {
                         key = make_keyx(dist, __ldg(p.ids + my_row), my_row);
                         pass = keyx_gt(key, tau);
@@ -206,6 +251,7 @@ scan_kernel(const ScanParams p) {
                 tb.push_warp(pass, key);
             }
         }
+        if (threadIdx.x == 0) sh.tile[ph ^ 1u] = next_tile;
     }
 
     // final cut: best `keep` of this CTA, written rank-major so the merge reads coalesced
@@ -243,10 +289,10 @@ scan_generic_kernel(const ScanParams p) {
 
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) sh.tile = atomicAdd(p.tile_counter, 1u);
+        if (threadIdx.x == 0) sh.tile[0] = atomicAdd(p.tile_counter, 1u);
         if (sh.cnt + kTileRows > p.cap) tb.compact();
         __syncthreads();
-        const uint32_t tile = sh.tile;
+        const uint32_t tile = sh.tile[0];
         if (tile >= n_tiles) break;
         const K tau = sh.tau;
         for (int it = 0; it < kItersPerTile; ++it) {
@@ -269,10 +315,9 @@ scan_generic_kernel(const ScanParams p) {
                 bool pass = false;
                 KeyX key = KeyOps<KeyX>::lowest();
                 if (my_row < p.n && kappa >= theta) {
-                    float sb, dotf; int idot, inorm;
-                    replay_row(reinterpret_cast<const uint8_t*>(p.rows) + (size_t)my_row * ((size_t)p.pitch16 * 16), p.qbytes,
-                               p.dim, sh.lut, sb, dotf, idot, inorm);
-                    float dist = ref_distance(qh.sa, sb, dotf);
+                    const ReplayOut ro = replay_row<false>(reinterpret_cast<const uint8_t*>(p.rows) + (size_t)my_row * ((size_t)p.pitch16 * 16),
+                                                           p.qbytes, p.q16, p.dim, qh.sum_cq, sh.lut);
+                    float dist = ref_distance(qh.sa, ro.sb, ro.dot);
                     if ((double)dist < p.max_dist) {
                         key = make_keyx(dist, __ldg(p.ids + my_row), my_row);
                         pass = keyx_gt(key, tau);
