@@ -43,7 +43,7 @@ extern "C" {
 #define PBX_E_K (-7)           /* k > PBX_MAX_K                                                  */
 #define PBX_E_INTERNAL (-8)    /* an internal invariant failed (a bug; never a silent wrong answer) */
 
-#define PBX_MAX_DIM 16384u
+#define PBX_MAX_DIM 4096u
 #define PBX_MAX_K 2048u
 #define PBX_MAX_ROWS 0xFFFFFFF0ull
 #define PBX_MAX_SHARDS 64u

@@ -18,7 +18,7 @@ ERROR_NAMES = {
     -1: "PBX_E_INVALID", -2: "PBX_E_DIM", -3: "PBX_E_OOM", -4: "PBX_E_CUDA", -5: "PBX_E_NO_DEVICE",
     -6: "PBX_E_CAPACITY", -7: "PBX_E_K", -8: "PBX_E_INTERNAL",
 }
-PBX_MAX_DIM = 16384
+PBX_MAX_DIM = 4096
 PBX_MAX_K = 2048
 DEFAULT_MAX_DIST = 1e3   # DEFAULT_MAX_QUERY_DISTANCE, src/engine.rs:23
 DEFAULT_K = 100          # the literal LIMIT of src/engine.rs:381

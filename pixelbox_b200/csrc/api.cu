@@ -73,6 +73,7 @@ struct pbx_corpus {
     size_t cand_bytes = 0;
     uint32_t* d_cand_cnt = nullptr;
     uint32_t* d_tile_counter = nullptr;
+    uint32_t* d_hist = nullptr;       // kappa histogram of the scan CTAs' final lists (zeroed by the finalize kernel)
     unsigned long long* d_exact_passes = nullptr;
     // pinned staging
     uint8_t* h_queries = nullptr;
@@ -98,7 +99,7 @@ static uint32_t default_keep(uint32_t k, uint32_t slack) {
     uint32_t s = slack ? slack : std::max<uint32_t>(156u, k / 4u);
     uint32_t keep = k + s;
     if (!slack) keep = (keep + 31u) & ~31u;
-    return std::min<uint32_t>(keep, 4096u);
+    return std::min<uint32_t>(keep, kMaxKeep);
 }
 
 static float certificate_margin(uint32_t dim) {
@@ -270,6 +271,8 @@ extern "C" int pbx_corpus_create(uint32_t dim, uint64_t capacity_hint, int devic
     if (e == cudaSuccess) e = cudaMalloc(&c->d_cand_cnt, kMaxScanGrid * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_tile_counter, 256);
     if (e == cudaSuccess) e = cudaMemset(c->d_tile_counter, 0, 256);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_hist, kHistBins * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(c->d_hist, 0, kHistBins * sizeof(uint32_t));
     if (e == cudaSuccess) { c->d_exact_passes = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(c->d_tile_counter) + 128); }
     if (e != cudaSuccess) {
         int rc = fail(PBX_E_CUDA, "corpus setup failed: %s", cudaGetErrorString(e));
@@ -291,7 +294,7 @@ extern "C" void pbx_corpus_destroy(pbx_corpus* c) {
     cudaDeviceSynchronize();
     free_corpus_buffers(c);
     cudaFree(c->d_queries); cudaFree(c->d_q16); cudaFree(c->d_qbytes); cudaFree(c->d_qh); cudaFree(c->d_status);
-    cudaFree(c->d_hits); cudaFree(c->d_counts); cudaFree(c->d_cand); cudaFree(c->d_cand_cnt); cudaFree(c->d_tile_counter);
+    cudaFree(c->d_hits); cudaFree(c->d_counts); cudaFree(c->d_cand); cudaFree(c->d_cand_cnt); cudaFree(c->d_tile_counter); cudaFree(c->d_hist);
     cudaFreeHost(c->h_queries); cudaFreeHost(c->h_hits); cudaFreeHost(c->h_counts); cudaFreeHost(c->h_stage);
     if (c->ev_chain) cudaEventDestroy(c->ev_chain);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
@@ -501,7 +504,7 @@ static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, 
         int rc = ensure_query_scratch(c, nq);
         if (rc != PBX_OK) return rc;
         const int grid = scan_grid(c);
-        const uint32_t keep = std::min<uint32_t>(default_keep(k, c->slack), 4096u);
+        const uint32_t keep = std::min<uint32_t>(default_keep(k, c->slack), kMaxKeep);
         const uint32_t cap_scan = next_pow2(keep + kTileRows);
         const uint32_t cap_scan_x = next_pow2(k + kTileRows);
         // merge round size: one element per thread, more only when a round must span a complete rank (2 * grid)
@@ -511,8 +514,17 @@ static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, 
         rc = ensure_cand(c, (size_t)std::max<uint32_t>(keep, k) * grid * sizeof(KeyX));
         if (rc != PBX_OK) return rc;
         const float margin = certificate_margin(c->dim);
-        const size_t fin_main = (std::max<size_t>((size_t)cap_merge * sizeof(u64), (size_t)next_pow2(keep) * sizeof(RerankEntry) + (size_t)keep * 12) + 15) & ~(size_t)15;
-        const size_t fin_smem = fin_main + (size_t)c->pitch * 3;
+        // finalize kernel shared memory: [buf cap][sorted cap] (re-used for the (dist, id) sort) | per-candidate
+        // arrays | decoded + centred query | staged candidate rows
+        const size_t off_sorted = (size_t)cap_merge * sizeof(u64);
+        const size_t off_dots = 2 * off_sorted;
+        const size_t off_q = (off_dots + (size_t)keep * 20 + 15) & ~(size_t)15;
+        const size_t off_stage = (off_q + (size_t)c->pitch * 6 + 15) & ~(size_t)15;
+        const size_t fin_budget = 200 * 1024;
+        const size_t srow = (size_t)c->pitch + 16;
+        if (off_stage + srow > fin_budget) return fail(PBX_E_INTERNAL, "finalize layout does not fit shared memory (k=%u dim=%u)", k, c->dim);
+        const uint32_t stage_rows = (uint32_t)std::min<size_t>(keep, (fin_budget - off_stage) / srow);
+        const size_t fin_smem = off_stage + (size_t)stage_rows * srow;
         const size_t finx_smem = (size_t)cap_merge_x * sizeof(KeyX);
 
         prep_query_kernel<<<nq, 256, 0, s>>>(d_queries, c->dim, c->pitch, c->d_q16, c->d_qbytes, c->d_qh);
@@ -533,6 +545,7 @@ static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, 
             sp.cand = c->d_cand;
             sp.cand_cnt = c->d_cand_cnt;
             sp.tile_counter = c->d_tile_counter;
+            sp.hist = c->d_hist;
             sp.status = c->d_status + q;
             sp.max_dist = max_dist;
             const bool time_scan = timed && q + 1 == nq;
@@ -555,7 +568,13 @@ static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, 
             fp.qbytes = sp.qbytes;
             fp.q16 = sp.q16;
             fp.chunk = chunk;
-            fp.q_off = (uint32_t)fin_main;
+            fp.hist = c->d_hist;
+            fp.stage_rows = stage_rows;
+            fp.off_sorted = (uint32_t)off_sorted;
+            fp.off_ent = 0;
+            fp.off_dots = (uint32_t)off_dots;
+            fp.off_q = (uint32_t)off_q;
+            fp.off_stage = (uint32_t)off_stage;
             fp.qh = c->d_qh + q;
             fp.max_dist = max_dist;
             fp.margin = margin;

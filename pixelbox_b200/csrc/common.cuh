@@ -19,6 +19,8 @@ constexpr int kTileRows = kScanWarps * kRowsPerWarpIter * kItersPerTile;   // 10
 constexpr int kFinalThreads = 1024;
 constexpr int kMergeChunk = 4 * kFinalThreads;
 constexpr uint32_t kMaxScanGrid = 2048;
+constexpr uint32_t kHistBins = 16384;        // global histogram of candidate keys over kappa in [-1, 1]
+constexpr uint32_t kMaxKeep = 3072;          // candidates per query the finalize kernel's shared memory is laid out for
 
 // plateau value of the reference distance: 1/1e-6f - 1 evaluated in f32 (src/engine.rs:587)
 #define PBX_PLATEAU_DIST 999999.0f
@@ -88,6 +90,12 @@ __device__ __forceinline__ float ref_distance(float sa, float sb, float dot) {
 
 // exact integer centring c(v) = 2v - 255
 __device__ __host__ __forceinline__ int centre(uint32_t v) { return 2 * (int)v - 255; }
+
+// monotone map of the ranking key to a histogram bin (bin width 2^-13 in cosine)
+__device__ __forceinline__ uint32_t kappa_bin(float kappa) {
+    int b = __float2int_rd((kappa + 1.0f) * (float)(kHistBins / 2));
+    return (uint32_t)min(max(b, 0), (int)kHistBins - 1);
+}
 
 // ---- candidate keys ----------------------------------------------------------------------
 // fast pass: 64-bit key, larger is better: (ord(kappa) << 32) | ~row  (higher cosine first, then lower row)

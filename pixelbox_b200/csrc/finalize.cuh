@@ -5,6 +5,7 @@
 // limit), :572-588 (distance), :608-622 (f32 -> f64 widening before the comparison).
 #pragma once
 #include "scan.cuh"
+#include "rerank.cuh"
 #include "../../include/pixelbox_b200.h"
 
 namespace pbx {
@@ -91,226 +92,6 @@ __global__ void synth_fill_kernel(uint8_t* __restrict__ rows, uint32_t pitch, ui
         else if (b0 + 8 > dim) x &= (~0ull) >> (8 * (b0 + 8 - dim));
         *reinterpret_cast<u64*>(rows + (dst_row0 + r) * pitch + b0) = x;
         if (c == 0) ids[dst_row0 + r] = (int64_t)(grow + 1);
-    }
-}
-
-// ---- merge + kernel C ----------------------------------------------------------------------------
-struct FinalizeParams {
-    const u64* cand;            // [keep][grid] rank-major, each CTA list sorted best first
-    const uint32_t* cand_cnt;   // [grid]
-    uint32_t grid;              // scan CTAs
-    uint32_t keep;              // k + slack
-    uint32_t cap;               // merge buffer capacity: power of two >= keep + kMergeChunk
-    uint32_t k;
-    uint32_t n;                 // rows searched
-    uint32_t dim;
-    uint32_t pitch;             // bytes
-    const uint8_t* rows;
-    const int64_t* ids;
-    const uint8_t* qbytes;      // this query, padded
-    const int16_t* q16;         // this query, centred, padded
-    QueryHeader* qh;            // sa is filled in here
-    uint32_t chunk;             // merge elements per round: a multiple of kFinalThreads, >= 2 * grid when possible
-    uint32_t q_off;             // byte offset of the staged query inside dynamic shared memory
-    double max_dist;
-    float margin;               // certificate margin on kappa
-    pbx_hit* hits;              // [k] this query
-    uint32_t* count;            // this query
-    SearchStatus* status;       // this query
-    uint32_t* tile_counter;     // reset for the next scan
-};
-
-struct RerankEntry {            // sort record of kernel C: (ord(dist), image_id) ascending
-    uint32_t od;
-    uint32_t slot;
-    int64_t id;
-};
-__device__ __forceinline__ bool rerank_before(const RerankEntry& a, const RerankEntry& b) {
-    if (a.od != b.od) return a.od < b.od;
-    if (a.id != b.id) return a.id < b.id;
-    return a.slot < b.slot;
-}
-__device__ void block_sort_rerank(RerankEntry* e, uint32_t n2) {
-    for (uint32_t k = 2; k <= n2; k <<= 1)
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
-                uint32_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;
-                bool asc = (lo & k) == 0;
-                RerankEntry a = e[lo], b = e[hi];
-                if (rerank_before(b, a) == asc) { e[lo] = b; e[hi] = a; }
-            }
-            __syncthreads();
-        }
-}
-
-// shared memory layout (dynamic): [cap] u64 merge buffer, later reused:
-//   RerankEntry ent[n2] | int dots[keep] | int norms[keep] | float dists[keep]
-__global__ void __launch_bounds__(kFinalThreads, 1)
-finalize_kernel(const FinalizeParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64* buf = reinterpret_cast<u64*>(smem_raw);
-    __shared__ uint32_t s_cnt, s_pushed, s_maxcnt, s_nonplateau;
-    __shared__ u64 s_tau;
-    __shared__ float s_lut[256];
-    __shared__ float s_kappa_k, s_kappa_last;
-    __shared__ uint32_t s_listcnt[kMaxScanGrid];
-
-    // the query is staged once: raw bytes for the f32 replay, centred s16 for the exact integers
-    uint8_t* s_q = smem_raw + p.q_off;
-    int16_t* s_q16 = reinterpret_cast<int16_t*>(smem_raw + p.q_off + p.pitch);
-    for (uint32_t i = threadIdx.x; i < p.pitch / 16; i += blockDim.x)
-        reinterpret_cast<uint4*>(s_q)[i] = __ldg(reinterpret_cast<const uint4*>(p.qbytes) + i);
-    for (uint32_t i = threadIdx.x; i < p.pitch / 8; i += blockDim.x)
-        reinterpret_cast<uint4*>(s_q16)[i] = __ldg(reinterpret_cast<const uint4*>(p.q16) + i);
-    if (threadIdx.x < 256) s_lut[threadIdx.x] = ref_decode(threadIdx.x);
-    if (threadIdx.x == 0) { s_cnt = 0; s_tau = 0ull; s_maxcnt = 0; s_nonplateau = 0; s_pushed = 0; }
-    __syncthreads();
-    const int sum_cq = p.qh->sum_cq;
-    for (uint32_t b = threadIdx.x; b < p.grid; b += blockDim.x) {
-        uint32_t c = p.cand_cnt[b];
-        s_listcnt[b] = c;
-        atomicMax(&s_maxcnt, c);
-    }
-    __syncthreads();
-
-    // ---- merge: best `keep` of the union of the CTA lists.  Elements are visited rank-major, so
-    // the strongest entries of every list come first and the threshold tightens immediately.
-    TopBuf<u64> tb{buf, &s_cnt, &s_tau, p.cap, p.keep};
-    const uint32_t total = s_maxcnt * p.grid;
-    for (uint32_t base = 0; base < total; base += p.chunk) {
-        if (s_cnt + p.chunk > p.cap) tb.compact();          // uniform (read after a barrier)
-        const u64 tau = s_tau;
-        __syncthreads();
-        if (threadIdx.x == 0) s_pushed = 0;
-        __syncthreads();
-        bool any = false;
-        for (uint32_t x = 0; x < p.chunk / kFinalThreads; ++x) {
-            const uint32_t e = base + x * kFinalThreads + threadIdx.x;
-            bool pass = false;
-            u64 key = 0;
-            if (e < total) {
-                const uint32_t rank = e / p.grid, b = e - rank * p.grid;
-                if (rank < s_listcnt[b]) { key = p.cand[e]; pass = key > tau; }
-            }
-            tb.push_warp(pass, key);
-            any |= pass;
-        }
-        if (any) s_pushed = 1;
-        __syncthreads();
-        // lists are sorted: a chunk that spans at least one complete rank and pushed nothing
-        // proves every remaining element is below the threshold
-        if (s_pushed == 0 && p.chunk >= 2 * p.grid) break;
-    }
-    __syncthreads();
-    tb.compact();
-    const uint32_t nc = s_cnt < p.keep ? s_cnt : p.keep;     // candidates, sorted by (kappa desc, row asc)
-    if (threadIdx.x == 0) {
-        s_kappa_k = (nc >= p.k && p.k > 0) ? key64_kappa(buf[p.k - 1]) : 0.0f;
-        s_kappa_last = nc > 0 ? key64_kappa(buf[nc - 1]) : 0.0f;
-    }
-    __syncthreads();
-
-    // ---- kernel C: replay the reference arithmetic on the candidates -----------------------------
-    // candidate rows move to registers before the buffer is reused
-    uint32_t my_rows[4];
-    const uint32_t per = (nc + kFinalThreads - 1) / kFinalThreads;     // <= 4 for keep <= 4096
-#pragma unroll
-    for (int x = 0; x < 4; ++x) {
-        uint32_t c = threadIdx.x + x * kFinalThreads;
-        my_rows[x] = (c < nc) ? key64_row(buf[c]) : 0xFFFFFFFFu;
-    }
-    __syncthreads();
-    const uint32_t n2 = next_pow2(nc < 2 ? 2 : nc);
-    RerankEntry* ent = reinterpret_cast<RerankEntry*>(smem_raw);
-    int* dots = reinterpret_cast<int*>(smem_raw + (size_t)n2 * sizeof(RerankEntry));
-    int* norms = dots + p.keep;
-    float* dists = reinterpret_cast<float*>(norms + p.keep);
-
-    // the query's own norm fold (engine.rs:580) by the last thread, which rarely owns a candidate
-    if (threadIdx.x == kFinalThreads - 1) {
-        float sa = 0.0f;
-        for (uint32_t i = 0; i < p.dim; ++i) { float a = s_lut[s_q[i]]; sa = ref_fold(sa, a, a); }
-        p.qh->sa = sa;
-    }
-    float my_sb[4], my_dot[4];
-#pragma unroll
-    for (int x = 0; x < 4; ++x) {
-        if (x < (int)per && my_rows[x] != 0xFFFFFFFFu) {
-            const ReplayOut ro = replay_row<true>(p.rows + (size_t)my_rows[x] * p.pitch, s_q, s_q16, p.dim, sum_cq, s_lut);
-            my_sb[x] = ro.sb;
-            my_dot[x] = ro.dot;
-            uint32_t c = threadIdx.x + x * kFinalThreads;
-            dots[c] = ro.idot;
-            norms[c] = ro.inorm;
-        }
-    }
-    __threadfence_block();
-    __syncthreads();
-    const float sa = p.qh->sa;
-    uint32_t nonplateau = 0;
-#pragma unroll
-    for (int x = 0; x < 4; ++x) {
-        uint32_t c = threadIdx.x + x * kFinalThreads;
-        if (x < (int)per && my_rows[x] != 0xFFFFFFFFu) {
-            float dist = ref_distance(sa, my_sb[x], my_dot[x]);
-            dists[c] = dist;
-            RerankEntry e;
-            e.od = ord_f32(dist);
-            e.slot = c;
-            e.id = p.ids[my_rows[x]];
-            ent[c] = e;
-            if (dist < PBX_PLATEAU_DIST) nonplateau++;
-        }
-    }
-    for (uint32_t c = nc + threadIdx.x; c < n2; c += blockDim.x) {
-        RerankEntry e; e.od = 0xFFFFFFFFu; e.slot = 0xFFFFFFFFu; e.id = INT64_MAX;
-        ent[c] = e;
-    }
-    if (nonplateau) atomicAdd(&s_nonplateau, nonplateau);
-    __syncthreads();
-    block_sort_rerank(ent, n2);
-
-    // ---- WHERE dist < ? ORDER BY dist ASC LIMIT k  (engine.rs:379-381) ----------------------------
-    // ascending order makes the passing rows a prefix
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
-    uint32_t local = 0;
-    for (uint32_t c = threadIdx.x; c < nc; c += blockDim.x) {
-        const RerankEntry e = ent[c];
-        const float dist = dists[e.slot];
-        const bool ok = (double)dist < p.max_dist;
-        if (ok) local++;
-        if (c < p.k) {
-            pbx_hit h;
-            if (ok) { h.image_id = e.id; h.dist = dist; h.dot = dots[e.slot]; h.norm2 = norms[e.slot]; h.flags = 0; }
-            else { h.image_id = INT64_MAX; h.dist = __int_as_float(0x7f800000); h.dot = 0; h.norm2 = 0; h.flags = 0; }
-            p.hits[c] = h;
-        }
-    }
-    for (uint32_t c = nc + threadIdx.x; c < p.k; c += blockDim.x) {
-        pbx_hit h; h.image_id = INT64_MAX; h.dist = __int_as_float(0x7f800000); h.dot = 0; h.norm2 = 0; h.flags = 0;
-        p.hits[c] = h;
-    }
-    if (local) atomicAdd(&s_cnt, local);
-    __syncthreads();
-
-    // ---- certificate ---------------------------------------------------------
-    if (threadIdx.x == 0) {
-        const uint32_t passing = s_cnt;
-        *p.count = passing < p.k ? passing : p.k;
-        SearchStatus st;
-        st.n_candidates = nc;
-        st.reserved = 0;
-        st.need_exact = 0;
-        st.theta = 0.0f;
-        if (p.n > nc) {                                   // some rows are not candidates
-            const bool plateau_reachable = p.max_dist > (double)PBX_PLATEAU_DIST && s_nonplateau < p.k;
-            const bool separated = (double)s_kappa_last < (double)s_kappa_k - (double)p.margin;
-            if (plateau_reachable) { st.need_exact = 1; st.theta = -__int_as_float(0x7f800000); }
-            else if (!separated) { st.need_exact = 1; st.theta = (float)((double)s_kappa_k - (double)p.margin - 1e-7); }
-        }
-        *p.status = st;
-        *p.tile_counter = 0;
     }
 }
 

@@ -1,0 +1,395 @@
+// rerank.cuh -- the tail of a fast-pass search, one CTA:
+//   1. merge: the best `keep` keys of the union of the per-CTA candidate lists.  The scan CTAs add
+//      their final lists to a global histogram over kappa; a suffix scan of it gives the bin b*
+//      at which `keep` candidates are reached, every list contributes its (sorted) prefix with
+//      bin >= b*, and the few hundred survivors are ordered by rank counting -- no barriers in the
+//      sort, no passes over the 75k list entries.  Pathologically tied corpora (one bin holding
+//      more than the buffer) fall back to threshold rounds over the rank-major lists.
+//   2. kernel C: bit-exact f32 replay of the reference distance (src/engine.rs:572-588) for every
+//      candidate: rows are staged in shared memory by all threads (one DRAM round trip), then one
+//      thread per candidate folds its row strictly in element order.
+//   3. ORDER BY dist ASC with ties by image_id, WHERE dist < max_dist, LIMIT k
+//      (src/engine.rs:379-381), and the certificate that decides whether the exact pass runs.
+#pragma once
+#include "scan.cuh"
+#include "../../include/pixelbox_b200.h"
+
+namespace pbx {
+
+struct FinalizeParams {
+    const u64* cand;            // [keep][grid] rank-major, each CTA list sorted best first
+    const uint32_t* cand_cnt;   // [grid]
+    uint32_t* hist;             // [kHistBins] counts of the final list entries per kappa bin (zeroed here)
+    uint32_t grid;              // scan CTAs
+    uint32_t keep;              // k + slack
+    uint32_t cap;               // key buffer capacity: power of two >= keep + chunk
+    uint32_t chunk;             // fallback merge: elements per round, a multiple of kFinalThreads
+    uint32_t k;
+    uint32_t n;                 // rows searched
+    uint32_t dim;
+    uint32_t pitch;             // bytes
+    uint32_t stage_rows;        // candidate rows staged in shared memory per batch
+    uint32_t off_sorted;        // byte offsets into dynamic shared memory
+    uint32_t off_ent, off_dots, off_q, off_stage;
+    const uint8_t* rows;
+    const int64_t* ids;
+    const uint8_t* qbytes;      // this query, padded
+    const int16_t* q16;         // this query, centred, padded
+    QueryHeader* qh;            // sa is filled in here
+    double max_dist;
+    float margin;               // certificate margin on kappa
+    pbx_hit* hits;              // [k] this query
+    uint32_t* count;            // this query
+    SearchStatus* status;       // this query
+    uint32_t* tile_counter;     // reset for the next scan
+};
+
+struct RerankEntry {            // sort record of kernel C: (ord(dist), image_id) ascending
+    uint32_t od;
+    uint32_t slot;
+    int64_t id;
+};
+__device__ __forceinline__ bool rerank_before(const RerankEntry& a, const RerankEntry& b) {
+    if (a.od != b.od) return a.od < b.od;
+    if (a.id != b.id) return a.id < b.id;
+    return a.slot < b.slot;
+}
+__device__ inline void block_sort_rerank(RerankEntry* e, uint32_t n2) {
+    for (uint32_t k = 2; k <= n2; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+                uint32_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;
+                bool asc = (lo & k) == 0;
+                RerankEntry a = e[lo], b = e[hi];
+                if (rerank_before(b, a) == asc) { e[lo] = b; e[hi] = a; }
+            }
+            __syncthreads();
+        }
+}
+
+// Fallback merge: threshold rounds over the rank-major lists (strongest entries of every list first).
+__device__ inline void merge_rounds(const FinalizeParams& p, TopBuf<u64>& tb, const uint32_t* s_listcnt, uint32_t maxcnt,
+                                    uint32_t* s_pushed) {
+    const uint32_t total = maxcnt * p.grid;
+    for (uint32_t base = 0; base < total; base += p.chunk) {
+        if (*tb.cnt + p.chunk > p.cap) tb.compact();        // uniform (read after a barrier)
+        const u64 tau = *tb.tau;
+        __syncthreads();
+        if (threadIdx.x == 0) *s_pushed = 0;
+        __syncthreads();
+        bool any = false;
+        for (uint32_t x = 0; x < p.chunk / kFinalThreads; ++x) {
+            const uint32_t e = base + x * kFinalThreads + threadIdx.x;
+            bool pass = false;
+            u64 key = 0;
+            if (e < total) {
+                const uint32_t rank = e / p.grid, b = e - rank * p.grid;
+                if (rank < s_listcnt[b]) { key = p.cand[e]; pass = key > tau; }
+            }
+            tb.push_warp(pass, key);
+            any |= pass;
+        }
+        if (any) *s_pushed = 1;
+        __syncthreads();
+        // lists are sorted: a round that spans a complete rank and pushed nothing ends the merge
+        if (*s_pushed == 0 && p.chunk >= 2 * p.grid) break;
+    }
+    __syncthreads();
+    tb.compact();
+}
+
+// 16 staged row bytes against 16 decoded query floats, strictly in element order
+__device__ __forceinline__ void fold16(const uint4& v, const float* qa, const float* lut, float& s, float& d) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(qa + 4 * i);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const float fb = lut[(w[i] >> (8 * b)) & 255u];
+            s = ref_fold(s, fb, fb);
+            d = ref_fold(d, av[b], fb);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kFinalThreads, 1)
+finalize_kernel(const FinalizeParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64* buf = reinterpret_cast<u64*>(smem_raw);                                   // [cap]
+    u64* sorted = reinterpret_cast<u64*>(smem_raw + p.off_sorted);                 // [cap]
+    RerankEntry* ent = reinterpret_cast<RerankEntry*>(smem_raw + p.off_ent);       // [next_pow2(keep)]
+    int* dots = reinterpret_cast<int*>(smem_raw + p.off_dots);                     // [keep]
+    int* norms = dots + p.keep;
+    float* dists = reinterpret_cast<float*>(norms + p.keep);
+    float* sbs = dists + p.keep;
+    float* fdots = sbs + p.keep;
+    float* s_qa = reinterpret_cast<float*>(smem_raw + p.off_q);                    // [pitch] decoded query
+    int16_t* s_q16 = reinterpret_cast<int16_t*>(smem_raw + p.off_q + 4 * p.pitch); // [pitch] centred query
+    unsigned char* stage = smem_raw + p.off_stage;                                 // [stage_rows][pitch + 16]
+
+    __shared__ uint32_t s_cnt, s_pushed, s_maxcnt, s_nonplateau, s_bstar, s_mprime, s_total;
+    __shared__ u64 s_tau;
+    __shared__ float s_lut[256];
+    __shared__ float s_kappa_k, s_kappa_last, s_sa;
+    __shared__ uint32_t s_listcnt[kMaxScanGrid];
+    __shared__ uint32_t s_warp[32];
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 256) s_lut[tid] = ref_decode(tid);
+    if (tid == 0) { s_cnt = 0; s_tau = 0ull; s_maxcnt = 0; s_nonplateau = 0; s_pushed = 0; s_bstar = 0; s_mprime = 0; }
+    for (uint32_t i = tid; i < p.pitch / 8; i += blockDim.x)
+        reinterpret_cast<uint4*>(s_q16)[i] = __ldg(reinterpret_cast<const uint4*>(p.q16) + i);
+    __syncthreads();
+    for (uint32_t i = tid; i < p.pitch; i += blockDim.x) s_qa[i] = s_lut[p.qbytes[i]];
+    for (uint32_t b = tid; b < p.grid; b += blockDim.x) {
+        uint32_t c = p.cand_cnt[b];
+        s_listcnt[b] = c;
+        atomicMax(&s_maxcnt, c);
+    }
+
+    // ---- 1a. histogram suffix scan: b* = highest bin with at least `keep` entries at or above it -------
+    constexpr uint32_t BPT = kHistBins / kFinalThreads;            // bins per thread (16)
+    uint32_t h[BPT];
+    {
+        uint4* hp = reinterpret_cast<uint4*>(p.hist) + (size_t)tid * (BPT / 4);
+#pragma unroll
+        for (uint32_t i = 0; i < BPT / 4; ++i) {
+            const uint4 v = hp[i];
+            h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w;
+            hp[i] = make_uint4(0, 0, 0, 0);                        // ready for the next query
+        }
+    }
+    uint32_t mine = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < BPT; ++i) mine += h[i];
+    // inclusive suffix sum over threads (thread t covers bins [t*BPT, (t+1)*BPT)): above = entries in higher threads
+    uint32_t incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        uint32_t v = __shfl_down_sync(0xFFFFFFFFu, incl, off);
+        if (lane + off < 32) incl += v;
+    }
+    if (lane == 0) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t above = incl - mine;
+    for (uint32_t w = warp + 1; w < kFinalThreads / 32; ++w) above += s_warp[w];
+    if (tid == 0) { uint32_t t = 0; for (uint32_t w = 0; w < kFinalThreads / 32; ++w) t += s_warp[w]; s_total = t; }
+    if (above < p.keep && above + mine >= p.keep) {                // the crossing bin is one of mine
+        uint32_t run = above;
+#pragma unroll
+        for (int i = BPT - 1; i >= 0; --i) {
+            run += h[i];
+            if (run >= p.keep) { s_bstar = tid * BPT + i; s_mprime = run; break; }
+        }
+    }
+    __syncthreads();
+    if (s_total < p.keep && tid == 0) { s_bstar = 0; s_mprime = s_total; }   // fewer entries than keep: take everything
+    __syncthreads();
+
+    uint32_t nc;
+    const uint32_t mprime = s_mprime, bstar = s_bstar;
+    if (mprime <= p.cap) {
+        // ---- 1b. gather the list prefixes with bin >= b* ---------------------------------------------
+        for (uint32_t b = tid; b < p.grid; b += blockDim.x) {
+            const uint32_t len = s_listcnt[b];
+            for (uint32_t r0 = 0; r0 < len; r0 += 4) {
+                u64 key[4];
+#pragma unroll
+                for (uint32_t i = 0; i < 4; ++i) key[i] = (r0 + i < len) ? p.cand[(size_t)(r0 + i) * p.grid + b] : 0ull;
+                uint32_t take = 0;
+#pragma unroll
+                for (uint32_t i = 0; i < 4; ++i)
+                    if (take == i && r0 + i < len && kappa_bin(key64_kappa(key[i])) >= bstar) take = i + 1;
+                if (take) {
+                    const uint32_t at = atomicAdd(&s_cnt, take);
+#pragma unroll
+                    for (uint32_t i = 0; i < 4; ++i) if (i < take) buf[at + i] = key[i];
+                }
+                if (take < 4) break;
+            }
+        }
+        __syncthreads();
+        const uint32_t m = s_cnt;                                   // == mprime
+        // ---- 1c. order by key: rank counting when small (no barriers), bitonic otherwise ----------------
+        if (m <= 2 * kFinalThreads) {
+            for (uint32_t t = tid; t < m; t += blockDim.x) {
+                const u64 me = buf[t];
+                uint32_t rank = 0;
+                for (uint32_t j = 0; j < m; ++j) rank += (buf[j] > me) ? 1u : 0u;
+                sorted[rank] = me;
+            }
+            __syncthreads();
+        } else {
+            const uint32_t m2 = next_pow2(m);
+            for (uint32_t i = m + tid; i < m2; i += blockDim.x) buf[i] = 0ull;
+            __syncthreads();
+            block_sort_desc<u64>(buf, m2);
+            for (uint32_t i = tid; i < m; i += blockDim.x) sorted[i] = buf[i];
+            __syncthreads();
+        }
+        nc = m < p.keep ? m : p.keep;
+    } else {
+        // ---- 1'. fallback: more ties in one bin than the buffer holds ----------------------------------
+        TopBuf<u64> tb{buf, &s_cnt, &s_tau, p.cap, p.keep};
+        merge_rounds(p, tb, s_listcnt, s_maxcnt, &s_pushed);
+        nc = s_cnt < p.keep ? s_cnt : p.keep;
+        for (uint32_t i = tid; i < nc; i += blockDim.x) sorted[i] = buf[i];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        s_kappa_k = (nc >= p.k && p.k > 0) ? key64_kappa(sorted[p.k - 1]) : 0.0f;
+        s_kappa_last = nc > 0 ? key64_kappa(sorted[nc - 1]) : 0.0f;
+    }
+
+    // ---- 2. kernel C ------------------------------------------------------------------------------------
+    // the query's own norm fold (src/engine.rs:580) by one thread of the last warp
+    if (tid == kFinalThreads - 1) {
+        float sa = 0.0f;
+        for (uint32_t i = 0; i < p.dim; ++i) { const float a = s_qa[i]; sa = ref_fold(sa, a, a); }
+        s_sa = sa;
+        p.qh->sa = sa;
+    }
+    const uint32_t pitch16 = p.pitch / 16, srow = p.pitch + 16;     // staged row stride: odd number of 16-byte units
+    const uint32_t full = p.dim >> 4;
+    const int sum_cq = p.qh->sum_cq;
+    for (uint32_t c0 = 0; c0 < nc; c0 += p.stage_rows) {
+        const uint32_t cb = min(p.stage_rows, nc - c0);
+        // all threads: one 16-byte load per (candidate, chunk)
+        for (uint32_t e = tid; e < cb * pitch16; e += blockDim.x) {
+            const uint32_t ci = e / pitch16, ch = e - ci * pitch16;
+            const uint32_t row = key64_row(sorted[c0 + ci]);
+            *reinterpret_cast<uint4*>(stage + (size_t)ci * srow + 16 * ch) =
+                __ldg(reinterpret_cast<const uint4*>(p.rows + (size_t)row * p.pitch) + ch);
+        }
+        __syncthreads();
+        for (uint32_t ci = tid; ci < cb; ci += blockDim.x) {
+            const unsigned char* r = stage + (size_t)ci * srow;
+            float s = 0.0f, d = 0.0f;
+            int acc = 0;
+            unsigned s1 = 0, s2 = 0;
+            for (uint32_t ch = 0; ch < pitch16; ++ch) {
+                const uint4 v = *reinterpret_cast<const uint4*>(r + 16 * ch);
+                if (ch < full) {
+                    fold16(v, s_qa + 16 * ch, s_lut, s, d);
+                } else {                                            // ragged tail: dim is not a multiple of 16
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                    for (uint32_t i = 16 * ch; i < p.dim; ++i) {
+                        const uint32_t o = i - 16 * ch;
+                        const float fb = s_lut[(w[o >> 2] >> (8 * (o & 3))) & 255u];
+                        s = ref_fold(s, fb, fb);
+                        d = ref_fold(d, s_qa[i], fb);
+                    }
+                }
+                const int4 a = *reinterpret_cast<const int4*>(s_q16 + 16 * ch), b = *reinterpret_cast<const int4*>(s_q16 + 16 * ch + 8);
+                const int qq[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                acc = dot16(v, qq, acc);
+                s1 = dp4a_uu(v.x, 0x01010101u, s1); s1 = dp4a_uu(v.y, 0x01010101u, s1);
+                s1 = dp4a_uu(v.z, 0x01010101u, s1); s1 = dp4a_uu(v.w, 0x01010101u, s1);
+                s2 = dp4a_uu(v.x, v.x, s2); s2 = dp4a_uu(v.y, v.y, s2);
+                s2 = dp4a_uu(v.z, v.z, s2); s2 = dp4a_uu(v.w, v.w, s2);
+            }
+            sbs[c0 + ci] = s;
+            fdots[c0 + ci] = d;
+            dots[c0 + ci] = 2 * acc - 255 * sum_cq;
+            norms[c0 + ci] = (int)(4u * s2 - 1020u * s1 + 65025u * p.dim);
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    const float sa = s_sa;
+    const uint32_t n2 = next_pow2(nc < 2 ? 2 : nc);
+    uint32_t nonplateau = 0;
+    // ent overlays buf/sorted: fetch the image ids through `sorted` first, write ent after a barrier
+    int64_t my_id[kMaxKeep / kFinalThreads];
+#pragma unroll
+    for (uint32_t x = 0; x < kMaxKeep / kFinalThreads; ++x) {
+        const uint32_t c = tid + x * kFinalThreads;
+        my_id[x] = (c < nc) ? p.ids[key64_row(sorted[c])] : INT64_MAX;
+    }
+    __syncthreads();
+#pragma unroll
+    for (uint32_t x = 0; x < kMaxKeep / kFinalThreads; ++x) {
+        const uint32_t c = tid + x * kFinalThreads;
+        if (c < nc) {
+            const float dist = ref_distance(sa, sbs[c], fdots[c]);
+            dists[c] = dist;
+            RerankEntry e;
+            e.od = ord_f32(dist);
+            e.slot = c;
+            e.id = my_id[x];
+            ent[c] = e;
+            if (dist < PBX_PLATEAU_DIST) nonplateau++;
+        }
+    }
+    for (uint32_t c = nc + tid; c < n2; c += blockDim.x) {
+        RerankEntry e; e.od = 0xFFFFFFFFu; e.slot = 0xFFFFFFFFu; e.id = INT64_MAX;
+        ent[c] = e;
+    }
+    if (nonplateau) atomicAdd(&s_nonplateau, nonplateau);
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+
+    // ---- 3. ORDER BY dist ASC (ties by image_id), WHERE dist < ?, LIMIT k  (engine.rs:379-381) ---------
+    // `pos` = position of candidate c in the final order; ascending order makes the passing rows a prefix
+    uint32_t local = 0;
+    if (nc <= kFinalThreads) {
+        // rank counting: one candidate per thread, no barriers
+        if (tid < nc) {
+            const RerankEntry me = ent[tid];
+            uint32_t pos = 0;
+            for (uint32_t j = 0; j < nc; ++j) pos += rerank_before(ent[j], me) ? 1u : 0u;
+            const float dist = dists[tid];
+            const bool ok = (double)dist < p.max_dist;
+            if (ok) local = 1;
+            if (pos < p.k) {
+                pbx_hit hh;
+                if (ok) { hh.image_id = me.id; hh.dist = dist; hh.dot = dots[tid]; hh.norm2 = norms[tid]; hh.flags = 0; }
+                else { hh.image_id = INT64_MAX; hh.dist = __int_as_float(0x7f800000); hh.dot = 0; hh.norm2 = 0; hh.flags = 0; }
+                p.hits[pos] = hh;
+            }
+        }
+    } else {
+        block_sort_rerank(ent, n2);
+        for (uint32_t c = tid; c < nc; c += blockDim.x) {
+            const RerankEntry e = ent[c];
+            const float dist = dists[e.slot];
+            const bool ok = (double)dist < p.max_dist;
+            if (ok) local++;
+            if (c < p.k) {
+                pbx_hit hh;
+                if (ok) { hh.image_id = e.id; hh.dist = dist; hh.dot = dots[e.slot]; hh.norm2 = norms[e.slot]; hh.flags = 0; }
+                else { hh.image_id = INT64_MAX; hh.dist = __int_as_float(0x7f800000); hh.dot = 0; hh.norm2 = 0; hh.flags = 0; }
+                p.hits[c] = hh;
+            }
+        }
+    }
+    for (uint32_t c = nc + tid; c < p.k; c += blockDim.x) {
+        pbx_hit hh; hh.image_id = INT64_MAX; hh.dist = __int_as_float(0x7f800000); hh.dot = 0; hh.norm2 = 0; hh.flags = 0;
+        p.hits[c] = hh;
+    }
+    if (local) atomicAdd(&s_cnt, local);
+    __syncthreads();
+
+    // ---- certificate ------------------------------------------------------------------
+    if (tid == 0) {
+        const uint32_t passing = s_cnt;
+        *p.count = passing < p.k ? passing : p.k;
+        SearchStatus st;
+        st.n_candidates = nc;
+        st.reserved = 0;
+        st.need_exact = 0;
+        st.theta = 0.0f;
+        if (p.n > nc) {                                   // some rows are not candidates
+            const bool plateau_reachable = p.max_dist > (double)PBX_PLATEAU_DIST && s_nonplateau < p.k;
+            const bool separated = (double)s_kappa_last < (double)s_kappa_k - (double)p.margin;
+            if (plateau_reachable) { st.need_exact = 1; st.theta = -__int_as_float(0x7f800000); }
+            else if (!separated) { st.need_exact = 1; st.theta = (float)((double)s_kappa_k - (double)p.margin - 1e-7); }
+        }
+        *p.status = st;
+        *p.tile_counter = 0;
+    }
+}
+
+}  // namespace pbx

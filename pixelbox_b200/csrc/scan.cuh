@@ -50,6 +50,7 @@ struct ScanParams {
     void* cand;                 // [keep][grid] keys, rank-major (u64 or KeyX)
     uint32_t* cand_cnt;         // [grid]
     uint32_t* tile_counter;     // dynamic tile scheduler (reset by the finalize kernel)
+    uint32_t* hist;             // [kHistBins] fast pass: kappa histogram of the final lists (merge threshold)
     const SearchStatus* status; // EXACT only
     double max_dist;            // EXACT only
 };
@@ -258,7 +259,10 @@ scan_kernel(const ScanParams p) {
     tb.compact();
     const uint32_t c = sh.cnt < p.keep ? sh.cnt : p.keep;
     K* out = reinterpret_cast<K*>(p.cand);
-    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) out[(size_t)i * gridDim.x + blockIdx.x] = buf[i];
+    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
+        out[(size_t)i * gridDim.x + blockIdx.x] = buf[i];
+        if constexpr (!EXACT) atomicAdd(p.hist + kappa_bin(key64_kappa(buf[i])), 1u);
+    }
     if (threadIdx.x == 0) p.cand_cnt[blockIdx.x] = c;
 }
 
@@ -330,7 +334,10 @@ scan_generic_kernel(const ScanParams p) {
     tb.compact();
     const uint32_t c = sh.cnt < p.keep ? sh.cnt : p.keep;
     K* out = reinterpret_cast<K*>(p.cand);
-    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) out[(size_t)i * gridDim.x + blockIdx.x] = buf[i];
+    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
+        out[(size_t)i * gridDim.x + blockIdx.x] = buf[i];
+        if constexpr (!EXACT) atomicAdd(p.hist + kappa_bin(key64_kappa(buf[i])), 1u);
+    }
     if (threadIdx.x == 0) p.cand_cnt[blockIdx.x] = c;
 }
 
