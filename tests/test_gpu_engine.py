@@ -1,0 +1,98 @@
+"""Drop-in check at the level the UI calls: the Engine mirror (GPU path) against the reference's
+verbatim SQL executed by SQLite with the oracle UDF (tests/sqlite_oracle.py) on the same DB file."""
+import numpy as np
+import pytest
+
+from pixelbox_b200.engine import Engine, IndexedImage
+from tests import sqlite_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _corpus(seed, n, d):
+    rng = np.random.default_rng(seed)
+    cent = rng.integers(0, 256, size=(30, d))
+    rows = np.clip(cent[rng.integers(0, 30, n)] + rng.integers(-3, 4, size=(n, d)), 0, 255).astype(np.uint8)
+    rows[10:70] = rows[10]                      # ties, ordered by image_id in SQLite
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    return ids, rows, rng
+
+
+@pytest.mark.parametrize("d", [8, 256])
+def test_query_by_image_hash_matches_verbatim_sql(tmp_path, d):
+    ids, rows, rng = _corpus(1, 4000, d)
+    path = str(tmp_path / "pixelbox.db")
+    conn = sqlite_oracle.make_db(path, ids, rows)
+    eng = Engine.open(path)
+    try:
+        assert len(eng.corpus) == len(ids)
+        for md in (1e3, 0.05):
+            eng.max_distance_from_query = md
+            for q in (rows[10], rows[2500], rng.integers(0, 256, d, dtype=np.uint8)):
+                # right-click "Search for Similar": the query is an IndexedImage carrying a stored hash (src/ui/search.rs:82-84)
+                eng.query_by_image_hash_from_image(IndexedImage(visual_hash=bytes(q)))
+                got = eng.get_query_results()
+                want = sqlite_oracle.query(conn, bytes(q), md, 100)       # LIMIT 100, src/engine.rs:381
+                assert [g.id for g in got] == [w[0] for w in want]
+                assert [g.distance_from_query for g in got] == [w[1] for w in want]   # f64 equality: same f32 widened
+                for g in got[:5]:
+                    assert g.visual_hash == bytes(rows[g.id - 1]) and g.filename == f"img{g.id}.png"
+        # missing hash: silent return, results untouched (src/engine.rs:364-368)
+        before = eng.get_query_results()
+        eng.query_by_image_hash_from_image(IndexedImage(visual_hash=None))
+        assert [g.id for g in eng.get_query_results()] == [g.id for g in before]
+        eng.clear_query_results()
+        assert eng.get_query_results() is None
+    finally:
+        eng.close()
+        conn.close()
+
+
+def test_insert_appends_only_changed_rows(tmp_path):
+    path = str(tmp_path / "new.db")
+    eng = Engine.new(path)
+    try:
+        rng = np.random.default_rng(2)
+        hashes = rng.integers(0, 256, size=(300, 64), dtype=np.uint8)
+        for i, h in enumerate(hashes):
+            eng.insert_image_from_memory(IndexedImage(filename=f"f{i}.png", path=f"/p/f{i}.png", resolution=(4, 4),
+                                                      thumbnail=b"\x00", visual_hash=bytes(h)))
+        assert len(eng.corpus) == 300
+        # duplicate path: INSERT OR IGNORE keeps the old row, last_insert_rowid is stale, nothing is appended (src/engine.rs:231-256)
+        eng.insert_image_from_memory(IndexedImage(filename="f7.png", path="/p/f7.png", resolution=(4, 4), thumbnail=b"\x00",
+                                                  visual_hash=bytes(hashes[8])))
+        assert len(eng.corpus) == 300
+        conn = sqlite_oracle.sqlite3.connect(path)
+        sqlite_oracle.register(conn)
+        assert conn.execute("SELECT COUNT(*) FROM semantic_hashes").fetchone()[0] == 300
+        eng.query_by_image_hash_from_image(IndexedImage(visual_hash=bytes(hashes[8])))
+        got = eng.get_query_results()
+        want = sqlite_oracle.query(conn, bytes(hashes[8]), 1e3, 100)
+        assert [g.id for g in got] == [w[0] for w in want] and got[0].id == 9
+        assert [g.distance_from_query for g in got] == [w[1] for w in want]
+        conn.close()
+        # re-open: the corpus is rebuilt from the table (the SQLite file is the durable state)
+        eng.close()
+        eng = Engine.open(path)
+        assert len(eng.corpus) == 300
+    finally:
+        eng.close()
+
+
+def test_hash_without_image_row_is_dropped_like_the_inner_join(tmp_path):
+    ids, rows, _ = _corpus(3, 500, 16)
+    path = str(tmp_path / "orphan.db")
+    conn = sqlite_oracle.make_db(path, ids, rows)
+    conn.execute("DELETE FROM images WHERE id IN (11, 12, 13)")
+    conn.commit()
+    eng = Engine.open(path)
+    try:
+        eng.query_by_image_hash_from_image(IndexedImage(visual_hash=bytes(rows[10])))
+        got = [g.id for g in eng.get_query_results()]
+        assert 11 not in got and 12 not in got and 13 not in got
+        want = sqlite_oracle.query(conn, bytes(rows[10]), 1e3, 100)
+        # upstream applies LIMIT after the join; the mirror over-fetches to fill the list the same way
+        assert got == [w[0] for w in want]
+    finally:
+        eng.close()
+        conn.close()
