@@ -14,8 +14,10 @@ typedef unsigned long long u64;
 constexpr int kScanThreads = 256;            // 8 warps per scan CTA
 constexpr int kScanWarps = kScanThreads / 32;
 constexpr int kRowsPerWarpIter = 32;         // every warp iteration yields one row result per lane
-constexpr int kItersPerTile = 4;             // warp iterations between two CTA-wide barriers
-constexpr int kTileRows = kScanWarps * kRowsPerWarpIter * kItersPerTile;   // 1024 rows
+constexpr int kItersPerTile = 4;             // generic kernel: warp iterations between two CTA-wide barriers
+constexpr int kItersPerChunk = 4;            // fast kernel: warp iterations per claimed chunk
+constexpr int kChunkRows = kRowsPerWarpIter * kItersPerChunk;              // 128 rows per warp claim
+constexpr int kTileRows = kScanWarps * kRowsPerWarpIter * kItersPerTile;   // 1024 rows: push headroom of a CTA
 constexpr int kFinalThreads = 1024;
 constexpr int kMergeChunk = 4 * kFinalThreads;
 constexpr uint32_t kMaxScanGrid = 2048;

@@ -160,7 +160,8 @@ __device__ __forceinline__ ReplayOut replay_row(const uint8_t* __restrict__ row,
 template <typename K, bool EXACT>
 struct ScanShared {
     uint32_t cnt;
-    uint32_t tile[2];           // double-buffered: the next tile index is fetched one tile ahead
+    uint32_t done;              // warps that have run out of work
+    uint32_t tile[2];           // generic kernel: tile index broadcast
     K tau;
     float lut[EXACT ? 256 : 1];
 };
@@ -197,62 +198,82 @@ scan_kernel(const ScanParams p) {
     float theta = 0.0f;
     if constexpr (EXACT) theta = p.status->theta;
 
-    if (threadIdx.x == 0) { sh.cnt = 0; sh.tau = KeyOps<K>::lowest(); }
+    if (threadIdx.x == 0) { sh.cnt = 0; sh.done = 0; sh.tau = KeyOps<K>::lowest(); }
     TopBuf<K> tb{buf, &sh.cnt, &sh.tau, p.cap, p.keep};
-    const uint32_t n_tiles = (p.n + kTileRows - 1) / kTileRows;
+    __syncthreads();
 
-    // dynamic tile scheduler: the atomic for tile t+1 is in flight while tile t is processed
-    if (threadIdx.x == 0) sh.tile[0] = atomicAdd(p.tile_counter, 1u);
-    for (uint32_t ph = 0;; ph ^= 1u) {
-        __syncthreads();                                   // pushes of the previous tile are complete
-        const uint32_t tile = sh.tile[ph];
-        uint32_t next_tile = 0;
-        if (threadIdx.x == 0) next_tile = atomicAdd(p.tile_counter, 1u);
-        if (sh.cnt + kTileRows > p.cap) tb.compact();      // uniform: cnt was read after the barrier
-        if (tile >= n_tiles) break;
-        const K tau = sh.tau;
-        const uint32_t tile_row0 = tile * kTileRows;
-
-        constexpr int UNR = (L * C >= 16) ? 1 : kItersPerTile;
-#pragma unroll UNR
-        for (int it = 0; it < kItersPerTile; ++it) {
-            const uint32_t row0 = tile_row0 + (uint32_t)(it * kScanWarps + warp) * kRowsPerWarpIter;
-            const uint32_t my_row = row0 + (uint32_t)(j * G + g);
-            const float inv_r = __ldg(p.inv_norm + my_row);      // capacity is padded to whole tiles
-            const uint4* base = p.rows + (size_t)row0 * P16 + (size_t)g * P16 + j;
-            int acc[L];
-#pragma unroll
-            for (int r = 0; r < L; ++r) {
-                int a = 0;
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    uint4 v = ldg_stream(base + (r * G) * P16 + c * L);
-                    a = dot16(v, q[c], a);
-                }
-                acc[r] = a;
-            }
-            const int s = transpose_reduce<L>(acc, j);
-            const int dot_i = 2 * s + bias;
-            const float kappa = __fmul_rn(__fmul_rn((float)dot_i, inv_r), qh.inv_q);
-            if constexpr (!EXACT) {
-                const u64 key = make_key64(kappa, my_row);
-                tb.push_warp(my_row < p.n && key > tau, key);
-            } else {
-                bool pass = false;
-                KeyX key = KeyOps<KeyX>::lowest();
-                if (my_row < p.n && kappa >= theta) {
-                    const ReplayOut ro = replay_row<false>(reinterpret_cast<const uint8_t*>(p.rows) + (size_t)my_row * (P16 * 16),
-                                                           p.qbytes, p.q16, p.dim, qh.sum_cq, sh.lut);
-                    float dist = ref_distance(qh.sa, ro.sb, ro.dot);
-                    if ((double)dist < p.max_dist) {
-                        key = make_keyx(dist, __ldg(p.ids + my_row), my_row);
-                        pass = keyx_gt(key, tau);
-                    }
-                }
-                tb.push_warp(pass, key);
-            }
+    // Warp-autonomous scheduling: every warp claims chunks of kChunkRows rows from a global counter
+    // (GRAB chunks per atomic, the next claim is in flight while the current one is processed) and never
+    // waits for its siblings in the steady state.  The CTA only meets at a barrier when the candidate
+    // buffer is within one round of pushes of its capacity (cut back to `keep`) or when every warp has
+    // run out of work.  A warp that starts a chunk has seen cnt <= threshold, so at most
+    // kScanWarps * kChunkRows = kTileRows pushes can follow: cap >= threshold + kTileRows.
+    constexpr uint32_t GRAB = (P16 >= 16) ? 1u : 16u / P16;
+    const uint32_t n_chunks = (p.n + kChunkRows - 1) / kChunkRows;
+    const uint32_t threshold = p.cap - kTileRows;
+    uint32_t cur = 0, end = 0, nxt = 0;
+    if (lane == 0) nxt = atomicAdd(p.tile_counter, GRAB);
+    bool counted = false;
+    for (;;) {
+        if (cur == end && !counted) {
+            cur = __shfl_sync(0xFFFFFFFFu, nxt, 0);
+            end = cur + GRAB;
+            if (lane == 0 && cur < n_chunks) nxt = atomicAdd(p.tile_counter, GRAB);
         }
-        if (threadIdx.x == 0) sh.tile[ph ^ 1u] = next_tile;
+        const bool have = cur < n_chunks;
+        if (have && *reinterpret_cast<volatile uint32_t*>(&sh.cnt) <= threshold) {
+            const K tau = sh.tau;
+            const uint32_t chunk_row0 = cur * kChunkRows;
+            ++cur;
+            constexpr int UNR = (L * C >= 16) ? 1 : kItersPerChunk;
+#pragma unroll UNR
+            for (int it = 0; it < kItersPerChunk; ++it) {
+                const uint32_t row0 = chunk_row0 + (uint32_t)it * kRowsPerWarpIter;
+                const uint32_t my_row = row0 + (uint32_t)(j * G + g);
+                const float inv_r = __ldg(p.inv_norm + my_row);      // capacity is padded to whole tiles
+                const uint4* base = p.rows + (size_t)row0 * P16 + (size_t)g * P16 + j;
+                int acc[L];
+#pragma unroll
+                for (int r = 0; r < L; ++r) {
+                    int a = 0;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        uint4 v = ldg_stream(base + (r * G) * P16 + c * L);
+                        a = dot16(v, q[c], a);
+                    }
+                    acc[r] = a;
+                }
+                const int s = transpose_reduce<L>(acc, j);
+                const int dot_i = 2 * s + bias;
+                const float kappa = __fmul_rn(__fmul_rn((float)dot_i, inv_r), qh.inv_q);
+                if constexpr (!EXACT) {
+                    const u64 key = make_key64(kappa, my_row);
+                    tb.push_warp(my_row < p.n && key > tau, key);
+                } else {
+                    bool pass = false;
+                    KeyX key = KeyOps<KeyX>::lowest();
+                    if (my_row < p.n && kappa >= theta) {
+                        const ReplayOut ro = replay_row<false>(reinterpret_cast<const uint8_t*>(p.rows) + (size_t)my_row * (P16 * 16),
+                                                               p.qbytes, p.q16, p.dim, qh.sum_cq, sh.lut);
+                        float dist = ref_distance(qh.sa, ro.sb, ro.dot);
+                        if ((double)dist < p.max_dist) {
+                            key = make_keyx(dist, __ldg(p.ids + my_row), my_row);
+                            pass = keyx_gt(key, tau);
+                        }
+                    }
+                    tb.push_warp(pass, key);
+                }
+            }
+            continue;
+        }
+        // rendezvous: this warp is out of work, or the buffer needs cutting back
+        if (!have && !counted) {
+            counted = true;
+            if (lane == 0) atomicAdd(&sh.done, 1u);
+        }
+        __syncthreads();
+        if (sh.done == (uint32_t)kScanWarps) break;          // uniform: done only changes before a rendezvous
+        tb.compact();
     }
 
     // final cut: best `keep` of this CTA, written rank-major so the merge reads coalesced
