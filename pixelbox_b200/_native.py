@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "lib", "libpixelbox_b200.so")
+SO_PATH = os.environ.get("PBX_SO", os.path.join(HERE, "lib", "libpixelbox_b200.so"))   # PBX_SO: experiment builds only
 
 PBX_OK = 0
 ERROR_NAMES = {

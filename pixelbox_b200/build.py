@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "libpixelbox_b200.so")
 SOURCES = ["api.cu"]
-HEADERS = ["common.cuh", "scan.cuh", "finalize.cuh", os.path.join("..", "..", "include", "pixelbox_b200.h")]
+HEADERS = ["common.cuh", "scan.cuh", "rerank.cuh", "finalize.cuh",os.path.join("..", "..", "include", "pixelbox_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -43,8 +43,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return SO
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = os.environ.get("PBX_NVCC_EXTRA", "").split()      # experiments only, e.g. -DPBX_EXP_NOMETA
+    out = os.environ.get("PBX_SO_OUT", SO)
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -505,7 +505,8 @@ static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, 
         if (rc != PBX_OK) return rc;
         const int grid = scan_grid(c);
         const uint32_t keep = std::min<uint32_t>(default_keep(k, c->slack), kMaxKeep);
-        const uint32_t cap_scan = next_pow2(keep + kTileRows);
+        // fast pass: room for two rounds of pushes, so the flood before the first global threshold needs no cut-back
+        const uint32_t cap_scan = next_pow2(keep + 2 * kTileRows);
         const uint32_t cap_scan_x = next_pow2(k + kTileRows);
         // merge round size: one element per thread, more only when a round must span a complete rank (2 * grid)
         const uint32_t chunk = std::min<uint32_t>(4u, std::max<uint32_t>(1u, (2u * (uint32_t)grid + kFinalThreads - 1) / kFinalThreads)) * kFinalThreads;

@@ -93,10 +93,44 @@ __device__ __forceinline__ float ref_distance(float sa, float sb, float dot) {
 // exact integer centring c(v) = 2v - 255
 __device__ __host__ __forceinline__ int centre(uint32_t v) { return 2 * (int)v - 255; }
 
-// monotone map of the ranking key to a histogram bin (bin width 2^-13 in cosine)
+// monotone map of the ranking key to a histogram bin (bin width 2^-13 in cosine).  t = fl(kappa + 1) is
+// formed with an explicit rounding so that "bin(kappa) >= b" and "t >= b / (bins/2)" are the same test
+// (the multiplication by a power of two is exact).
+__device__ __forceinline__ float kappa_shift(float kappa) { return __fadd_rn(kappa, 1.0f); }
 __device__ __forceinline__ uint32_t kappa_bin(float kappa) {
-    int b = __float2int_rd((kappa + 1.0f) * (float)(kHistBins / 2));
+    int b = __float2int_rd(__fmul_rn(kappa_shift(kappa), (float)(kHistBins / 2)));
     return (uint32_t)min(max(b, 0), (int)kHistBins - 1);
+}
+__device__ __forceinline__ float bin_threshold(uint32_t b) {      // kappa_shift(kappa) >= this  <=>  kappa_bin(kappa) >= b
+    return b == 0 ? -__int_as_float(0x7f800000) : (float)b * (2.0f / (float)kHistBins);
+}
+
+// One warp: the highest bin b* with at least `keep` histogram entries at or above it (0 if there are
+// fewer than `keep` entries).  Counts only grow while the scan runs, so a stale read is still valid.
+__device__ inline uint32_t hist_threshold_warp(const uint32_t* hist, uint32_t keep, int lane) {
+    constexpr uint32_t PER = kHistBins / 32;                      // lane l covers bins [l*PER, (l+1)*PER)
+    const uint4* hp = reinterpret_cast<const uint4*>(hist + (size_t)lane * PER);
+    uint32_t mine = 0;
+#pragma unroll 8
+    for (uint32_t i = 0; i < PER / 4; ++i) { const uint4 v = __ldcg(hp + i); mine += v.x + v.y + v.z + v.w; }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t v = __shfl_down_sync(0xFFFFFFFFu, incl, off);
+        if (lane + off < 32) incl += v;
+    }
+    const uint32_t above = incl - mine;
+    const bool has = above < keep && above + mine >= keep;
+    uint32_t b = 0;
+    if (has) {
+        uint32_t run = above;
+        for (int i = (int)PER - 1; i >= 0; --i) {
+            run += __ldcg(hist + (size_t)lane * PER + i);
+            if (run >= keep) { b = (uint32_t)lane * PER + (uint32_t)i; break; }
+        }
+    }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, has);
+    return m ? __shfl_sync(0xFFFFFFFFu, b, __ffs(m) - 1) : 0u;
 }
 
 // ---- candidate keys ----------------------------------------------------------------------

@@ -388,7 +388,8 @@ finalize_kernel(const FinalizeParams p) {
             else if (!separated) { st.need_exact = 1; st.theta = (float)((double)s_kappa_k - (double)p.margin - 1e-7); }
         }
         *p.status = st;
-        *p.tile_counter = 0;
+        p.tile_counter[0] = 0;                            // chunk scheduler
+        p.tile_counter[1] = 0;                            // global bin threshold of the scan
     }
 }
 

@@ -50,7 +50,7 @@ struct ScanParams {
     void* cand;                 // [keep][grid] keys, rank-major (u64 or KeyX)
     uint32_t* cand_cnt;         // [grid]
     uint32_t* tile_counter;     // dynamic tile scheduler (reset by the finalize kernel)
-    uint32_t* hist;             // [kHistBins] fast pass: kappa histogram of the final lists (merge threshold)
+    uint32_t* hist;             // [kHistBins] fast pass: kappa histogram of every pushed key (global + merge threshold)
     const SearchStatus* status; // EXACT only
     double max_dist;            // EXACT only
 };
@@ -202,6 +202,15 @@ scan_kernel(const ScanParams p) {
     TopBuf<K> tb{buf, &sh.cnt, &sh.tau, p.cap, p.keep};
     __syncthreads();
 
+    // Global threshold (fast pass): every pushed key is also counted in a global histogram over kappa.
+    // At geometrically spaced claim numbers the claiming warp scans the histogram for the highest bin b*
+    // with at least `keep` entries at or above it and publishes it (atomicMax): rows below b* cannot be
+    // among the best `keep` of the whole shard, whichever CTA sees them.  After the first few chunks the
+    // push rate is ~keep / rows-seen-by-all-CTAs, so buffers almost never need cutting back mid-scan.
+    uint32_t* const gbin = p.tile_counter + 1;
+    uint32_t gb = 0;
+    const uint32_t total_warps = gridDim.x * kScanWarps;
+
     // Warp-autonomous scheduling: every warp claims chunks of kChunkRows rows from a global counter
     // (GRAB chunks per atomic, the next claim is in flight while the current one is processed) and never
     // waits for its siblings in the steady state.  The CTA only meets at a barrier when the candidate
@@ -219,18 +228,36 @@ scan_kernel(const ScanParams p) {
             cur = __shfl_sync(0xFFFFFFFFu, nxt, 0);
             end = cur + GRAB;
             if (lane == 0 && cur < n_chunks) nxt = atomicAdd(p.tile_counter, GRAB);
+            if constexpr (!EXACT) {
+                const uint32_t claim = cur / GRAB;
+                if (cur < n_chunks && claim >= total_warps && claim % total_warps == 0 &&
+                    ((claim / total_warps) & (claim / total_warps - 1)) == 0) {
+                    const uint32_t b = hist_threshold_warp(p.hist, p.keep, lane);
+                    if (lane == 0 && b) atomicMax(gbin, b);
+                }
+            }
         }
         const bool have = cur < n_chunks;
         if (have && *reinterpret_cast<volatile uint32_t*>(&sh.cnt) <= threshold) {
             const K tau = sh.tau;
             const uint32_t chunk_row0 = cur * kChunkRows;
             ++cur;
+            float gthr = -__int_as_float(0x7f800000);
+            uint32_t gb_new = 0;
+            if constexpr (!EXACT) {
+                gthr = bin_threshold(gb);
+                gb_new = *reinterpret_cast<volatile uint32_t*>(gbin);   // consumed at the next chunk: latency is hidden
+            }
             constexpr int UNR = (L * C >= 16) ? 1 : kItersPerChunk;
 #pragma unroll UNR
             for (int it = 0; it < kItersPerChunk; ++it) {
                 const uint32_t row0 = chunk_row0 + (uint32_t)it * kRowsPerWarpIter;
                 const uint32_t my_row = row0 + (uint32_t)(j * G + g);
+#ifdef PBX_EXP_NOMETA
+                const float inv_r = 1.0e-4f;
+#else
                 const float inv_r = __ldg(p.inv_norm + my_row);      // capacity is padded to whole tiles
+#endif
                 const uint4* base = p.rows + (size_t)row0 * P16 + (size_t)g * P16 + j;
                 int acc[L];
 #pragma unroll
@@ -248,7 +275,13 @@ scan_kernel(const ScanParams p) {
                 const float kappa = __fmul_rn(__fmul_rn((float)dot_i, inv_r), qh.inv_q);
                 if constexpr (!EXACT) {
                     const u64 key = make_key64(kappa, my_row);
-                    tb.push_warp(my_row < p.n && key > tau, key);
+#ifdef PBX_EXP_NOPUSH
+                    if (key == 0x1234567ull) buf[0] = key;
+#else
+                    const bool pass = my_row < p.n && key > tau && kappa_shift(kappa) >= gthr;
+                    tb.push_warp(pass, key);
+                    if (pass) atomicAdd(p.hist + kappa_bin(kappa), 1u);
+#endif
                 } else {
                     bool pass = false;
                     KeyX key = KeyOps<KeyX>::lowest();
@@ -264,6 +297,7 @@ scan_kernel(const ScanParams p) {
                     tb.push_warp(pass, key);
                 }
             }
+            if constexpr (!EXACT) gb = max(gb, gb_new);
             continue;
         }
         // rendezvous: this warp is out of work, or the buffer needs cutting back
@@ -276,14 +310,28 @@ scan_kernel(const ScanParams p) {
         tb.compact();
     }
 
-    // final cut: best `keep` of this CTA, written rank-major so the merge reads coalesced
+    // final cut.  Fast pass: entries below the freshest global bin threshold go first (in place, one
+    // barrier per 256 entries: survivors are written below the region already read), so the sort that
+    // follows is over a handful of keys.
+    if constexpr (!EXACT) {
+        const float gfinal = bin_threshold(*reinterpret_cast<volatile uint32_t*>(gbin));
+        const uint32_t cnt0 = sh.cnt;
+        __syncthreads();
+        if (threadIdx.x == 0) sh.cnt = 0;
+        for (uint32_t base = 0; base < cnt0; base += blockDim.x) {
+            const uint32_t i = base + threadIdx.x;
+            u64 e = 0;
+            bool keep_it = false;
+            if (i < cnt0) { e = buf[i]; keep_it = kappa_shift(key64_kappa(e)) >= gfinal; }
+            __syncthreads();
+            tb.push_warp(keep_it, e);
+        }
+        __syncthreads();
+    }
     tb.compact();
     const uint32_t c = sh.cnt < p.keep ? sh.cnt : p.keep;
     K* out = reinterpret_cast<K*>(p.cand);
-    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
-        out[(size_t)i * gridDim.x + blockIdx.x] = buf[i];
-        if constexpr (!EXACT) atomicAdd(p.hist + kappa_bin(key64_kappa(buf[i])), 1u);
-    }
+    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) out[(size_t)i * gridDim.x + blockIdx.x] = buf[i];
     if (threadIdx.x == 0) p.cand_cnt[blockIdx.x] = c;
 }
 
@@ -335,7 +383,9 @@ scan_generic_kernel(const ScanParams p) {
             const float kappa = __fmul_rn(__fmul_rn((float)dot_i, inv_r), qh.inv_q);
             if constexpr (!EXACT) {
                 const u64 key = make_key64(kappa, my_row);
-                tb.push_warp(my_row < p.n && key > tau, key);
+                const bool pass = my_row < p.n && key > tau;
+                tb.push_warp(pass, key);
+                if (pass) atomicAdd(p.hist + kappa_bin(kappa), 1u);
             } else {
                 bool pass = false;
                 KeyX key = KeyOps<KeyX>::lowest();
@@ -355,10 +405,7 @@ scan_generic_kernel(const ScanParams p) {
     tb.compact();
     const uint32_t c = sh.cnt < p.keep ? sh.cnt : p.keep;
     K* out = reinterpret_cast<K*>(p.cand);
-    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
-        out[(size_t)i * gridDim.x + blockIdx.x] = buf[i];
-        if constexpr (!EXACT) atomicAdd(p.hist + kappa_bin(key64_kappa(buf[i])), 1u);
-    }
+    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) out[(size_t)i * gridDim.x + blockIdx.x] = buf[i];
     if (threadIdx.x == 0) p.cand_cnt[blockIdx.x] = c;
 }
 
