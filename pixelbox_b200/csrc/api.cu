@@ -813,3 +813,15 @@ extern "C" int pbx_set_scan_ctas_per_sm(pbx_corpus* c, uint32_t ctas_per_sm) {
     c->ctas_per_sm = ctas_per_sm;
     return PBX_OK;
 }
+
+#ifdef PBX_EXP_PROFILE
+// experiment builds only (not declared in the public header)
+extern "C" __attribute__((visibility("default"))) int pbx_debug_scan_profile(unsigned long long* out, int reset) {
+    if (out && cudaMemcpyFromSymbol(out, g_scan_prof, sizeof(unsigned long long) * kMaxScanGrid * 8) != cudaSuccess) return -1;
+    if (reset) {
+        static unsigned long long zeros[kMaxScanGrid * 8];
+        if (cudaMemcpyToSymbol(g_scan_prof, zeros, sizeof(zeros)) != cudaSuccess) return -1;
+    }
+    return 0;
+}
+#endif

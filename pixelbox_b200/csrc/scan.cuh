@@ -157,6 +157,16 @@ __device__ __forceinline__ ReplayOut replay_row(const uint8_t* __restrict__ row,
     return o;
 }
 
+#ifdef PBX_EXP_PROFILE
+// experiment builds only: per-CTA counters of the fast pass
+// [0] pushes  [1] compactions  [2] cycles waiting at rendezvous  [3] cycles in compaction  [4] total cycles
+// [5] entries before the final filter  [6] entries after it  [7] chunks processed
+__device__ unsigned long long g_scan_prof[kMaxScanGrid][8];
+#define PBX_PROF_ADD(i, v) do { if (threadIdx.x == 0) g_scan_prof[blockIdx.x][i] += (unsigned long long)(v); } while (0)
+#else
+#define PBX_PROF_ADD(i, v) do { } while (0)
+#endif
+
 template <typename K, bool EXACT>
 struct ScanShared {
     uint32_t cnt;
@@ -164,6 +174,7 @@ struct ScanShared {
     uint32_t tile[2];           // generic kernel: tile index broadcast
     K tau;
     float lut[EXACT ? 256 : 1];
+    SelectScratch sel;
 };
 
 // Fast shapes: pitch16 == L * C, L lanes per row, C chunks per lane.
@@ -183,6 +194,10 @@ scan_kernel(const ScanParams p) {
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane / L, j = lane % L;
+    (void)warp;
+#ifdef PBX_EXP_PROFILE
+    const long long t_kernel0 = clock64();
+#endif
 
     // centred query chunks of this lane: chunk index j + c*L, 16 values = 8 packed registers each
     int q[C][8];
@@ -242,17 +257,18 @@ scan_kernel(const ScanParams p) {
             const K tau = sh.tau;
             const uint32_t chunk_row0 = cur * kChunkRows;
             ++cur;
-            float gthr = -__int_as_float(0x7f800000);
-            uint32_t gb_new = 0;
-            if constexpr (!EXACT) {
-                gthr = bin_threshold(gb);
-                gb_new = *reinterpret_cast<volatile uint32_t*>(gbin);   // consumed at the next chunk: latency is hidden
-            }
+            if constexpr (!EXACT) gb = max(gb, *reinterpret_cast<volatile uint32_t*>(gbin));
             constexpr int UNR = (L * C >= 16) ? 1 : kItersPerChunk;
 #pragma unroll UNR
             for (int it = 0; it < kItersPerChunk; ++it) {
                 const uint32_t row0 = chunk_row0 + (uint32_t)it * kRowsPerWarpIter;
                 const uint32_t my_row = row0 + (uint32_t)(j * G + g);
+                float gthr = -__int_as_float(0x7f800000);
+                uint32_t gb_new = 0;
+                if constexpr (!EXACT) {
+                    gthr = bin_threshold(gb);
+                    gb_new = *reinterpret_cast<volatile uint32_t*>(gbin);   // refreshed every 32 rows; used by the next iteration
+                }
 #ifdef PBX_EXP_NOMETA
                 const float inv_r = 1.0e-4f;
 #else
@@ -281,6 +297,9 @@ scan_kernel(const ScanParams p) {
                     const bool pass = my_row < p.n && key > tau && kappa_shift(kappa) >= gthr;
                     tb.push_warp(pass, key);
                     if (pass) atomicAdd(p.hist + kappa_bin(kappa), 1u);
+#ifdef PBX_EXP_PROFILE
+                    if (pass) atomicAdd(&g_scan_prof[blockIdx.x][0], 1ull);
+#endif
 #endif
                 } else {
                     bool pass = false;
@@ -296,8 +315,8 @@ scan_kernel(const ScanParams p) {
                     }
                     tb.push_warp(pass, key);
                 }
+                if constexpr (!EXACT) gb = max(gb, gb_new);
             }
-            if constexpr (!EXACT) gb = max(gb, gb_new);
             continue;
         }
         // rendezvous: this warp is out of work, or the buffer needs cutting back
@@ -305,9 +324,19 @@ scan_kernel(const ScanParams p) {
             counted = true;
             if (lane == 0) atomicAdd(&sh.done, 1u);
         }
+#ifdef PBX_EXP_PROFILE
+        const long long t_r0 = clock64();
+#endif
         __syncthreads();
+#ifdef PBX_EXP_PROFILE
+        const long long t_r1 = clock64();
+        if constexpr (!EXACT) PBX_PROF_ADD(2, t_r1 - t_r0);
+#endif
         if (sh.done == (uint32_t)kScanWarps) break;          // uniform: done only changes before a rendezvous
-        tb.compact();
+        if constexpr (EXACT) tb.compact(); else block_select_top(tb, &sh.sel);
+#ifdef PBX_EXP_PROFILE
+        if constexpr (!EXACT) { PBX_PROF_ADD(3, clock64() - t_r1); PBX_PROF_ADD(1, 1); }
+#endif
     }
 
     // final cut.  Fast pass: entries below the freshest global bin threshold go first (in place, one
@@ -315,24 +344,19 @@ scan_kernel(const ScanParams p) {
     // follows is over a handful of keys.
     if constexpr (!EXACT) {
         const float gfinal = bin_threshold(*reinterpret_cast<volatile uint32_t*>(gbin));
-        const uint32_t cnt0 = sh.cnt;
-        __syncthreads();
-        if (threadIdx.x == 0) sh.cnt = 0;
-        for (uint32_t base = 0; base < cnt0; base += blockDim.x) {
-            const uint32_t i = base + threadIdx.x;
-            u64 e = 0;
-            bool keep_it = false;
-            if (i < cnt0) { e = buf[i]; keep_it = kappa_shift(key64_kappa(e)) >= gfinal; }
-            __syncthreads();
-            tb.push_warp(keep_it, e);
-        }
-        __syncthreads();
+        PBX_PROF_ADD(5, sh.cnt);
+        tb.filter_inplace([gfinal](const u64& e) { return kappa_shift(key64_kappa(e)) >= gfinal; });
+        if (sh.cnt > p.keep) block_select_top(tb, &sh.sel);      // uniform; only adversarial row orders get here
     }
+    if constexpr (!EXACT) PBX_PROF_ADD(6, sh.cnt);
     tb.compact();
     const uint32_t c = sh.cnt < p.keep ? sh.cnt : p.keep;
     K* out = reinterpret_cast<K*>(p.cand);
     for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) out[(size_t)i * gridDim.x + blockIdx.x] = buf[i];
     if (threadIdx.x == 0) p.cand_cnt[blockIdx.x] = c;
+#ifdef PBX_EXP_PROFILE
+    if constexpr (!EXACT) PBX_PROF_ADD(4, clock64() - t_kernel0);
+#endif
 }
 
 // Any other pitch: one lane per row, query chunks from shared memory.  Correctness path for odd
