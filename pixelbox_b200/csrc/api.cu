@@ -219,6 +219,7 @@ static cudaError_t init_kernel_attributes() {
     if (e == cudaSuccess) e = allow_smem(scan_kernel<16, 1, false, 4>, scan_cap);
     if (e == cudaSuccess) e = allow_smem(scan_generic_kernel<false>, scan_cap);
     if (e == cudaSuccess) e = allow_smem(scan_generic_kernel<true>, scan_cap);
+    if (e == cudaSuccess) e = allow_smem(seed_kernel, PBX_MAX_DIM * 2 + 1024);
     if (e == cudaSuccess) e = allow_smem(finalize_kernel, fin_cap);
     if (e == cudaSuccess) e = allow_smem(finalize_exact_kernel, fin_cap);
     return e;
@@ -269,11 +270,11 @@ extern "C" int pbx_corpus_create(uint32_t dim, uint64_t capacity_hint, int devic
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_s1);
     if (e == cudaSuccess) e = init_kernel_attributes();
     if (e == cudaSuccess) e = cudaMalloc(&c->d_cand_cnt, kMaxScanGrid * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_tile_counter, 256);
-    if (e == cudaSuccess) e = cudaMemset(c->d_tile_counter, 0, 256);
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_hist, kHistBins * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMemset(c->d_hist, 0, kHistBins * sizeof(uint32_t));
-    if (e == cudaSuccess) { c->d_exact_passes = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(c->d_tile_counter) + 128); }
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_tile_counter, 512);      // [0] chunk counter, [32] global bin, +256 B exact-pass count
+    if (e == cudaSuccess) e = cudaMemset(c->d_tile_counter, 0, 512);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_hist, 2 * kHistBins * sizeof(uint32_t));     // scan histogram | seed histogram
+    if (e == cudaSuccess) e = cudaMemset(c->d_hist, 0, 2 * kHistBins * sizeof(uint32_t));
+    if (e == cudaSuccess) { c->d_exact_passes = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(c->d_tile_counter) + 256); }
     if (e != cudaSuccess) {
         int rc = fail(PBX_E_CUDA, "corpus setup failed: %s", cudaGetErrorString(e));
         pbx_corpus_destroy(c);
@@ -507,6 +508,8 @@ static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, 
         const uint32_t keep = std::min<uint32_t>(default_keep(k, c->slack), kMaxKeep);
         // fast pass: room for two rounds of pushes, so the flood before the first global threshold needs no cut-back
         const uint32_t cap_scan = next_pow2(keep + 2 * kTileRows);
+        const int seed_grid = c->sm_count;
+        const bool seeded = (uint64_t)n >= (uint64_t)seed_grid * kSeedThreads * 8;       // small shards: not worth a launch
         const uint32_t cap_scan_x = next_pow2(k + kTileRows);
         // merge round size: one element per thread, more only when a round must span a complete rank (2 * grid)
         const uint32_t chunk = std::min<uint32_t>(4u, std::max<uint32_t>(1u, (2u * (uint32_t)grid + kFinalThreads - 1) / kFinalThreads)) * kFinalThreads;
@@ -549,6 +552,14 @@ static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, 
             sp.hist = c->d_hist;
             sp.status = c->d_status + q;
             sp.max_dist = max_dist;
+            if (seeded) {
+                SeedParams sd;
+                sd.rows = sp.rows; sd.inv_norm = sp.inv_norm; sd.n = n; sd.pitch16 = c->pitch16;
+                sd.q16 = sp.q16; sd.qh = sp.qh; sd.keep = keep;
+                sd.seed_hist = c->d_hist + kHistBins; sd.ticket = c->d_tile_counter + 96; sd.gbin = c->d_tile_counter + 32;
+                seed_kernel<<<seed_grid, kSeedThreads, (size_t)c->pitch16 * 32, s>>>(sd);
+                CU_TRY(cudaGetLastError());
+            }
             const bool time_scan = timed && q + 1 == nq;
             if (time_scan) CU_TRY(cudaEventRecord(c->ev_s0, s));
             CU_TRY(launch_scan<false>(c, sp, grid, (size_t)cap_scan * sizeof(u64), s));

@@ -21,7 +21,8 @@ constexpr int kTileRows = kScanWarps * kRowsPerWarpIter * kItersPerTile;   // 10
 constexpr int kFinalThreads = 1024;
 constexpr int kMergeChunk = 4 * kFinalThreads;
 constexpr uint32_t kMaxScanGrid = 2048;
-constexpr uint32_t kHistBins = 16384;        // global histogram of candidate keys over kappa in [-1, 1]
+constexpr uint32_t kHistBins = 4096;         // global histogram of candidate keys over kappa in [-1, 1]: 16 KB, one warp scans it in ~3 us
+constexpr int kSeedThreads = 256;            // seed kernel: one sampled row per thread
 constexpr uint32_t kMaxKeep = 3072;          // candidates per query the finalize kernel's shared memory is laid out for
 
 // plateau value of the reference distance: 1/1e-6f - 1 evaluated in f32 (src/engine.rs:587)
@@ -93,7 +94,7 @@ __device__ __forceinline__ float ref_distance(float sa, float sb, float dot) {
 // exact integer centring c(v) = 2v - 255
 __device__ __host__ __forceinline__ int centre(uint32_t v) { return 2 * (int)v - 255; }
 
-// monotone map of the ranking key to a histogram bin (bin width 2^-13 in cosine).  t = fl(kappa + 1) is
+// monotone map of the ranking key to a histogram bin (bin width 2 / kHistBins in cosine).  t = fl(kappa + 1) is
 // formed with an explicit rounding so that "bin(kappa) >= b" and "t >= b / (bins/2)" are the same test
 // (the multiplication by a power of two is exact).
 __device__ __forceinline__ float kappa_shift(float kappa) { return __fadd_rn(kappa, 1.0f); }
@@ -111,7 +112,7 @@ __device__ inline uint32_t hist_threshold_warp(const uint32_t* hist, uint32_t ke
     constexpr uint32_t PER = kHistBins / 32;                      // lane l covers bins [l*PER, (l+1)*PER)
     const uint4* hp = reinterpret_cast<const uint4*>(hist + (size_t)lane * PER);
     uint32_t mine = 0;
-#pragma unroll 8
+#pragma unroll
     for (uint32_t i = 0; i < PER / 4; ++i) { const uint4 v = __ldcg(hp + i); mine += v.x + v.y + v.z + v.w; }
     uint32_t incl = mine;
 #pragma unroll

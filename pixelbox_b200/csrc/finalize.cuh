@@ -48,6 +48,67 @@ __global__ void prep_query_kernel(const uint8_t* __restrict__ queries, uint32_t 
     }
 }
 
+// ---- seed of the scan's global threshold --------------------------------------------------------
+// A strided sample of the shard (gridDim.x * kSeedThreads rows, one per thread) is scored with the same
+// integer arithmetic as the scan and counted in a private histogram; the last CTA to finish turns it into
+// the bin b0 with at least `keep` sampled rows at or above it and stores it as the scan's starting global
+// threshold.  b0 is a valid bound (the sampled rows are real rows of the shard), so the scan's candidate
+// buffers never see the flood of "everything passes" rows.  The private histogram is left zeroed.
+struct SeedParams {
+    const uint4* rows;
+    const float* inv_norm;
+    uint32_t n;
+    uint32_t pitch16;
+    const int16_t* q16;         // written by prep_query_kernel
+    const QueryHeader* qh;
+    uint32_t keep;
+    uint32_t* seed_hist;        // [kHistBins], zero on entry and on exit
+    uint32_t* ticket;           // zero on entry and on exit
+    uint32_t* gbin;             // out: the scan's global bin threshold
+};
+
+__global__ void __launch_bounds__(kSeedThreads)
+seed_kernel(const SeedParams p) {
+    extern __shared__ __align__(16) unsigned char seed_smem[];
+    int4* sq = reinterpret_cast<int4*>(seed_smem);                  // [pitch16][2] centred query
+    __shared__ uint32_t s_last;
+    for (uint32_t i = threadIdx.x; i < p.pitch16 * 2; i += blockDim.x) sq[i] = __ldg(reinterpret_cast<const int4*>(p.q16) + i);
+    __syncthreads();
+    const QueryHeader qh = *p.qh;
+    const uint32_t total = gridDim.x * blockDim.x;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    // CTA b samples a contiguous run of blockDim.x rows starting at b * (n / gridDim.x): spread over the shard
+    const uint32_t stride = p.n / gridDim.x;
+    const uint32_t row = blockIdx.x * stride + threadIdx.x;
+    if (total <= p.n && threadIdx.x < stride && row < p.n) {
+        const uint4* rp = p.rows + (size_t)row * p.pitch16;
+        int s = 0;
+#pragma unroll 8
+        for (uint32_t c = 0; c < p.pitch16; ++c) {
+            const uint4 v = __ldg(rp + c);
+            const int4 a = sq[2 * c], b = sq[2 * c + 1];
+            const int qq[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            s = dot16(v, qq, s);
+        }
+        const int dot_i = 2 * s - 255 * qh.sum_cq;
+        const float kappa = __fmul_rn(__fmul_rn((float)dot_i, __ldg(p.inv_norm + row)), qh.inv_q);
+        atomicAdd(p.seed_hist + kappa_bin(kappa), 1u);
+    }
+    (void)t;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < 32) {
+        const uint32_t b = hist_threshold_warp(p.seed_hist, p.keep, threadIdx.x);
+        if (threadIdx.x == 0) { *p.gbin = b; *p.ticket = 0; }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < kHistBins; i += blockDim.x) p.seed_hist[i] = 0;
+}
+
 // ---- per-row metadata: inv_norm[r] = 1/sqrt(sum c(r_i)^2), one warp per row ----------------------
 __global__ void row_meta_kernel(const uint4* __restrict__ rows, uint32_t pitch16, uint32_t dim, uint64_t first, uint64_t n,
                                 float* __restrict__ inv_norm) {

@@ -150,16 +150,12 @@ finalize_kernel(const FinalizeParams p) {
     }
 
     // ---- 1a. histogram suffix scan: b* = highest bin with at least `keep` entries at or above it -------
-    constexpr uint32_t BPT = kHistBins / kFinalThreads;            // bins per thread (16)
+    constexpr uint32_t BPT = kHistBins / kFinalThreads;            // bins per thread
     uint32_t h[BPT];
-    {
-        uint4* hp = reinterpret_cast<uint4*>(p.hist) + (size_t)tid * (BPT / 4);
 #pragma unroll
-        for (uint32_t i = 0; i < BPT / 4; ++i) {
-            const uint4 v = hp[i];
-            h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w;
-            hp[i] = make_uint4(0, 0, 0, 0);                        // ready for the next query
-        }
+    for (uint32_t i = 0; i < BPT; ++i) {
+        h[i] = __ldcg(p.hist + (size_t)tid * BPT + i);
+        p.hist[(size_t)tid * BPT + i] = 0;                         // ready for the next query
     }
     uint32_t mine = 0;
 #pragma unroll
@@ -389,7 +385,7 @@ finalize_kernel(const FinalizeParams p) {
         }
         *p.status = st;
         p.tile_counter[0] = 0;                            // chunk scheduler
-        p.tile_counter[1] = 0;                            // global bin threshold of the scan
+        p.tile_counter[32] = 0;                           // global bin threshold of the scan
     }
 }
 

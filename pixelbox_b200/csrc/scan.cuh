@@ -171,6 +171,7 @@ template <typename K, bool EXACT>
 struct ScanShared {
     uint32_t cnt;
     uint32_t done;              // warps that have run out of work
+    uint32_t gb;                // CTA copy of the global bin threshold (polled by warp 0 only: one hot line, few readers)
     uint32_t tile[2];           // generic kernel: tile index broadcast
     K tau;
     float lut[EXACT ? 256 : 1];
@@ -194,7 +195,6 @@ scan_kernel(const ScanParams p) {
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane / L, j = lane % L;
-    (void)warp;
 #ifdef PBX_EXP_PROFILE
     const long long t_kernel0 = clock64();
 #endif
@@ -213,7 +213,7 @@ scan_kernel(const ScanParams p) {
     float theta = 0.0f;
     if constexpr (EXACT) theta = p.status->theta;
 
-    if (threadIdx.x == 0) { sh.cnt = 0; sh.done = 0; sh.tau = KeyOps<K>::lowest(); }
+    if (threadIdx.x == 0) { sh.cnt = 0; sh.done = 0; sh.gb = 0; sh.tau = KeyOps<K>::lowest(); }   // sh.gb is re-seeded below
     TopBuf<K> tb{buf, &sh.cnt, &sh.tau, p.cap, p.keep};
     __syncthreads();
 
@@ -222,8 +222,12 @@ scan_kernel(const ScanParams p) {
     // with at least `keep` entries at or above it and publishes it (atomicMax): rows below b* cannot be
     // among the best `keep` of the whole shard, whichever CTA sees them.  After the first few chunks the
     // push rate is ~keep / rows-seen-by-all-CTAs, so buffers almost never need cutting back mid-scan.
-    uint32_t* const gbin = p.tile_counter + 1;
+    uint32_t* const gbin = p.tile_counter + 32;        // its own 128-byte line, away from the chunk counter
     uint32_t gb = 0;
+    if constexpr (!EXACT) {                            // seeded by seed_kernel from a strided sample of the shard
+        gb = *reinterpret_cast<volatile uint32_t*>(gbin);
+        if (threadIdx.x == 0) sh.gb = gb;
+    }
     const uint32_t total_warps = gridDim.x * kScanWarps;
 
     // Warp-autonomous scheduling: every warp claims chunks of kChunkRows rows from a global counter
@@ -248,7 +252,7 @@ scan_kernel(const ScanParams p) {
                 if (cur < n_chunks && claim >= total_warps && claim % total_warps == 0 &&
                     ((claim / total_warps) & (claim / total_warps - 1)) == 0) {
                     const uint32_t b = hist_threshold_warp(p.hist, p.keep, lane);
-                    if (lane == 0 && b) atomicMax(gbin, b);
+                    if (lane == 0 && b) { atomicMax(gbin, b); atomicMax(&sh.gb, b); }
                 }
             }
         }
@@ -257,7 +261,12 @@ scan_kernel(const ScanParams p) {
             const K tau = sh.tau;
             const uint32_t chunk_row0 = cur * kChunkRows;
             ++cur;
-            if constexpr (!EXACT) gb = max(gb, *reinterpret_cast<volatile uint32_t*>(gbin));
+            uint32_t gpoll = 0;
+            if constexpr (!EXACT) {
+                // warp 0 polls the global word once per chunk (consumed at the end of the chunk, so the L2 round
+                // trip is hidden) and republishes it in shared memory for its siblings
+                if (warp == 0 && lane == 0) gpoll = *reinterpret_cast<volatile uint32_t*>(gbin);
+            }
             constexpr int UNR = (L * C >= 16) ? 1 : kItersPerChunk;
 #pragma unroll UNR
             for (int it = 0; it < kItersPerChunk; ++it) {
@@ -267,7 +276,7 @@ scan_kernel(const ScanParams p) {
                 uint32_t gb_new = 0;
                 if constexpr (!EXACT) {
                     gthr = bin_threshold(gb);
-                    gb_new = *reinterpret_cast<volatile uint32_t*>(gbin);   // refreshed every 32 rows; used by the next iteration
+                    gb_new = *reinterpret_cast<volatile uint32_t*>(&sh.gb);  // refreshed every 32 rows; used by the next iteration
                 }
 #ifdef PBX_EXP_NOMETA
                 const float inv_r = 1.0e-4f;
@@ -317,6 +326,9 @@ scan_kernel(const ScanParams p) {
                 }
                 if constexpr (!EXACT) gb = max(gb, gb_new);
             }
+            if constexpr (!EXACT) {
+                if (warp == 0 && lane == 0 && gpoll > sh.gb) sh.gb = gpoll;
+            }
             continue;
         }
         // rendezvous: this warp is out of work, or the buffer needs cutting back
@@ -343,7 +355,7 @@ scan_kernel(const ScanParams p) {
     // barrier per 256 entries: survivors are written below the region already read), so the sort that
     // follows is over a handful of keys.
     if constexpr (!EXACT) {
-        const float gfinal = bin_threshold(*reinterpret_cast<volatile uint32_t*>(gbin));
+        const float gfinal = bin_threshold(max(sh.gb, *reinterpret_cast<volatile uint32_t*>(gbin)));
         PBX_PROF_ADD(5, sh.cnt);
         tb.filter_inplace([gfinal](const u64& e) { return kappa_shift(key64_kappa(e)) >= gfinal; });
         if (sh.cnt > p.keep) block_select_top(tb, &sh.sel);      // uniform; only adversarial row orders get here
