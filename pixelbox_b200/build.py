@@ -19,6 +19,7 @@ HEADERS = ["common.cuh", "scan.cuh", "rerank.cuh", "finalize.cuh",os.path.join("
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
+    "-rdc=true", "-DPBX_USE_CDP",          # the exact pass is tail-launched from the finalize kernel
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2",
     "-shared",
 ]
@@ -46,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     extra = os.environ.get("PBX_NVCC_EXTRA", "").split()      # experiments only, e.g. -DPBX_EXP_NOMETA
     out = os.environ.get("PBX_SO_OUT", SO)
     cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+          ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudadevrt"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -219,7 +219,7 @@ static cudaError_t init_kernel_attributes() {
     if (e == cudaSuccess) e = allow_smem(scan_kernel<16, 1, false, 4>, scan_cap);
     if (e == cudaSuccess) e = allow_smem(scan_generic_kernel<false>, scan_cap);
     if (e == cudaSuccess) e = allow_smem(scan_generic_kernel<true>, scan_cap);
-    if (e == cudaSuccess) e = allow_smem(seed_kernel, PBX_MAX_DIM * 2 + 1024);
+    if (e == cudaSuccess) e = allow_smem(prep_seed_kernel, PBX_MAX_DIM * 2 + 1024);
     if (e == cudaSuccess) e = allow_smem(finalize_kernel, fin_cap);
     if (e == cudaSuccess) e = allow_smem(finalize_exact_kernel, fin_cap);
     return e;
@@ -531,8 +531,6 @@ static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, 
         const size_t fin_smem = off_stage + (size_t)stage_rows * srow;
         const size_t finx_smem = (size_t)cap_merge_x * sizeof(KeyX);
 
-        prep_query_kernel<<<nq, 256, 0, s>>>(d_queries, c->dim, c->pitch, c->d_q16, c->d_qbytes, c->d_qh);
-        CU_TRY(cudaGetLastError());
         for (uint32_t q = 0; q < nq; ++q) {
             ScanParams sp;
             sp.rows = reinterpret_cast<const uint4*>(c->d_rows);
@@ -552,12 +550,17 @@ static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, 
             sp.hist = c->d_hist;
             sp.status = c->d_status + q;
             sp.max_dist = max_dist;
-            if (seeded) {
-                SeedParams sd;
-                sd.rows = sp.rows; sd.inv_norm = sp.inv_norm; sd.n = n; sd.pitch16 = c->pitch16;
-                sd.q16 = sp.q16; sd.qh = sp.qh; sd.keep = keep;
-                sd.seed_hist = c->d_hist + kHistBins; sd.ticket = c->d_tile_counter + 96; sd.gbin = c->d_tile_counter + 32;
-                seed_kernel<<<seed_grid, kSeedThreads, (size_t)c->pitch16 * 32, s>>>(sd);
+            {
+                PrepSeedParams ps;
+                ps.query = d_queries + (size_t)q * c->dim;
+                ps.dim = c->dim; ps.pitch = c->pitch; ps.pitch16 = c->pitch16;
+                ps.q16 = c->d_q16 + (size_t)q * c->pitch;
+                ps.qbytes = c->d_qbytes + (size_t)q * c->pitch;
+                ps.qh = c->d_qh + q;
+                ps.rows = sp.rows; ps.inv_norm = sp.inv_norm; ps.n = n; ps.keep = keep;
+                ps.do_seed = seeded ? 1u : 0u;
+                ps.seed_hist = c->d_hist + kHistBins; ps.ticket = c->d_tile_counter + 96; ps.gbin = c->d_tile_counter + 32;
+                prep_seed_kernel<<<seeded ? seed_grid : 1, kSeedThreads, (size_t)c->pitch * 2, s>>>(ps);
                 CU_TRY(cudaGetLastError());
             }
             const bool time_scan = timed && q + 1 == nq;
@@ -594,13 +597,10 @@ static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, 
             fp.count = d_count + q;
             fp.status = c->d_status + q;
             fp.tile_counter = c->d_tile_counter;
-            finalize_kernel<<<1, kFinalThreads, fin_smem, s>>>(fp);
-            CU_TRY(cudaGetLastError());
-
-            // exact pass: both kernels return at once unless status->need_exact was raised
-            sp.keep = k;
-            sp.cap = cap_scan_x;
-            CU_TRY(launch_scan<true>(c, sp, grid, (size_t)cap_scan_x * sizeof(KeyX), s));
+            // exact pass parameters: k entries per CTA, (dist, image_id) keys
+            ScanParams spx = sp;
+            spx.keep = k;
+            spx.cap = cap_scan_x;
             FinalizeExactParams xp;
             xp.cand = reinterpret_cast<const KeyX*>(c->d_cand);
             xp.cand_cnt = c->d_cand_cnt;
@@ -616,8 +616,20 @@ static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, 
             xp.status = c->d_status + q;
             xp.tile_counter = c->d_tile_counter;
             xp.exact_passes = c->d_exact_passes;
+            fp.x.scan = spx;
+            fp.x.fin = xp;
+            fp.x.grid = (uint32_t)grid;
+            fp.x.scan_smem = (uint32_t)((size_t)cap_scan_x * sizeof(KeyX));
+            fp.x.fin_smem = (uint32_t)finx_smem;
+            fp.x.pad = 0;
+            finalize_kernel<<<1, kFinalThreads, fin_smem, s>>>(fp);
+            CU_TRY(cudaGetLastError());
+#ifndef PBX_USE_CDP
+            // without device-side launch both kernels are enqueued always and return at once unless need_exact was raised
+            CU_TRY(launch_scan<true>(c, spx, grid, (size_t)cap_scan_x * sizeof(KeyX), s));
             finalize_exact_kernel<<<1, kFinalThreads, finx_smem, s>>>(xp);
             CU_TRY(cudaGetLastError());
+#endif
         }
         c->last_grid = grid;
     }
@@ -826,6 +838,9 @@ extern "C" int pbx_set_scan_ctas_per_sm(pbx_corpus* c, uint32_t ctas_per_sm) {
 }
 
 #ifdef PBX_EXP_PROFILE
+extern "C" __attribute__((visibility("default"))) int pbx_debug_fin_profile(long long* out) {
+    return cudaMemcpyFromSymbol(out, g_fin_prof, sizeof(long long) * 16) == cudaSuccess ? 0 : -1;
+}
 // experiment builds only (not declared in the public header)
 extern "C" __attribute__((visibility("default"))) int pbx_debug_scan_profile(unsigned long long* out, int reset) {
     if (out && cudaMemcpyFromSymbol(out, g_scan_prof, sizeof(unsigned long long) * kMaxScanGrid * 8) != cudaSuccess) return -1;

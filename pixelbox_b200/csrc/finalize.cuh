@@ -10,91 +10,95 @@
 
 namespace pbx {
 
-// ---- query preparation: one CTA per query -----------------------------------------------------
-// Writes the centred 16-bit query (zero in the row padding), a padded byte copy and the header.
-__global__ void prep_query_kernel(const uint8_t* __restrict__ queries, uint32_t dim, uint32_t pitch,
-                                  int16_t* __restrict__ q16, uint8_t* __restrict__ qbytes, QueryHeader* __restrict__ qh) {
-    const uint32_t qi = blockIdx.x;
-    const uint8_t* src = queries + (size_t)qi * dim;
-    int16_t* d16 = q16 + (size_t)qi * pitch;
-    uint8_t* db = qbytes + (size_t)qi * pitch;
-    int s = 0, n2 = 0;
-    for (uint32_t i = threadIdx.x; i < pitch; i += blockDim.x) {
-        if (i < dim) {
-            uint32_t v = src[i];
-            int c = centre(v);
-            d16[i] = (int16_t)c;
-            db[i] = (uint8_t)v;
-            s += c;
-            n2 += c * c;
-        } else {
-            d16[i] = 0;
-            db[i] = 0;
-        }
-    }
-    __shared__ int ss[32], sn[32];
-    for (int off = 16; off; off >>= 1) { s += __shfl_xor_sync(~0u, s, off); n2 += __shfl_xor_sync(~0u, n2, off); }
-    if ((threadIdx.x & 31) == 0) { ss[threadIdx.x >> 5] = s; sn[threadIdx.x >> 5] = n2; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int S = 0, N = 0;
-        for (uint32_t w = 0; w < (blockDim.x + 31) / 32; ++w) { S += ss[w]; N += sn[w]; }
-        QueryHeader h;
-        h.sum_cq = S;
-        h.norm2_q = N;
-        h.inv_q = (float)(1.0 / sqrt((double)N));
-        h.sa = 0.0f;
-        qh[qi] = h;
-    }
-}
-
-// ---- seed of the scan's global threshold --------------------------------------------------------
-// A strided sample of the shard (gridDim.x * kSeedThreads rows, one per thread) is scored with the same
-// integer arithmetic as the scan and counted in a private histogram; the last CTA to finish turns it into
-// the bin b0 with at least `keep` sampled rows at or above it and stores it as the scan's starting global
-// threshold.  b0 is a valid bound (the sampled rows are real rows of the shard), so the scan's candidate
-// buffers never see the flood of "everything passes" rows.  The private histogram is left zeroed.
-struct SeedParams {
+// ---- query preparation + seed of the scan's global threshold: one launch per query -----------------
+// Every CTA centres the query into shared memory (c(q) = 2q - 255 as s16, zero in the row padding) and
+// reduces sum c(q), sum c(q)^2; CTA 0 also writes them out for the scan / finalize kernels.
+// Seed: a strided sample of the shard (gridDim.x * 256 rows: CTA b takes 256 consecutive rows starting at
+// b * n / gridDim.x, one row per thread with 16 independent 16-byte loads in flight) is
+// scored with the scan's integer arithmetic and counted in a private histogram; the last CTA to finish
+// turns it into the bin b0 with at least `keep` sampled rows at or above it and stores it as the scan's
+// starting global threshold.  b0 is a valid bound (sampled rows are real rows of the shard), so the scan's
+// candidate buffers never see a flood of "everything passes" rows.  The private histogram is left zeroed.
+struct PrepSeedParams {
+    const uint8_t* query;       // raw [dim] bytes of this query
+    uint32_t dim, pitch, pitch16;
+    int16_t* q16;               // out [pitch]
+    uint8_t* qbytes;            // out [pitch]
+    QueryHeader* qh;            // out
     const uint4* rows;
     const float* inv_norm;
     uint32_t n;
-    uint32_t pitch16;
-    const int16_t* q16;         // written by prep_query_kernel
-    const QueryHeader* qh;
     uint32_t keep;
+    uint32_t do_seed;           // 0: gridDim.x == 1, the global threshold starts at 0
     uint32_t* seed_hist;        // [kHistBins], zero on entry and on exit
     uint32_t* ticket;           // zero on entry and on exit
     uint32_t* gbin;             // out: the scan's global bin threshold
 };
 
 __global__ void __launch_bounds__(kSeedThreads)
-seed_kernel(const SeedParams p) {
+prep_seed_kernel(const PrepSeedParams p) {
     extern __shared__ __align__(16) unsigned char seed_smem[];
-    int4* sq = reinterpret_cast<int4*>(seed_smem);                  // [pitch16][2] centred query
+    int16_t* sq16 = reinterpret_cast<int16_t*>(seed_smem);           // [pitch] centred query
+    __shared__ int ss[kSeedThreads / 32], sn[kSeedThreads / 32];
     __shared__ uint32_t s_last;
-    for (uint32_t i = threadIdx.x; i < p.pitch16 * 2; i += blockDim.x) sq[i] = __ldg(reinterpret_cast<const int4*>(p.q16) + i);
+    __shared__ QueryHeader s_qh;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int s = 0, n2 = 0;
+    for (uint32_t i = threadIdx.x; i < p.pitch; i += blockDim.x) {
+        int c = 0;
+        uint32_t v = 0;
+        if (i < p.dim) { v = p.query[i]; c = centre(v); }
+        sq16[i] = (int16_t)c;
+        s += c;
+        n2 += c * c;
+        if (blockIdx.x == 0) { p.q16[i] = (int16_t)c; p.qbytes[i] = (uint8_t)v; }
+    }
+    for (int off = 16; off; off >>= 1) { s += __shfl_xor_sync(~0u, s, off); n2 += __shfl_xor_sync(~0u, n2, off); }
+    if (lane == 0) { ss[warp] = s; sn[warp] = n2; }
     __syncthreads();
-    const QueryHeader qh = *p.qh;
-    const uint32_t total = gridDim.x * blockDim.x;
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    // CTA b samples a contiguous run of blockDim.x rows starting at b * (n / gridDim.x): spread over the shard
-    const uint32_t stride = p.n / gridDim.x;
-    const uint32_t row = blockIdx.x * stride + threadIdx.x;
-    if (total <= p.n && threadIdx.x < stride && row < p.n) {
-        const uint4* rp = p.rows + (size_t)row * p.pitch16;
-        int s = 0;
-#pragma unroll 8
-        for (uint32_t c = 0; c < p.pitch16; ++c) {
-            const uint4 v = __ldg(rp + c);
-            const int4 a = sq[2 * c], b = sq[2 * c + 1];
-            const int qq[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-            s = dot16(v, qq, s);
+    if (threadIdx.x == 0) {
+        int S = 0, N = 0;
+        for (int w = 0; w < kSeedThreads / 32; ++w) { S += ss[w]; N += sn[w]; }
+        QueryHeader h;
+        h.sum_cq = S;
+        h.norm2_q = N;
+        h.inv_q = (float)(1.0 / sqrt((double)N));
+        h.sa = 0.0f;
+        s_qh = h;
+        if (blockIdx.x == 0) {
+            *p.qh = h;
+            if (!p.do_seed) *p.gbin = 0;
         }
-        const int dot_i = 2 * s - 255 * qh.sum_cq;
+    }
+    __syncthreads();
+    if (!p.do_seed) return;
+
+    const QueryHeader qh = s_qh;
+    const uint32_t stride = p.n / gridDim.x;                        // >= 8 * 256 by the host's seeding condition
+    {
+        // one sampled row per thread, 16 independent 16-byte loads in flight (one DRAM round trip per 256 B of row)
+        const uint32_t row = blockIdx.x * stride + threadIdx.x;
+        const uint4* rp = p.rows + (size_t)row * p.pitch16;
+        const int4* sq = reinterpret_cast<const int4*>(sq16);
+        const uint4 zero = make_uint4(0, 0, 0, 0);
+        int a = 0;
+        for (uint32_t c0 = 0; c0 < p.pitch16; c0 += 16) {
+            uint4 v[16];
+#pragma unroll
+            for (uint32_t i = 0; i < 16; ++i) v[i] = (c0 + i < p.pitch16) ? __ldg(rp + c0 + i) : zero;
+#pragma unroll
+            for (uint32_t i = 0; i < 16; ++i) {
+                if (c0 + i < p.pitch16) {
+                    const int4 x = sq[2 * (c0 + i)], y = sq[2 * (c0 + i) + 1];
+                    const int qq[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+                    a = dot16(v[i], qq, a);
+                }
+            }
+        }
+        const int dot_i = 2 * a - 255 * qh.sum_cq;
         const float kappa = __fmul_rn(__fmul_rn((float)dot_i, __ldg(p.inv_norm + row)), qh.inv_q);
         atomicAdd(p.seed_hist + kappa_bin(kappa), 1u);
     }
-    (void)t;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
@@ -157,23 +161,6 @@ __global__ void synth_fill_kernel(uint8_t* __restrict__ rows, uint32_t pitch, ui
 }
 
 // ---- exact pass: merge of the per-CTA (dist, id) lists and output ----------------------------------
-struct FinalizeExactParams {
-    const KeyX* cand;           // [k][grid] rank-major
-    const uint32_t* cand_cnt;
-    uint32_t grid;
-    uint32_t k;
-    uint32_t cap;               // power of two >= k + kMergeChunk
-    uint32_t dim;
-    uint32_t pitch;
-    const uint8_t* rows;
-    const uint8_t* qbytes;
-    pbx_hit* hits;
-    uint32_t* count;
-    const SearchStatus* status;
-    uint32_t* tile_counter;
-    unsigned long long* exact_passes;
-};
-
 __global__ void __launch_bounds__(kFinalThreads, 1)
 finalize_exact_kernel(const FinalizeExactParams p) {
     if (p.status->need_exact == 0) return;

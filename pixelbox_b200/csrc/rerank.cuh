@@ -16,7 +16,35 @@
 
 namespace pbx {
 
+struct FinalizeExactParams {
+    const KeyX* cand;           // [k][grid] rank-major
+    const uint32_t* cand_cnt;
+    uint32_t grid;
+    uint32_t k;
+    uint32_t cap;               // power of two >= k + kMergeChunk
+    uint32_t dim;
+    uint32_t pitch;
+    const uint8_t* rows;
+    const uint8_t* qbytes;
+    pbx_hit* hits;
+    uint32_t* count;
+    const SearchStatus* status;
+    uint32_t* tile_counter;
+    unsigned long long* exact_passes;
+};
+__global__ void finalize_exact_kernel(const FinalizeExactParams p);     // finalize.cuh
+
+// The exact (tie-resolving) pass is launched from the device, by the finalize kernel, only when the
+// certificate fails: two tail launches (CUDA dynamic parallelism) that run after the finalize grid and
+// before anything else in the stream.  A certified query -- the normal case -- pays nothing for it.
+struct ExactLaunch {
+    ScanParams scan;
+    FinalizeExactParams fin;
+    uint32_t grid, scan_smem, fin_smem, pad;
+};
+
 struct FinalizeParams {
+    ExactLaunch x;
     const u64* cand;            // [keep][grid] rank-major, each CTA list sorted best first
     const uint32_t* cand_cnt;   // [grid]
     uint32_t* hist;             // [kHistBins] counts of the final list entries per kappa bin (zeroed here)
@@ -114,8 +142,32 @@ __device__ __forceinline__ void fold16(const uint4& v, const float* qa, const fl
     }
 }
 
+#ifdef PBX_USE_CDP
+__device__ inline void launch_exact_tail(const ExactLaunch& x) {
+#define PBX_X_CASE(LL, CC) \
+    case LL * CC: scan_kernel<LL, CC, true><<<x.grid, kScanThreads, x.scan_smem, cudaStreamTailLaunch>>>(x.scan); break;
+    switch (x.scan.pitch16) {
+        PBX_X_CASE(1, 1) PBX_X_CASE(2, 1) PBX_X_CASE(4, 1) PBX_X_CASE(8, 1) PBX_X_CASE(16, 1) PBX_X_CASE(32, 1)
+        PBX_X_CASE(32, 2) PBX_X_CASE(32, 4)
+        default:
+            scan_generic_kernel<true><<<x.grid, kScanThreads, x.scan_smem + x.scan.pitch16 * 32, cudaStreamTailLaunch>>>(x.scan);
+            break;
+    }
+#undef PBX_X_CASE
+    finalize_exact_kernel<<<1, kFinalThreads, x.fin_smem, cudaStreamTailLaunch>>>(x.fin);
+}
+#endif
+
+#ifdef PBX_EXP_PROFILE
+__device__ long long g_fin_prof[16];     // experiment builds only: clock64 stamps of the finalize phases
+#define PBX_FIN_STAMP(i) do { if (threadIdx.x == 0) g_fin_prof[i] = clock64(); } while (0)
+#else
+#define PBX_FIN_STAMP(i) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(kFinalThreads, 1)
 finalize_kernel(const FinalizeParams p) {
+    PBX_FIN_STAMP(0);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* buf = reinterpret_cast<u64*>(smem_raw);                                   // [cap]
     u64* sorted = reinterpret_cast<u64*>(smem_raw + p.off_sorted);                 // [cap]
@@ -149,6 +201,7 @@ finalize_kernel(const FinalizeParams p) {
         atomicMax(&s_maxcnt, c);
     }
 
+    PBX_FIN_STAMP(1);
     // ---- 1a. histogram suffix scan: b* = highest bin with at least `keep` entries at or above it -------
     constexpr uint32_t BPT = kHistBins / kFinalThreads;            // bins per thread
     uint32_t h[BPT];
@@ -184,6 +237,7 @@ finalize_kernel(const FinalizeParams p) {
     if (s_total < p.keep && tid == 0) { s_bstar = 0; s_mprime = s_total; }   // fewer entries than keep: take everything
     __syncthreads();
 
+    PBX_FIN_STAMP(2);
     uint32_t nc;
     const uint32_t mprime = s_mprime, bstar = s_bstar;
     if (mprime <= p.cap) {
@@ -207,9 +261,20 @@ finalize_kernel(const FinalizeParams p) {
             }
         }
         __syncthreads();
-        const uint32_t m = s_cnt;                                   // == mprime
+        PBX_FIN_STAMP(3);
+        const uint32_t m = s_cnt;                                   // <= mprime
         // ---- 1c. order by key: rank counting when small (no barriers), bitonic otherwise ----------------
-        if (m <= 2 * kFinalThreads) {
+        if (m <= kFinalThreads) {
+            // TPE threads share one element: each counts a strided part of the buffer, shuffles add up
+            const uint32_t tpe = min(32u, (uint32_t)kFinalThreads / next_pow2(m < 2 ? 2 : m));
+            const uint32_t e = tid / tpe, sub = tid - e * tpe;
+            const u64 me = e < m ? buf[e] : 0ull;
+            uint32_t rank = 0;
+            for (uint32_t j = sub; j < m; j += tpe) rank += (buf[j] > me) ? 1u : 0u;
+            for (uint32_t off = tpe >> 1; off; off >>= 1) rank += __shfl_xor_sync(0xFFFFFFFFu, rank, off);
+            if (e < m && sub == 0) sorted[rank] = me;
+            __syncthreads();
+        } else if (m <= 2 * kFinalThreads) {
             for (uint32_t t = tid; t < m; t += blockDim.x) {
                 const u64 me = buf[t];
                 uint32_t rank = 0;
@@ -239,6 +304,7 @@ finalize_kernel(const FinalizeParams p) {
         s_kappa_last = nc > 0 ? key64_kappa(sorted[nc - 1]) : 0.0f;
     }
 
+    PBX_FIN_STAMP(4);
     // ---- 2. kernel C ------------------------------------------------------------------------------------
     // the query's own norm fold (src/engine.rs:580) by one thread of the last warp
     if (tid == kFinalThreads - 1) {
@@ -260,6 +326,7 @@ finalize_kernel(const FinalizeParams p) {
                 __ldg(reinterpret_cast<const uint4*>(p.rows + (size_t)row * p.pitch) + ch);
         }
         __syncthreads();
+        PBX_FIN_STAMP(5);
         for (uint32_t ci = tid; ci < cb; ci += blockDim.x) {
             const unsigned char* r = stage + (size_t)ci * srow;
             float s = 0.0f, d = 0.0f;
@@ -294,6 +361,7 @@ finalize_kernel(const FinalizeParams p) {
         __syncthreads();
     }
     __syncthreads();
+    PBX_FIN_STAMP(6);
     const float sa = s_sa;
     const uint32_t n2 = next_pow2(nc < 2 ? 2 : nc);
     uint32_t nonplateau = 0;
@@ -327,21 +395,26 @@ finalize_kernel(const FinalizeParams p) {
     if (tid == 0) s_cnt = 0;
     __syncthreads();
 
+    PBX_FIN_STAMP(7);
     // ---- 3. ORDER BY dist ASC (ties by image_id), WHERE dist < ?, LIMIT k  (engine.rs:379-381) ---------
     // `pos` = position of candidate c in the final order; ascending order makes the passing rows a prefix
     uint32_t local = 0;
     if (nc <= kFinalThreads) {
-        // rank counting: one candidate per thread, no barriers
-        if (tid < nc) {
-            const RerankEntry me = ent[tid];
-            uint32_t pos = 0;
-            for (uint32_t j = 0; j < nc; ++j) pos += rerank_before(ent[j], me) ? 1u : 0u;
-            const float dist = dists[tid];
+        // rank counting, TPE threads per candidate, no barriers
+        const uint32_t tpe = min(32u, (uint32_t)kFinalThreads / next_pow2(nc < 2 ? 2 : nc));
+        const uint32_t c = tid / tpe, sub = tid - c * tpe;
+        RerankEntry me; me.od = 0; me.slot = 0; me.id = 0;
+        if (c < nc) me = ent[c];
+        uint32_t pos = 0;
+        for (uint32_t j = sub; j < nc; j += tpe) pos += rerank_before(ent[j], me) ? 1u : 0u;
+        for (uint32_t off = tpe >> 1; off; off >>= 1) pos += __shfl_xor_sync(0xFFFFFFFFu, pos, off);
+        if (c < nc && sub == 0) {
+            const float dist = dists[c];
             const bool ok = (double)dist < p.max_dist;
             if (ok) local = 1;
             if (pos < p.k) {
                 pbx_hit hh;
-                if (ok) { hh.image_id = me.id; hh.dist = dist; hh.dot = dots[tid]; hh.norm2 = norms[tid]; hh.flags = 0; }
+                if (ok) { hh.image_id = me.id; hh.dist = dist; hh.dot = dots[c]; hh.norm2 = norms[c]; hh.flags = 0; }
                 else { hh.image_id = INT64_MAX; hh.dist = __int_as_float(0x7f800000); hh.dot = 0; hh.norm2 = 0; hh.flags = 0; }
                 p.hits[pos] = hh;
             }
@@ -368,6 +441,7 @@ finalize_kernel(const FinalizeParams p) {
     if (local) atomicAdd(&s_cnt, local);
     __syncthreads();
 
+    PBX_FIN_STAMP(8);
     // ---- certificate ------------------------------------------------------------------
     if (tid == 0) {
         const uint32_t passing = s_cnt;
@@ -386,6 +460,9 @@ finalize_kernel(const FinalizeParams p) {
         *p.status = st;
         p.tile_counter[0] = 0;                            // chunk scheduler
         p.tile_counter[32] = 0;                           // global bin threshold of the scan
+#ifdef PBX_USE_CDP
+        if (st.need_exact) { __threadfence(); launch_exact_tail(p.x); }
+#endif
     }
 }
 

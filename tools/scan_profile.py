@@ -32,3 +32,12 @@ names = ["pushes", "compactions", "rendezvous_wait_cyc", "compaction_cyc", "tota
 print(f"rows={rows} dim={dim} k={k} grid={g} scan_ms={c.stats().last_scan_ms:.4f}")
 for i, nm in enumerate(names):
     print(f"  {nm:22s} mean={p[:, i].mean():12.1f} min={p[:, i].min():12.1f} max={p[:, i].max():12.1f}")
+
+fin = np.zeros(16, np.int64)
+L.pbx_debug_fin_profile.argtypes = [ctypes.c_void_p]
+L.pbx_debug_fin_profile(fin.ctypes.data)
+labels = ["prologue", "hist suffix scan", "gather", "rank sort", "(kappa stats)", "stage rows", "replay", "dist+ids", "order+output"]
+print("  finalize phases (cycles @~1.9 GHz):")
+for i in range(8):
+    print(f"    {labels[i]:18s} {int(fin[i + 1] - fin[i]):8d}")
+print(f"    {'total':18s} {int(fin[8] - fin[0]):8d}")
