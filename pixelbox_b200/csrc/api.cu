@@ -454,13 +454,28 @@ __global__ void empty_result_kernel(pbx_hit* hits, uint32_t* counts, uint32_t nq
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x) counts[i] = 0;
 }
 
+// Launch with programmatic stream serialization: the kernel may begin before its predecessor in the stream has
+// finished; it orders itself with pdl_wait() (common.cuh).
+template <typename P>
+static cudaError_t launch_pdl(void (*kern)(const P), int grid, int block, size_t smem, cudaStream_t s, const P& params) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, params);
+}
+
 template <bool EXACT>
 static cudaError_t launch_scan(const pbx_corpus* c, const ScanParams& p, int grid, size_t smem, cudaStream_t s) {
 #define PBX_SCAN_CASE(LL, CC)                                                                                   \
     {                                                                                                           \
-        auto kern = scan_kernel<LL, CC, EXACT>;                                                                 \
-        kern<<<grid, kScanThreads, smem, s>>>(p);                                                               \
-        return cudaGetLastError();                                                                              \
+        return launch_pdl<ScanParams>(scan_kernel<LL, CC, EXACT>, grid, kScanThreads, smem, s, p);               \
     }
     switch (c->pitch16) {
         case 1: PBX_SCAN_CASE(1, 1)
@@ -469,25 +484,24 @@ static cudaError_t launch_scan(const pbx_corpus* c, const ScanParams& p, int gri
         case 8: PBX_SCAN_CASE(8, 1)
         case 16:
             if constexpr (!EXACT) {                  // occupancy variants of the d=256 fast pass (pbx_set_scan_ctas_per_sm)
-                if (c->ctas_per_sm == 3) { auto kern = scan_kernel<16, 1, false, 3>; kern<<<grid, kScanThreads, smem, s>>>(p); return cudaGetLastError(); }
-                if (c->ctas_per_sm >= 4) { auto kern = scan_kernel<16, 1, false, 4>; kern<<<grid, kScanThreads, smem, s>>>(p); return cudaGetLastError(); }
+                if (c->ctas_per_sm == 3 || c->ctas_per_sm == 0) return launch_pdl<ScanParams>(scan_kernel<16, 1, false, 3>, grid, kScanThreads, smem, s, p);
+                if (c->ctas_per_sm >= 4) return launch_pdl<ScanParams>(scan_kernel<16, 1, false, 4>, grid, kScanThreads, smem, s, p);
             }
             PBX_SCAN_CASE(16, 1)
         case 32: PBX_SCAN_CASE(32, 1)
         case 64: PBX_SCAN_CASE(32, 2)
         case 128: PBX_SCAN_CASE(32, 4)
         default: {
-            auto kern = scan_generic_kernel<EXACT>;
             size_t sm = smem + (size_t)c->pitch16 * 32;
-            kern<<<grid, kScanThreads, sm, s>>>(p);
-            return cudaGetLastError();
+            return launch_pdl<ScanParams>(scan_generic_kernel<EXACT>, grid, kScanThreads, sm, s, p);
         }
     }
 #undef PBX_SCAN_CASE
 }
 
 static int scan_grid(const pbx_corpus* c) {
-    uint32_t per_sm = c->ctas_per_sm ? c->ctas_per_sm : ((c->pitch16 >= 16) ? 2u : 4u);
+    // 3 CTAs per SM (<= 80 registers) measured best for 256-byte rows; larger rows need the registers, smaller ones fit 4
+    uint32_t per_sm = c->ctas_per_sm ? c->ctas_per_sm : ((c->pitch16 == 16) ? 3u : (c->pitch16 > 16) ? 2u : 4u);
     int g = c->sm_count * (int)per_sm;
     return std::min<int>(g, (int)kMaxScanGrid);
 }
@@ -560,8 +574,7 @@ static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, 
                 ps.rows = sp.rows; ps.inv_norm = sp.inv_norm; ps.n = n; ps.keep = keep;
                 ps.do_seed = seeded ? 1u : 0u;
                 ps.seed_hist = c->d_hist + kHistBins; ps.ticket = c->d_tile_counter + 96; ps.gbin = c->d_tile_counter + 32;
-                prep_seed_kernel<<<seeded ? seed_grid : 1, kSeedThreads, (size_t)c->pitch * 2, s>>>(ps);
-                CU_TRY(cudaGetLastError());
+                CU_TRY(launch_pdl<PrepSeedParams>(prep_seed_kernel, seeded ? seed_grid : 1, kSeedThreads, (size_t)c->pitch * 2, s, ps));
             }
             const bool time_scan = timed && q + 1 == nq;
             if (time_scan) CU_TRY(cudaEventRecord(c->ev_s0, s));
@@ -622,8 +635,7 @@ static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, 
             fp.x.scan_smem = (uint32_t)((size_t)cap_scan_x * sizeof(KeyX));
             fp.x.fin_smem = (uint32_t)finx_smem;
             fp.x.pad = 0;
-            finalize_kernel<<<1, kFinalThreads, fin_smem, s>>>(fp);
-            CU_TRY(cudaGetLastError());
+            CU_TRY(launch_pdl<FinalizeParams>(finalize_kernel, 1, kFinalThreads, fin_smem, s, fp));
 #ifndef PBX_USE_CDP
             // without device-side launch both kernels are enqueued always and return at once unless need_exact was raised
             CU_TRY(launch_scan<true>(c, spx, grid, (size_t)cap_scan_x * sizeof(KeyX), s));

@@ -28,6 +28,13 @@ constexpr uint32_t kMaxKeep = 3072;          // candidates per query the finaliz
 // plateau value of the reference distance: 1/1e-6f - 1 evaluated in f32 (src/engine.rs:587)
 #define PBX_PLATEAU_DIST 999999.0f
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------
+// pdl_trigger(): lets the next kernel of the stream (launched with the programmatic-serialization attribute)
+// start its independent prologue while this grid is still running.  pdl_wait(): blocks until every grid this
+// one depends on has completed and its memory is visible.  Both are no-ops for a plain launch.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- integer dot products --------------------------------------------------------------
 // dp2a: a holds two s16, b four u8.  lo: a.lo*b.byte0 + a.hi*b.byte1; hi: a.lo*b.byte2 + a.hi*b.byte3.
 // SASS: IDP.2A.LO.S16.U8 / IDP.2A.HI.S16.U8.

@@ -43,15 +43,18 @@ prep_seed_kernel(const PrepSeedParams p) {
     __shared__ uint32_t s_last;
     __shared__ QueryHeader s_qh;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // No pdl_trigger() here on purpose: if the scan were launched early its CTAs would fill every SM while they
+    // wait for this grid, and this grid waits for the previous query's finalize kernel *and its tail-launched
+    // exact pass*, which needs those SMs: a deadlock.  The scan starts when this grid has completed.
+    // Everything up to pdl_wait() reads only the caller's query and the immutable corpus, and writes only the
+    // seed histogram / ticket (private to this kernel): it may overlap the previous query's finalize kernel.
     int s = 0, n2 = 0;
     for (uint32_t i = threadIdx.x; i < p.pitch; i += blockDim.x) {
         int c = 0;
-        uint32_t v = 0;
-        if (i < p.dim) { v = p.query[i]; c = centre(v); }
+        if (i < p.dim) c = centre(p.query[i]);
         sq16[i] = (int16_t)c;
         s += c;
         n2 += c * c;
-        if (blockIdx.x == 0) { p.q16[i] = (int16_t)c; p.qbytes[i] = (uint8_t)v; }
     }
     for (int off = 16; off; off >>= 1) { s += __shfl_xor_sync(~0u, s, off); n2 += __shfl_xor_sync(~0u, n2, off); }
     if (lane == 0) { ss[warp] = s; sn[warp] = n2; }
@@ -65,12 +68,19 @@ prep_seed_kernel(const PrepSeedParams p) {
         h.inv_q = (float)(1.0 / sqrt((double)N));
         h.sa = 0.0f;
         s_qh = h;
-        if (blockIdx.x == 0) {
-            *p.qh = h;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0) {      // publish the query scratch only once the previous query's kernels are done with it
+        pdl_wait();
+        for (uint32_t i = threadIdx.x; i < p.pitch; i += blockDim.x) {
+            p.q16[i] = sq16[i];
+            p.qbytes[i] = i < p.dim ? p.query[i] : (uint8_t)0;
+        }
+        if (threadIdx.x == 0) {
+            *p.qh = s_qh;
             if (!p.do_seed) *p.gbin = 0;
         }
     }
-    __syncthreads();
     if (!p.do_seed) return;
 
     const QueryHeader qh = s_qh;
@@ -107,6 +117,7 @@ prep_seed_kernel(const PrepSeedParams p) {
     __threadfence();
     if (threadIdx.x < 32) {
         const uint32_t b = hist_threshold_warp(p.seed_hist, p.keep, threadIdx.x);
+        pdl_wait();             // the previous finalize kernel resets the global threshold: publish after it
         if (threadIdx.x == 0) { *p.gbin = b; *p.ticket = 0; }
     }
     __syncthreads();

@@ -189,8 +189,11 @@ finalize_kernel(const FinalizeParams p) {
     __shared__ uint32_t s_warp[32];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // No pdl_trigger() here: this grid may tail-launch the exact pass, which must run before anything else in
+    // the stream; a next-query kernel that was already started early would wait for it while it waits for them.
     if (tid < 256) s_lut[tid] = ref_decode(tid);
     if (tid == 0) { s_cnt = 0; s_tau = 0ull; s_maxcnt = 0; s_nonplateau = 0; s_pushed = 0; s_bstar = 0; s_mprime = 0; }
+    pdl_wait();                 // the scan is complete: lists, histogram and the query scratch are visible
     for (uint32_t i = tid; i < p.pitch / 8; i += blockDim.x)
         reinterpret_cast<uint4*>(s_q16)[i] = __ldg(reinterpret_cast<const uint4*>(p.q16) + i);
     __syncthreads();

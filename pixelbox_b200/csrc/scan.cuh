@@ -189,6 +189,8 @@ scan_kernel(const ScanParams p) {
     K* buf = reinterpret_cast<K*>(smem_raw);
     __shared__ ScanShared<K, EXACT> sh;
 
+    pdl_wait();                 // the query preparation / threshold seed (and everything before it) is complete
+    pdl_trigger();              // the finalize kernel may be scheduled as soon as an SM has room for it
     if constexpr (EXACT) {
         if (p.status->need_exact == 0) return;
         sh.lut[threadIdx.x & 255] = ref_decode(threadIdx.x & 255);

@@ -279,3 +279,38 @@ def test_full_size_10m_properties():
                     assert int(i) in set(int(x) for x in r.ids), f"stripe row {i} (dist {dd}) missing from q{qi}"
         st = c.stats()
         assert st.rows == n and st.exact_passes == 0
+
+
+def test_async_back_to_back_with_forced_exact_passes():
+    """Queries enqueued back to back on one stream, each needing the exact pass (device-side tail launch):
+    kernels of consecutive queries overlap through programmatic dependent launch and share scratch, so any
+    ordering hole shows up as a wrong list."""
+    import torch
+    rng = np.random.default_rng(321)
+    n, d, k = 300_000, 64, 40
+    corpus = clustered(rng, n, d, 500, 1)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    nq = 24
+    queries = np.stack([corpus[int(rng.integers(0, n))] for _ in range(nq)])
+    with Corpus(d) as c:
+        c.load(ids, corpus)
+        for slack in (1, 0):                     # 1 forces the exact pass, 0 = default
+            c.set_candidate_slack(slack)
+            dq = torch.from_numpy(queries).cuda()
+            dh = torch.zeros(nq * k * 24, dtype=torch.uint8, device="cuda")
+            dc = torch.zeros(nq, dtype=torch.int32, device="cuda")
+            s = torch.cuda.Stream()
+            torch.cuda.synchronize()
+            for rep in range(3):
+                for qi in range(nq):
+                    c.search_device(dq.data_ptr() + qi * d, 1, k, 1e3, dh.data_ptr() + qi * k * 24, dc.data_ptr() + 4 * qi, s.cuda_stream)
+            s.synchronize()
+            hits = dh.cpu().numpy().view(nat.HIT_DTYPE).reshape(nq, k)
+            cnt = dc.cpu().numpy()
+            for qi in range(nq):
+                o_ids, o_dist, o_dot, _ = oracle.topk(corpus, ids, queries[qi], k, 1e3, threads=4)
+                assert cnt[qi] == len(o_ids)
+                assert np.array_equal(hits[qi]["image_id"][:cnt[qi]], o_ids), (slack, qi)
+                assert np.array_equal(bits(hits[qi]["dist"][:cnt[qi]]), bits(o_dist))
+                assert np.array_equal(hits[qi]["dot"][:cnt[qi]], o_dot)
+        assert c.stats().exact_passes >= 3 * nq
