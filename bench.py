@@ -70,7 +70,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                        "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -239,7 +239,7 @@ def run_ours(args):
         return sc.search(q, k, 1e3)[0]
 
     # ---- value: device-resident, back to back ---------------------------------------------------
-    launches_per_step = 5 + (1 if world > 1 else 0)   # prep, scan, finalize, exact scan, exact finalize (+ merge)
+    launches_per_step = 3 + (1 if world > 1 else 0)   # prep+seed, scan, finalize (+ merge); the exact pass is device-launched on demand
     with torch.cuda.stream(stream):
         for i in range(max(args.warmup, 3)):
             step_device(i)
@@ -306,7 +306,7 @@ def run_ours(args):
                     "ms_per_query": e2e_step, "h2d_bytes_per_step": dim, "d2h_bytes_per_step": k * 24 + 4,
                     "api": "pbx_search (C ABI, host buffers)" if world == 1 else "ShardedCorpus.search (host buffers, NCCL all-gather)"},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"bound": "hbm", "kernel": "scan_kernel<16,1,false>" if dim == 256 else "scan_kernel", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "scan_kernel<16,1,false,3>" if dim == 256 else "scan_kernel", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": rows * dim, "launch_ms": scan_ms,
                          "share_of_step": scan_ms / ms_step},
