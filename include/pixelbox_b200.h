@@ -80,6 +80,7 @@ typedef struct pbx_stats {
     int32_t sm_count;
     int32_t scan_grid;         /* CTAs of the persistent scan kernel               */
     int32_t reserved;
+    uint64_t batched_queries;  /* queries answered by the tensor-core batched path */
 } pbx_stats;
 
 /* ---- lifecycle -------------------------------------------------------------------------
@@ -171,6 +172,11 @@ PBX_API int pbx_get_stats(const pbx_corpus* c, pbx_stats* out);
 /* Tuning knob for tests: candidate slack of the fast pass (candidates = k + slack); 0 restores
  * the default.  A tiny slack forces the exact pass and must not change any result. */
 PBX_API int pbx_set_candidate_slack(pbx_corpus* c, uint32_t slack);
+/* Batches of at least `min_queries` queries (per call) take the tensor-core path (tcgen05 kind::i8 contraction with
+ * the top-k fused into the epilogue) when the row pitch allows it (dim a multiple of 128, <= 1024); smaller batches loop
+ * over the single-query scan.  0 restores the default (16); UINT32_MAX disables the batched path.  Results are identical
+ * either way. */
+PBX_API int pbx_set_batch_min(pbx_corpus* c, uint32_t min_queries);
 /* CTAs per SM of the persistent scan kernel (0 = default). */
 PBX_API int pbx_set_scan_ctas_per_sm(pbx_corpus* c, uint32_t ctas_per_sm);
 PBX_API const char* pbx_last_error(void);

@@ -141,6 +141,10 @@ class Corpus:
     def set_candidate_slack(self, slack: int) -> None:
         nat.check(nat.lib().pbx_set_candidate_slack(self._h, int(slack)))
 
+    def set_batch_min(self, n: int) -> None:
+        """Batches of at least n queries per call use the tensor-core path (0 = default 16, 0xFFFFFFFF = never)."""
+        nat.check(nat.lib().pbx_set_batch_min(self._h, int(n)))
+
     def set_scan_ctas_per_sm(self, n: int) -> None:
         nat.check(nat.lib().pbx_set_scan_ctas_per_sm(self._h, int(n)))
 

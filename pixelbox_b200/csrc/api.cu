@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "finalize.cuh"
+#include "batch.cuh"
 
 using namespace pbx;
 
@@ -48,6 +49,7 @@ struct pbx_corpus {
     uint64_t capacity = 0;            // allocated rows, multiple of kTileRows
     uint8_t* d_rows = nullptr;
     float* d_inv = nullptr;
+    int* d_rsum = nullptr;            // sum of the raw bytes of each row (batched tensor-core path)
     int64_t* d_ids = nullptr;
 
     cudaStream_t stream = nullptr;    // default search stream
@@ -93,6 +95,20 @@ struct pbx_corpus {
     float last_search_ms = 0.f;
     uint64_t last_bytes = 0;
     int last_grid = 0;
+    uint64_t rows_generation = 0;     // bumped whenever the row buffers are re-allocated
+    // batched (tensor-core) path
+    uint32_t batch_pad = 0;           // padded queries the batch scratch is sized for
+    uint8_t* d_qpad = nullptr;        // [batch_pad][pitch] raw query bytes, the MMA's B operand
+    int* d_colterm = nullptr;
+    float* d_thr = nullptr;
+    uint32_t* d_bcnt = nullptr;
+    uint32_t* d_boverflow = nullptr;
+    u64* d_bcand = nullptr;           // [batch_pad][kBatchCap]
+    CUtensorMap map_rows, map_q;
+    uint64_t map_rows_gen = ~0ull;
+    uint32_t map_q_pad = 0, map_q_box = 0;
+    uint32_t batch_min = 16;          // batches at least this large use the tensor-core path
+    uint64_t batched_queries = 0;
 };
 
 static uint32_t default_keep(uint32_t k, uint32_t slack) {
@@ -108,8 +124,8 @@ static float certificate_margin(uint32_t dim) {
 }
 
 static int free_corpus_buffers(pbx_corpus* c) {
-    cudaFree(c->d_rows); cudaFree(c->d_inv); cudaFree(c->d_ids);
-    c->d_rows = nullptr; c->d_inv = nullptr; c->d_ids = nullptr;
+    cudaFree(c->d_rows); cudaFree(c->d_inv); cudaFree(c->d_ids); cudaFree(c->d_rsum);
+    c->d_rows = nullptr; c->d_inv = nullptr; c->d_ids = nullptr; c->d_rsum = nullptr;
     c->capacity = 0;
     return PBX_OK;
 }
@@ -120,20 +136,22 @@ static int reserve_rows(pbx_corpus* c, uint64_t rows) {
     if (rows > PBX_MAX_ROWS) return fail(PBX_E_CAPACITY, "shard would hold %llu rows (max %llu)", (unsigned long long)rows, (unsigned long long)PBX_MAX_ROWS);
     uint64_t want = std::max<uint64_t>(rows, c->capacity + c->capacity / 2);
     want = (want + kTileRows - 1) / kTileRows * kTileRows;
-    uint8_t* nr = nullptr; float* ni = nullptr; int64_t* nid = nullptr;
+    uint8_t* nr = nullptr; float* ni = nullptr; int64_t* nid = nullptr; int* ns = nullptr;
     cudaError_t e = cudaMalloc(&nr, want * c->pitch);
     if (e == cudaSuccess) e = cudaMalloc(&ni, want * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&nid, want * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&ns, want * sizeof(int));
     if (e != cudaSuccess && want > rows) {          // retry without growth head-room
-        cudaFree(nr); cudaFree(ni); cudaFree(nid); nr = nullptr; ni = nullptr; nid = nullptr;
+        cudaFree(nr); cudaFree(ni); cudaFree(nid); cudaFree(ns); nr = nullptr; ni = nullptr; nid = nullptr; ns = nullptr;
         cudaGetLastError();
         want = (rows + kTileRows - 1) / kTileRows * kTileRows;
         e = cudaMalloc(&nr, want * c->pitch);
         if (e == cudaSuccess) e = cudaMalloc(&ni, want * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&nid, want * sizeof(int64_t));
+        if (e == cudaSuccess) e = cudaMalloc(&ns, want * sizeof(int));
     }
     if (e != cudaSuccess) {
-        cudaFree(nr); cudaFree(ni); cudaFree(nid);
+        cudaFree(nr); cudaFree(ni); cudaFree(nid); cudaFree(ns);
         cudaGetLastError();
         return fail(PBX_E_OOM, "cannot allocate %llu rows x %u bytes on device %d: %s", (unsigned long long)want, c->pitch, c->device, cudaGetErrorString(e));
     }
@@ -143,14 +161,17 @@ static int reserve_rows(pbx_corpus* c, uint64_t rows) {
         CU_TRY(cudaMemcpyAsync(nr, c->d_rows, n * c->pitch, cudaMemcpyDeviceToDevice, c->stream));
         CU_TRY(cudaMemcpyAsync(ni, c->d_inv, n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
         CU_TRY(cudaMemcpyAsync(nid, c->d_ids, n * sizeof(int64_t), cudaMemcpyDeviceToDevice, c->stream));
+        CU_TRY(cudaMemcpyAsync(ns, c->d_rsum, n * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
     }
     // rows beyond the committed prefix are read (and ignored) by whole-tile loads: keep them defined
     CU_TRY(cudaMemsetAsync(nr + n * c->pitch, 0, (want - n) * c->pitch, c->stream));
     CU_TRY(cudaMemsetAsync(ni + n, 0, (want - n) * sizeof(float), c->stream));
     CU_TRY(cudaMemsetAsync(nid + n, 0, (want - n) * sizeof(int64_t), c->stream));
+    CU_TRY(cudaMemsetAsync(ns + n, 0, (want - n) * sizeof(int), c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
-    cudaFree(c->d_rows); cudaFree(c->d_inv); cudaFree(c->d_ids);
-    c->d_rows = nr; c->d_inv = ni; c->d_ids = nid;
+    cudaFree(c->d_rows); cudaFree(c->d_inv); cudaFree(c->d_ids); cudaFree(c->d_rsum);
+    c->d_rows = nr; c->d_inv = ni; c->d_ids = nid; c->d_rsum = ns;
+    c->rows_generation++;                           // device pointers moved: tensor maps must be rebuilt
     c->capacity = want;
     return PBX_OK;
 }
@@ -220,7 +241,10 @@ static cudaError_t init_kernel_attributes() {
     if (e == cudaSuccess) e = allow_smem(scan_generic_kernel<false>, scan_cap);
     if (e == cudaSuccess) e = allow_smem(scan_generic_kernel<true>, scan_cap);
     if (e == cudaSuccess) e = allow_smem(prep_seed_kernel, PBX_MAX_DIM * 2 + 1024);
-    if (e == cudaSuccess) e = allow_smem(finalize_kernel, fin_cap);
+    if (e == cudaSuccess) e = allow_smem(finalize_kernel<false>, fin_cap);
+    if (e == cudaSuccess) e = allow_smem(finalize_kernel<true>, fin_cap);
+    if (e == cudaSuccess) e = allow_smem(batch_mma_kernel, 220 * 1024);
+    if (e == cudaSuccess) e = allow_smem(batch_tighten_kernel, kBatchCap * sizeof(u64));
     if (e == cudaSuccess) e = allow_smem(finalize_exact_kernel, fin_cap);
     return e;
 }
@@ -295,6 +319,7 @@ extern "C" void pbx_corpus_destroy(pbx_corpus* c) {
     cudaDeviceSynchronize();
     free_corpus_buffers(c);
     cudaFree(c->d_queries); cudaFree(c->d_q16); cudaFree(c->d_qbytes); cudaFree(c->d_qh); cudaFree(c->d_status);
+    cudaFree(c->d_qpad); cudaFree(c->d_colterm); cudaFree(c->d_thr); cudaFree(c->d_bcnt); cudaFree(c->d_boverflow); cudaFree(c->d_bcand);
     cudaFree(c->d_hits); cudaFree(c->d_counts); cudaFree(c->d_cand); cudaFree(c->d_cand_cnt); cudaFree(c->d_tile_counter); cudaFree(c->d_hist);
     cudaFreeHost(c->h_queries); cudaFreeHost(c->h_hits); cudaFreeHost(c->h_counts); cudaFreeHost(c->h_stage);
     if (c->ev_chain) cudaEventDestroy(c->ev_chain);
@@ -359,7 +384,7 @@ static int upload_rows(pbx_corpus* c, uint64_t at, const int64_t* ids, const uin
             const unsigned warps_per_block = 8;
             const unsigned blocks = (unsigned)((m + warps_per_block - 1) / warps_per_block);
             row_meta_kernel<<<blocks, warps_per_block * 32, 0, c->copy_stream>>>(reinterpret_cast<const uint4*>(c->d_rows), c->pitch16, c->dim,
-                                                                                at + off, m, c->d_inv);
+                                                                                at + off, m, c->d_inv, c->d_rsum);
             e = cudaGetLastError();
         }
         if (e == cudaSuccess) e = cudaEventRecord(done[slot], c->copy_stream);
@@ -422,7 +447,7 @@ extern "C" int pbx_corpus_fill_synthetic(pbx_corpus* c, uint64_t n, uint64_t see
         const uint64_t m = std::min<uint64_t>(step, n - off);
         synth_fill_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_rows, c->pitch, c->dim, off, m, seed, first_row + off, c->d_ids);
         const unsigned blocks = (unsigned)((m + 7) / 8);
-        row_meta_kernel<<<blocks, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_rows), c->pitch16, c->dim, off, m, c->d_inv);
+        row_meta_kernel<<<blocks, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_rows), c->pitch16, c->dim, off, m, c->d_inv, c->d_rsum);
     }
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaStreamSynchronize(c->stream));
@@ -506,6 +531,166 @@ static int scan_grid(const pbx_corpus* c) {
     return std::min<int>(g, (int)kMaxScanGrid);
 }
 
+// ------------------------------------------------------------------------------------------------
+// batched (tensor-core) search
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess) fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// [rows][pitch] u8 matrix, boxes of {128 bytes, box_rows rows}, 128-byte swizzle (the UMMA K-major operand layout)
+static int make_u8_map(CUtensorMap* m, void* base, uint64_t rows, uint32_t pitch, uint32_t box_rows) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return fail(PBX_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch};
+    cuuint32_t box[2] = {128, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PBX_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return PBX_OK;
+}
+
+static bool batch_eligible(const pbx_corpus* c, uint32_t nq, uint32_t n) {
+    return nq >= c->batch_min && c->pitch % 128 == 0 && c->pitch <= 1024 && n >= 16u * kBatchTileRows;
+}
+
+static int ensure_batch_scratch(pbx_corpus* c, uint32_t nq_pad) {
+    if (nq_pad <= c->batch_pad) return PBX_OK;
+    CU_TRY(cudaDeviceSynchronize());
+    cudaFree(c->d_qpad); cudaFree(c->d_colterm); cudaFree(c->d_thr); cudaFree(c->d_bcnt); cudaFree(c->d_boverflow); cudaFree(c->d_bcand);
+    c->d_qpad = nullptr; c->d_colterm = nullptr; c->d_thr = nullptr; c->d_bcnt = nullptr; c->d_boverflow = nullptr; c->d_bcand = nullptr;
+    c->batch_pad = 0; c->map_q_pad = 0;
+    CU_TRY(cudaMalloc(&c->d_qpad, (size_t)nq_pad * c->pitch));
+    CU_TRY(cudaMalloc(&c->d_colterm, (size_t)nq_pad * sizeof(int)));
+    CU_TRY(cudaMalloc(&c->d_thr, (size_t)nq_pad * sizeof(float)));
+    CU_TRY(cudaMalloc(&c->d_bcnt, (size_t)nq_pad * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&c->d_boverflow, (size_t)nq_pad * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&c->d_bcand, (size_t)nq_pad * kBatchCap * sizeof(u64)));
+    c->batch_pad = nq_pad;
+    return PBX_OK;
+}
+
+// Enqueues the tensor-core search of nq (<= 1024) device-resident queries.  Caller holds c->mu.
+static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, uint32_t k, double max_dist, pbx_hit* d_hits,
+                                  uint32_t* d_count, cudaStream_t s, uint32_t n) {
+    const uint32_t pitch = c->pitch, kc = pitch / 128;
+    const uint32_t qg = pitch <= 256 ? 512u : pitch <= 512 ? 256u : 128u;      // resident queries per CTA: qg * pitch <= 128 KB
+    const uint32_t groups = (nq + qg - 1) / qg, nq_pad = groups * qg;
+    const uint32_t nmma = qg < 256 ? qg : 256;
+    int rc = ensure_query_scratch(c, nq);
+    if (rc != PBX_OK) return rc;
+    rc = ensure_batch_scratch(c, nq_pad);
+    if (rc != PBX_OK) return rc;
+    if (c->map_rows_gen != c->rows_generation) {
+        rc = make_u8_map(&c->map_rows, c->d_rows, c->capacity, pitch, kBatchTileRows);
+        if (rc != PBX_OK) return rc;
+        c->map_rows_gen = c->rows_generation;
+    }
+    if (c->map_q_pad != c->batch_pad || c->map_q_box != nmma) {
+        rc = make_u8_map(&c->map_q, c->d_qpad, c->batch_pad, pitch, nmma);
+        if (rc != PBX_OK) return rc;
+        c->map_q_pad = c->batch_pad; c->map_q_box = nmma;
+    }
+    const int grid_scan = scan_grid(c);
+    const uint32_t keep = std::min<uint32_t>(default_keep(k, c->slack), kMaxKeep);
+    rc = ensure_cand(c, (size_t)std::max<uint32_t>(keep, k) * grid_scan * sizeof(KeyX));      // exact-pass scratch
+    if (rc != PBX_OK) return rc;
+
+    BatchPrepParams bp;
+    bp.queries = d_queries; bp.nq = nq; bp.dim = c->dim; bp.pitch = pitch;
+    bp.qpad = c->d_qpad; bp.q16 = c->d_q16; bp.qbytes = c->d_qbytes; bp.qh = c->d_qh;
+    bp.colterm = c->d_colterm; bp.thr = c->d_thr; bp.cand_cnt = c->d_bcnt; bp.overflow = c->d_boverflow;
+    batch_prep_kernel<<<nq_pad, 128, 0, s>>>(bp);
+    CU_TRY(cudaGetLastError());
+
+    BatchMmaParams mp;
+    mp.map_rows = c->map_rows; mp.map_q = c->map_q;
+    mp.inv_norm = c->d_inv; mp.row_sum = c->d_rsum; mp.colterm = c->d_colterm; mp.thr = c->d_thr;
+    mp.cand = c->d_bcand; mp.cand_cnt = c->d_bcnt; mp.overflow = c->d_boverflow;
+    mp.n = n; mp.dim = c->dim; mp.kc = kc; mp.qg = qg; mp.groups = groups;
+    const int grid = std::max<int>((int)groups, (c->sm_count / (int)groups) * (int)groups);
+    const size_t mma_smem = (size_t)qg * pitch + (size_t)kBatchStages * kBatchTileRows * 128 + (size_t)qg * 8 + 1024;
+    BatchTightenParams tp;
+    tp.cand = c->d_bcand; tp.cand_cnt = c->d_bcnt; tp.thr = c->d_thr; tp.keep = keep; tp.nq = nq;
+
+    // rounds over geometrically growing row ranges: round 0 floods (threshold -inf) 16 tiles = 2048 candidates per
+    // query; afterwards the threshold is the keep-th best of everything seen, so a round over 8x the rows seen adds
+    // about 8 * keep candidates -- the buffers (kBatchCap entries) are cut back to keep between rounds
+    const uint32_t tiles = (n + kBatchTileRows - 1) / kBatchTileRows;
+    const uint32_t grow = std::max<uint32_t>(2u, (kBatchCap / 2) / std::max<uint32_t>(keep, 1u));
+    uint32_t begin = 0, end = std::min<uint32_t>(tiles, 16u);
+    while (begin < tiles) {
+        mp.tile_begin = begin; mp.tile_end = end;
+        batch_mma_kernel<<<grid, kBatchThreads, mma_smem, s>>>(mp);
+        CU_TRY(cudaGetLastError());
+        begin = end;
+        if (begin < tiles) {
+            batch_tighten_kernel<<<nq, 256, kBatchCap * sizeof(u64), s>>>(tp);
+            CU_TRY(cudaGetLastError());
+            const uint64_t next = (uint64_t)end + (uint64_t)end * grow;
+            end = (uint32_t)std::min<uint64_t>(tiles, next);
+        }
+    }
+
+    // per-query finalize: cut to keep, bit-exact re-rank, certificate; exact passes are tail-launched by its last CTA
+    const uint32_t chunk = kFinalThreads;
+    const uint32_t cap_merge = std::max<uint32_t>(next_pow2(keep + chunk), kBatchCap);
+    const size_t off_sorted = (size_t)cap_merge * sizeof(u64);
+    const size_t off_dots = 2 * off_sorted;
+    const size_t off_q = (off_dots + (size_t)keep * 20 + 15) & ~(size_t)15;
+    const size_t off_stage = (off_q + (size_t)pitch * 6 + 15) & ~(size_t)15;
+    const size_t fin_budget = 200 * 1024;
+    const size_t srow = (size_t)pitch + 16;
+    if (off_stage + srow > fin_budget) return fail(PBX_E_INTERNAL, "finalize layout does not fit shared memory (k=%u dim=%u)", k, c->dim);
+    const uint32_t stage_rows = (uint32_t)std::min<size_t>(keep, (fin_budget - off_stage) / srow);
+    const size_t fin_smem = off_stage + (size_t)stage_rows * srow;
+    const uint32_t cap_scan_x = next_pow2(k + kTileRows);
+    const uint32_t cap_merge_x = next_pow2(k + kMergeChunk);
+
+    FinalizeParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.grid = (uint32_t)grid_scan; fp.keep = keep; fp.cap = cap_merge; fp.chunk = chunk; fp.k = k; fp.n = n;
+    fp.dim = c->dim; fp.pitch = pitch; fp.stage_rows = stage_rows;
+    fp.off_sorted = (uint32_t)off_sorted; fp.off_ent = 0; fp.off_dots = (uint32_t)off_dots; fp.off_q = (uint32_t)off_q; fp.off_stage = (uint32_t)off_stage;
+    fp.rows = c->d_rows; fp.ids = c->d_ids; fp.qbytes = c->d_qbytes; fp.q16 = c->d_q16; fp.qh = c->d_qh;
+    fp.max_dist = max_dist; fp.margin = certificate_margin(c->dim);
+    fp.hits = d_hits; fp.count = d_count; fp.status = c->d_status; fp.tile_counter = c->d_tile_counter;
+    fp.hist = c->d_hist; fp.cand = nullptr; fp.cand_cnt = nullptr;
+    fp.bcand = c->d_bcand; fp.bcnt = c->d_bcnt; fp.boverflow = c->d_boverflow; fp.bticket = c->d_tile_counter + 100;
+    fp.bcap = kBatchCap; fp.nq = nq;
+    // exact-pass template (query 0); the launching CTA offsets the per-query pointers
+    ScanParams spx;
+    memset(&spx, 0, sizeof(spx));
+    spx.rows = reinterpret_cast<const uint4*>(c->d_rows); spx.inv_norm = c->d_inv; spx.ids = c->d_ids; spx.n = n;
+    spx.pitch16 = c->pitch16; spx.dim = c->dim; spx.q16 = c->d_q16; spx.qbytes = c->d_qbytes; spx.qh = c->d_qh;
+    spx.keep = k; spx.cap = cap_scan_x; spx.cand = c->d_cand; spx.cand_cnt = c->d_cand_cnt; spx.tile_counter = c->d_tile_counter;
+    spx.hist = c->d_hist; spx.status = c->d_status; spx.max_dist = max_dist;
+    FinalizeExactParams xp;
+    memset(&xp, 0, sizeof(xp));
+    xp.cand = reinterpret_cast<const KeyX*>(c->d_cand); xp.cand_cnt = c->d_cand_cnt; xp.grid = (uint32_t)grid_scan; xp.k = k;
+    xp.cap = cap_merge_x; xp.dim = c->dim; xp.pitch = pitch; xp.rows = c->d_rows; xp.qbytes = c->d_qbytes;
+    xp.hits = d_hits; xp.count = d_count; xp.status = c->d_status; xp.tile_counter = c->d_tile_counter; xp.exact_passes = c->d_exact_passes;
+    fp.x.scan = spx; fp.x.fin = xp; fp.x.grid = (uint32_t)grid_scan;
+    fp.x.scan_smem = (uint32_t)((size_t)cap_scan_x * sizeof(KeyX)); fp.x.fin_smem = (uint32_t)((size_t)cap_merge_x * sizeof(KeyX)); fp.x.pad = 0;
+    finalize_kernel<true><<<nq, kFinalThreads, fin_smem, s>>>(fp);
+    CU_TRY(cudaGetLastError());
+    c->batched_queries += nq;
+    c->last_grid = grid;
+    return PBX_OK;
+}
+
 // Enqueues the whole search for nq queries already on the device.  Caller holds c->mu.
 static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, uint32_t k, double max_dist, pbx_hit* d_hits,
                           uint32_t* d_count, cudaStream_t s, bool timed) {
@@ -515,6 +700,12 @@ static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, 
     if (n == 0) {
         empty_result_kernel<<<64, 256, 0, s>>>(d_hits, d_count, nq, k);
         CU_TRY(cudaGetLastError());
+    } else if (batch_eligible(c, nq, n)) {
+        for (uint32_t q0 = 0; q0 < nq; q0 += 1024) {
+            const uint32_t b = std::min<uint32_t>(1024u, nq - q0);
+            int rc = enqueue_search_batched(c, d_queries + (size_t)q0 * c->dim, b, k, max_dist, d_hits + (size_t)q0 * k, d_count + q0, s, n);
+            if (rc != PBX_OK) return rc;
+        }
     } else {
         int rc = ensure_query_scratch(c, nq);
         if (rc != PBX_OK) return rc;
@@ -635,7 +826,7 @@ static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, 
             fp.x.scan_smem = (uint32_t)((size_t)cap_scan_x * sizeof(KeyX));
             fp.x.fin_smem = (uint32_t)finx_smem;
             fp.x.pad = 0;
-            CU_TRY(launch_pdl<FinalizeParams>(finalize_kernel, 1, kFinalThreads, fin_smem, s, fp));
+            CU_TRY(launch_pdl<FinalizeParams>(finalize_kernel<false>, 1, kFinalThreads, fin_smem, s, fp));
 #ifndef PBX_USE_CDP
             // without device-side launch both kernels are enqueued always and return at once unless need_exact was raised
             CU_TRY(launch_scan<true>(c, spx, grid, (size_t)cap_scan_x * sizeof(KeyX), s));
@@ -831,6 +1022,7 @@ extern "C" int pbx_get_stats(const pbx_corpus* cc, pbx_stats* out) {
     out->device = c->device;
     out->sm_count = c->sm_count;
     out->scan_grid = c->last_grid ? c->last_grid : scan_grid(c);
+    out->batched_queries = c->batched_queries;
     return PBX_OK;
 }
 
@@ -838,6 +1030,13 @@ extern "C" int pbx_set_candidate_slack(pbx_corpus* c, uint32_t slack) {
     if (!c) return fail(PBX_E_INVALID, "corpus is NULL");
     std::lock_guard<std::mutex> lk(c->mu);
     c->slack = slack;
+    return PBX_OK;
+}
+
+extern "C" int pbx_set_batch_min(pbx_corpus* c, uint32_t min_queries) {
+    if (!c) return fail(PBX_E_INVALID, "corpus is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->batch_min = min_queries ? min_queries : 16u;
     return PBX_OK;
 }
 

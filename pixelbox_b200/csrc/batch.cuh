@@ -1,0 +1,325 @@
+// batch.cuh -- kernel B: the batched-query path.  A batch of queries against the corpus is a dense
+// u8 x u8 -> s32 contraction  S[r, q] = sum_i r_i q_i,  run on the 5th-generation tensor cores
+// (tcgen05.mma.kind::i8, accumulators in TMEM), with the top-k selection fused into the epilogue so the
+// N x Q score matrix (10^10 entries for 10M x 1024) never exists in memory.
+//
+//   exact integers:  dot_i = sum c(q)c(r) = 4 S - 510 (sum q + sum r) + 65025 d      (c(v) = 2v - 255)
+//   ranking key   :  kappa' = fl(fl(dot_i) * inv_norm_r)      (the per-query factor 1/|c(q)| is applied later)
+//
+// One CTA = one query group (QG <= 512 queries resident in shared memory, loaded once by TMA) x a strided set of
+// 128-row corpus tiles.  Warp 0 streams corpus tiles with TMA (128-byte swizzle, 16 KB K-chunks, 4-stage
+// mbarrier ring), one thread of warp 1 issues the MMAs (M = 128 rows, N = up to 256 queries, K = 32 bytes per
+// instruction), warps 2..5 are the epilogue: tcgen05.ld of their TMEM lane quarter, two integer adds, one
+// int->float, one multiply and a compare per score; the few scores that beat the query's current threshold are
+// pushed into that query's candidate buffer in global memory.  Thresholds start at -inf and are tightened
+// between rounds over geometrically growing row ranges (batch_tighten_kernel), so each round adds ~2k
+// candidates per query.  The final candidates go through the same bit-exact re-rank and certificate as the
+// single-query path (finalize_kernel<true>).
+#pragma once
+#include <cuda.h>
+#include "rerank.cuh"
+
+namespace pbx {
+
+constexpr int kBatchThreads = 192;           // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int kBatchStages = 4;              // corpus K-chunk ring: 4 x 16 KB
+constexpr int kBatchTileRows = 128;          // UMMA M
+constexpr uint32_t kBatchCap = 4096;         // candidate buffer entries per query
+constexpr uint32_t kBatchQueryBytes = 128 * 1024;   // resident queries per CTA
+
+// ---- PTX helpers -------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "PBX_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra PBX_DONE;\n\t"
+        "bra PBX_WAIT;\n\t"
+        "PBX_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+// K-major operand, 128-byte swizzle: start address >> 4, LBO unused (1), SBO = 1024 B (8 rows x 128 B), version 1
+__device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem_ptr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_u32(smem_ptr) & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- per-batch query preparation: one CTA per (padded) query ---------------------------------------------
+struct BatchPrepParams {
+    const uint8_t* queries;     // [nq][dim]
+    uint32_t nq, dim, pitch;
+    uint8_t* qpad;              // [nq_pad][pitch] raw bytes, zero padded (rows beyond nq are zero): the MMA's B operand
+    int16_t* q16;               // [nq][pitch] centred (re-rank)
+    uint8_t* qbytes;            // [nq][pitch]
+    QueryHeader* qh;            // [nq]
+    int* colterm;               // [nq_pad]  -510 * sum q_i
+    float* thr;                 // [nq_pad]  -inf for real queries, +inf for padding
+    uint32_t* cand_cnt;         // [nq_pad]
+    uint32_t* overflow;         // [nq_pad]
+};
+
+__global__ void batch_prep_kernel(const BatchPrepParams p) {
+    const uint32_t q = blockIdx.x;
+    const bool real = q < p.nq;
+    int s = 0, n2 = 0, raw = 0;
+    for (uint32_t i = threadIdx.x; i < p.pitch; i += blockDim.x) {
+        uint32_t v = 0;
+        int c = 0;
+        if (real && i < p.dim) { v = p.queries[(size_t)q * p.dim + i]; c = centre(v); }
+        p.qpad[(size_t)q * p.pitch + i] = (uint8_t)v;
+        if (real) { p.q16[(size_t)q * p.pitch + i] = (int16_t)c; p.qbytes[(size_t)q * p.pitch + i] = (uint8_t)v; }
+        s += c; n2 += c * c; raw += (int)v;
+    }
+    __shared__ int ss[32], sn[32], sr[32];
+    for (int off = 16; off; off >>= 1) {
+        s += __shfl_xor_sync(~0u, s, off); n2 += __shfl_xor_sync(~0u, n2, off); raw += __shfl_xor_sync(~0u, raw, off);
+    }
+    if ((threadIdx.x & 31) == 0) { ss[threadIdx.x >> 5] = s; sn[threadIdx.x >> 5] = n2; sr[threadIdx.x >> 5] = raw; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int S = 0, N = 0, R = 0;
+        for (uint32_t w = 0; w < (blockDim.x + 31) / 32; ++w) { S += ss[w]; N += sn[w]; R += sr[w]; }
+        if (real) {
+            QueryHeader h;
+            h.sum_cq = S; h.norm2_q = N; h.inv_q = (float)(1.0 / sqrt((double)N)); h.sa = 0.0f;
+            p.qh[q] = h;
+        }
+        p.colterm[q] = -510 * R;
+        p.thr[q] = real ? -__int_as_float(0x7f800000) : __int_as_float(0x7f800000);
+        p.cand_cnt[q] = 0;
+        p.overflow[q] = 0;
+    }
+}
+
+// ---- the contraction + selection kernel ---------------------------------------------------------------------
+struct BatchMmaParams {
+    CUtensorMap map_rows;       // corpus [capacity][pitch] u8, box {128 B, 128 rows}, 128-byte swizzle
+    CUtensorMap map_q;          // padded queries [nq_pad][pitch] u8, box {128 B, min(256, QG) rows}
+    const float* inv_norm;
+    const int* row_sum;
+    const int* colterm;         // [nq_pad]
+    const float* thr;           // [nq_pad] thresholds on kappa' for this round
+    u64* cand;                  // [nq_pad][kBatchCap]
+    uint32_t* cand_cnt;         // [nq_pad]
+    uint32_t* overflow;         // [nq_pad]
+    uint32_t n;                 // rows visible to this search
+    uint32_t dim;
+    uint32_t kc;                // K-chunks of 128 bytes per row (pitch / 128)
+    uint32_t qg;                // queries per group (resident per CTA): 128, 256 or 512
+    uint32_t groups;            // query groups; gridDim.x is a multiple of it
+    uint32_t tile_begin, tile_end;   // 128-row tiles of this round
+};
+
+__global__ void __launch_bounds__(kBatchThreads, 1)
+batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
+    extern __shared__ __align__(1024) uint8_t bsm[];
+    const uint32_t QG = p.qg, KC = p.kc;
+    const uint32_t NMMA = QG < 256 ? QG : 256;          // queries per MMA instruction
+    const uint32_t NB = QG / NMMA;                      // accumulators per tile (1 or 2)
+    uint8_t* sQ = bsm;                                  // [KC][QG][128]
+    uint8_t* sA = bsm + (size_t)QG * KC * 128;          // [stages][128][128]
+    int* s_colterm = reinterpret_cast<int*>(sA + kBatchStages * kBatchTileRows * 128);
+    float* s_thr = reinterpret_cast<float*>(s_colterm + QG);
+    __shared__ __align__(8) uint64_t q_full, a_full[kBatchStages], a_empty[kBatchStages], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t g = blockIdx.x % p.groups;
+    const uint32_t ci = blockIdx.x / p.groups, cstride = gridDim.x / p.groups;
+
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(&q_full, 1);
+        for (int i = 0; i < kBatchStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (uint32_t i = threadIdx.x; i < QG; i += blockDim.x) {
+        s_colterm[i] = p.colterm[g * QG + i];
+        s_thr[i] = p.thr[g * QG + i];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            mbar_expect_tx(&q_full, QG * KC * 128);
+            for (uint32_t kc = 0; kc < KC; ++kc)
+                for (uint32_t h = 0; h < QG; h += NMMA)
+                    tma_load_2d(sQ + ((size_t)kc * QG + h) * 128, &p.map_q, &q_full, (int)(kc * 128), (int)(g * QG + h));
+            uint32_t it = 0;
+            for (uint32_t t = p.tile_begin + ci; t < p.tile_end; t += cstride) {
+                for (uint32_t kc = 0; kc < KC; ++kc, ++it) {
+                    const uint32_t st = it % kBatchStages, ph = (it / kBatchStages) & 1u;
+                    mbar_wait(&a_empty[st], ph ^ 1u);
+                    mbar_expect_tx(&a_full[st], kBatchTileRows * 128);
+                    tma_load_2d(sA + (size_t)st * kBatchTileRows * 128, &p.map_rows, &a_full[st], (int)(kc * 128), (int)(t * kBatchTileRows));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            // instruction descriptor: D = s32 (2 << 4), A = B = u8 (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+            const uint32_t idesc = (2u << 4) | ((NMMA >> 3) << 17) | ((uint32_t)(kBatchTileRows >> 4) << 24);
+            mbar_wait(&q_full, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t it = 0, tile_iter = 0;
+            uint32_t acc_uses[2] = {0, 0};
+            for (uint32_t t = p.tile_begin + ci; t < p.tile_end; t += cstride, ++tile_iter) {
+                const uint32_t it0 = it;
+                for (uint32_t nb = 0; nb < NB; ++nb) {
+                    const uint32_t ab = (NB == 2) ? nb : (tile_iter & 1u);       // accumulator buffer
+                    mbar_wait(&acc_empty[ab], (acc_uses[ab] & 1u) ^ 1u);          // the epilogue has drained its previous use
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t d_tmem = tmem + ab * 256u;
+                    for (uint32_t kc = 0; kc < KC; ++kc) {
+                        const uint32_t itk = it0 + kc;
+                        const uint32_t st = itk % kBatchStages, ph = (itk / kBatchStages) & 1u;
+                        if (nb == 0) {
+                            mbar_wait(&a_full[st], ph);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        }
+                        const uint64_t da = umma_desc_sw128(sA + (size_t)st * kBatchTileRows * 128);
+                        const uint64_t db = umma_desc_sw128(sQ + ((size_t)kc * QG + (size_t)nb * NMMA) * 128);
+#pragma unroll
+                        for (uint32_t ks = 0; ks < 4; ++ks)
+                            umma_i8(d_tmem, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, (kc | ks) ? 1u : 0u);
+                        if (nb == NB - 1) umma_commit(&a_empty[st]);              // the stage is free once these MMAs retire
+                    }
+                    umma_commit(&acc_full[ab]);
+                    acc_uses[ab]++;
+                }
+                it = it0 + KC;
+            }
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
+        const uint32_t quarter = (uint32_t)warp & 3u;
+        uint32_t tile_iter = 0;
+        uint32_t acc_uses[2] = {0, 0};
+        const int dterm = 65025 * (int)p.dim;
+        for (uint32_t t = p.tile_begin + ci; t < p.tile_end; t += cstride, ++tile_iter) {
+            const uint32_t row = t * kBatchTileRows + quarter * 32u + (uint32_t)lane;
+            const bool row_ok = row < p.n;
+            const float inv_r = row_ok ? __ldg(p.inv_norm + row) : 0.0f;
+            const int rowterm = row_ok ? (dterm - 510 * __ldg(p.row_sum + row)) : 0;
+            for (uint32_t nb = 0; nb < NB; ++nb) {
+                const uint32_t ab = (NB == 2) ? nb : (tile_iter & 1u);
+                mbar_wait(&acc_full[ab], acc_uses[ab] & 1u);
+                acc_uses[ab]++;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (uint32_t c0 = 0; c0 < NMMA; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem + ((quarter * 32u) << 16) + ab * 256u + c0, r);
+                    const uint32_t colbase = nb * NMMA + c0;
+#pragma unroll
+                    for (int i4 = 0; i4 < 8; ++i4) {
+                        const int4 ct = *reinterpret_cast<const int4*>(s_colterm + colbase + 4 * i4);
+                        const float4 th = *reinterpret_cast<const float4*>(s_thr + colbase + 4 * i4);
+                        const int cts[4] = {ct.x, ct.y, ct.z, ct.w};
+                        const float ths[4] = {th.x, th.y, th.z, th.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int dot_i = 4 * (int)r[4 * i4 + j] + rowterm + cts[j];
+                            const float kf = __fmul_rn((float)dot_i, inv_r);
+                            if (kf >= ths[j] && row_ok) {
+                                const uint32_t qi = g * QG + colbase + 4 * i4 + j;
+                                const uint32_t slot = atomicAdd(p.cand_cnt + qi, 1u);
+                                if (slot < kBatchCap) p.cand[(size_t)qi * kBatchCap + slot] = make_key64(kf, row);
+                                else p.overflow[qi] = 1u;
+                            }
+                        }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[ab]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+}
+
+// ---- between rounds: cut every query's candidate buffer back to `keep` and tighten its threshold ----------
+struct BatchTightenParams {
+    u64* cand;
+    uint32_t* cand_cnt;
+    float* thr;
+    uint32_t keep;
+    uint32_t nq;
+};
+
+__global__ void __launch_bounds__(256)
+batch_tighten_kernel(const BatchTightenParams p) {
+    extern __shared__ __align__(16) unsigned char tsm[];
+    u64* buf = reinterpret_cast<u64*>(tsm);              // [kBatchCap]
+    __shared__ uint32_t s_cnt;
+    __shared__ u64 s_tau;
+    __shared__ SelectScratch sel;
+    const uint32_t q = blockIdx.x;
+    const uint32_t c = min(p.cand_cnt[q], kBatchCap);
+    if (c <= p.keep) return;                             // nothing to cut: the threshold stays where it is
+    u64* src = p.cand + (size_t)q * kBatchCap;
+    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) buf[i] = src[i];
+    if (threadIdx.x == 0) { s_cnt = c; s_tau = 0; }
+    __syncthreads();
+    TopBuf<u64> tb{buf, &s_cnt, &s_tau, kBatchCap, p.keep};
+    block_select_top(tb, &sel);
+    const uint32_t kept = s_cnt;
+    for (uint32_t i = threadIdx.x; i < kept; i += blockDim.x) src[i] = buf[i];
+    if (threadIdx.x == 0) {
+        p.cand_cnt[q] = kept;
+        p.thr[q] = key64_kappa(s_tau);                   // every kept key has kappa' >= this
+    }
+}
+
+}  // namespace pbx

@@ -124,9 +124,9 @@ prep_seed_kernel(const PrepSeedParams p) {
     for (uint32_t i = threadIdx.x; i < kHistBins; i += blockDim.x) p.seed_hist[i] = 0;
 }
 
-// ---- per-row metadata: inv_norm[r] = 1/sqrt(sum c(r_i)^2), one warp per row ----------------------
+// ---- per-row metadata: inv_norm[r] = 1/sqrt(sum c(r_i)^2) and row_sum[r] = sum r_i, one warp per row ----------------------
 __global__ void row_meta_kernel(const uint4* __restrict__ rows, uint32_t pitch16, uint32_t dim, uint64_t first, uint64_t n,
-                                float* __restrict__ inv_norm) {
+                                float* __restrict__ inv_norm, int* __restrict__ row_sum) {
     const uint64_t r = first + (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= first + n) return;
@@ -143,6 +143,7 @@ __global__ void row_meta_kernel(const uint4* __restrict__ rows, uint32_t pitch16
         // sum (2v-255)^2 = 4 sum v^2 - 1020 sum v + 65025 d   (padding bytes are zero and excluded through d)
         long long n2 = 4ll * s2 - 1020ll * s1 + 65025ll * dim;
         inv_norm[r] = (float)(1.0 / sqrt((double)n2));
+        row_sum[r] = (int)s1;                      // sum of the raw bytes: the batched (u8 x u8) path needs it per row
     }
 }
 

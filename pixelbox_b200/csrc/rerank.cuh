@@ -70,6 +70,13 @@ struct FinalizeParams {
     uint32_t* count;            // this query
     SearchStatus* status;       // this query
     uint32_t* tile_counter;     // reset for the next scan
+    // batched path (finalize_kernel<true>, one CTA per query; the per-query pointers above are those of query 0)
+    const u64* bcand;           // [nq][kBatchCapacity] candidate keys (kappa' = dot_i * inv_norm_r, row)
+    const uint32_t* bcnt;       // [nq]
+    const uint32_t* boverflow;  // [nq] the candidate buffer overflowed: the exact pass must answer this query
+    uint32_t* bticket;          // zero on entry and on exit: the last CTA launches the exact passes
+    uint32_t bcap;              // entries per query in bcand
+    uint32_t nq;
 };
 
 struct RerankEntry {            // sort record of kernel C: (ord(dist), image_id) ascending
@@ -165,6 +172,39 @@ __device__ long long g_fin_prof[16];     // experiment builds only: clock64 stam
 #define PBX_FIN_STAMP(i) do { } while (0)
 #endif
 
+// Orders m unique keys best-first from buf into sorted: rank counting when small (no barriers), bitonic otherwise.
+// All threads; barrier before; ends with a barrier.  buf may be clobbered.
+__device__ inline void block_order_keys(u64* buf, u64* sorted, uint32_t m) {
+    const uint32_t tid = threadIdx.x;
+    if (m <= kFinalThreads) {
+        // TPE threads share one element: each counts a strided part of the buffer, shuffles add up
+        const uint32_t tpe = min(32u, (uint32_t)kFinalThreads / next_pow2(m < 2 ? 2 : m));
+        const uint32_t e = tid / tpe, sub = tid - e * tpe;
+        const u64 me = e < m ? buf[e] : 0ull;
+        uint32_t rank = 0;
+        for (uint32_t j = sub; j < m; j += tpe) rank += (buf[j] > me) ? 1u : 0u;
+        for (uint32_t off = tpe >> 1; off; off >>= 1) rank += __shfl_xor_sync(0xFFFFFFFFu, rank, off);
+        if (e < m && sub == 0) sorted[rank] = me;
+        __syncthreads();
+    } else if (m <= 2 * kFinalThreads) {
+        for (uint32_t t = tid; t < m; t += blockDim.x) {
+            const u64 me = buf[t];
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < m; ++j) rank += (buf[j] > me) ? 1u : 0u;
+            sorted[rank] = me;
+        }
+        __syncthreads();
+    } else {
+        const uint32_t m2 = next_pow2(m);
+        for (uint32_t i = m + tid; i < m2; i += blockDim.x) buf[i] = 0ull;
+        __syncthreads();
+        block_sort_desc<u64>(buf, m2);
+        for (uint32_t i = tid; i < m; i += blockDim.x) sorted[i] = buf[i];
+        __syncthreads();
+    }
+}
+
+template <bool BATCH>
 __global__ void __launch_bounds__(kFinalThreads, 1)
 finalize_kernel(const FinalizeParams p) {
     PBX_FIN_STAMP(0);
@@ -189,118 +229,122 @@ finalize_kernel(const FinalizeParams p) {
     __shared__ uint32_t s_warp[32];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t q = BATCH ? blockIdx.x : 0u;
+    const int16_t* q16_g = p.q16 + (size_t)q * p.pitch;
+    const uint8_t* qbytes_g = p.qbytes + (size_t)q * p.pitch;
+    QueryHeader* qh_g = p.qh + q;
+    pbx_hit* hits_g = p.hits + (size_t)q * p.k;
+    uint32_t* count_g = p.count + q;
+    SearchStatus* status_g = p.status + q;
+    __shared__ SelectScratch s_sel;
     // No pdl_trigger() here: this grid may tail-launch the exact pass, which must run before anything else in
     // the stream; a next-query kernel that was already started early would wait for it while it waits for them.
     if (tid < 256) s_lut[tid] = ref_decode(tid);
     if (tid == 0) { s_cnt = 0; s_tau = 0ull; s_maxcnt = 0; s_nonplateau = 0; s_pushed = 0; s_bstar = 0; s_mprime = 0; }
     pdl_wait();                 // the scan is complete: lists, histogram and the query scratch are visible
     for (uint32_t i = tid; i < p.pitch / 8; i += blockDim.x)
-        reinterpret_cast<uint4*>(s_q16)[i] = __ldg(reinterpret_cast<const uint4*>(p.q16) + i);
+        reinterpret_cast<uint4*>(s_q16)[i] = __ldg(reinterpret_cast<const uint4*>(q16_g) + i);
     __syncthreads();
-    for (uint32_t i = tid; i < p.pitch; i += blockDim.x) s_qa[i] = s_lut[p.qbytes[i]];
-    for (uint32_t b = tid; b < p.grid; b += blockDim.x) {
-        uint32_t c = p.cand_cnt[b];
-        s_listcnt[b] = c;
-        atomicMax(&s_maxcnt, c);
-    }
-
-    PBX_FIN_STAMP(1);
-    // ---- 1a. histogram suffix scan: b* = highest bin with at least `keep` entries at or above it -------
-    constexpr uint32_t BPT = kHistBins / kFinalThreads;            // bins per thread
-    uint32_t h[BPT];
-#pragma unroll
-    for (uint32_t i = 0; i < BPT; ++i) {
-        h[i] = __ldcg(p.hist + (size_t)tid * BPT + i);
-        p.hist[(size_t)tid * BPT + i] = 0;                         // ready for the next query
-    }
-    uint32_t mine = 0;
-#pragma unroll
-    for (uint32_t i = 0; i < BPT; ++i) mine += h[i];
-    // inclusive suffix sum over threads (thread t covers bins [t*BPT, (t+1)*BPT)): above = entries in higher threads
-    uint32_t incl = mine;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        uint32_t v = __shfl_down_sync(0xFFFFFFFFu, incl, off);
-        if (lane + off < 32) incl += v;
-    }
-    if (lane == 0) s_warp[warp] = incl;
-    __syncthreads();
-    uint32_t above = incl - mine;
-    for (uint32_t w = warp + 1; w < kFinalThreads / 32; ++w) above += s_warp[w];
-    if (tid == 0) { uint32_t t = 0; for (uint32_t w = 0; w < kFinalThreads / 32; ++w) t += s_warp[w]; s_total = t; }
-    if (above < p.keep && above + mine >= p.keep) {                // the crossing bin is one of mine
-        uint32_t run = above;
-#pragma unroll
-        for (int i = BPT - 1; i >= 0; --i) {
-            run += h[i];
-            if (run >= p.keep) { s_bstar = tid * BPT + i; s_mprime = run; break; }
-        }
-    }
-    __syncthreads();
-    if (s_total < p.keep && tid == 0) { s_bstar = 0; s_mprime = s_total; }   // fewer entries than keep: take everything
-    __syncthreads();
-
-    PBX_FIN_STAMP(2);
+    for (uint32_t i = tid; i < p.pitch; i += blockDim.x) s_qa[i] = s_lut[qbytes_g[i]];
     uint32_t nc;
-    const uint32_t mprime = s_mprime, bstar = s_bstar;
-    if (mprime <= p.cap) {
-        // ---- 1b. gather the list prefixes with bin >= b* ---------------------------------------------
+    if constexpr (!BATCH) {
         for (uint32_t b = tid; b < p.grid; b += blockDim.x) {
-            const uint32_t len = s_listcnt[b];
-            for (uint32_t r0 = 0; r0 < len; r0 += 4) {
-                u64 key[4];
-#pragma unroll
-                for (uint32_t i = 0; i < 4; ++i) key[i] = (r0 + i < len) ? p.cand[(size_t)(r0 + i) * p.grid + b] : 0ull;
-                uint32_t take = 0;
-#pragma unroll
-                for (uint32_t i = 0; i < 4; ++i)
-                    if (take == i && r0 + i < len && kappa_bin(key64_kappa(key[i])) >= bstar) take = i + 1;
-                if (take) {
-                    const uint32_t at = atomicAdd(&s_cnt, take);
-#pragma unroll
-                    for (uint32_t i = 0; i < 4; ++i) if (i < take) buf[at + i] = key[i];
+            uint32_t c = p.cand_cnt[b];
+            s_listcnt[b] = c;
+            atomicMax(&s_maxcnt, c);
+        }
+
+        PBX_FIN_STAMP(1);
+        // ---- 1a. histogram suffix scan: b* = highest bin with at least `keep` entries at or above it -------
+        constexpr uint32_t BPT = kHistBins / kFinalThreads;            // bins per thread
+        uint32_t h[BPT];
+    #pragma unroll
+        for (uint32_t i = 0; i < BPT; ++i) {
+            h[i] = __ldcg(p.hist + (size_t)tid * BPT + i);
+            p.hist[(size_t)tid * BPT + i] = 0;                         // ready for the next query
+        }
+        uint32_t mine = 0;
+    #pragma unroll
+        for (uint32_t i = 0; i < BPT; ++i) mine += h[i];
+        // inclusive suffix sum over threads (thread t covers bins [t*BPT, (t+1)*BPT)): above = entries in higher threads
+        uint32_t incl = mine;
+    #pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t v = __shfl_down_sync(0xFFFFFFFFu, incl, off);
+            if (lane + off < 32) incl += v;
+        }
+        if (lane == 0) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t above = incl - mine;
+        for (uint32_t w = warp + 1; w < kFinalThreads / 32; ++w) above += s_warp[w];
+        if (tid == 0) { uint32_t t = 0; for (uint32_t w = 0; w < kFinalThreads / 32; ++w) t += s_warp[w]; s_total = t; }
+        if (above < p.keep && above + mine >= p.keep) {                // the crossing bin is one of mine
+            uint32_t run = above;
+    #pragma unroll
+            for (int i = BPT - 1; i >= 0; --i) {
+                run += h[i];
+                if (run >= p.keep) { s_bstar = tid * BPT + i; s_mprime = run; break; }
+            }
+        }
+        __syncthreads();
+        if (s_total < p.keep && tid == 0) { s_bstar = 0; s_mprime = s_total; }   // fewer entries than keep: take everything
+        __syncthreads();
+
+        PBX_FIN_STAMP(2);
+        const uint32_t mprime = s_mprime, bstar = s_bstar;
+        if (mprime <= p.cap) {
+            // ---- 1b. gather the list prefixes with bin >= b* ---------------------------------------------
+            for (uint32_t b = tid; b < p.grid; b += blockDim.x) {
+                const uint32_t len = s_listcnt[b];
+                for (uint32_t r0 = 0; r0 < len; r0 += 4) {
+                    u64 key[4];
+    #pragma unroll
+                    for (uint32_t i = 0; i < 4; ++i) key[i] = (r0 + i < len) ? p.cand[(size_t)(r0 + i) * p.grid + b] : 0ull;
+                    uint32_t take = 0;
+    #pragma unroll
+                    for (uint32_t i = 0; i < 4; ++i)
+                        if (take == i && r0 + i < len && kappa_bin(key64_kappa(key[i])) >= bstar) take = i + 1;
+                    if (take) {
+                        const uint32_t at = atomicAdd(&s_cnt, take);
+    #pragma unroll
+                        for (uint32_t i = 0; i < 4; ++i) if (i < take) buf[at + i] = key[i];
+                    }
+                    if (take < 4) break;
                 }
-                if (take < 4) break;
-            }
-        }
-        __syncthreads();
-        PBX_FIN_STAMP(3);
-        const uint32_t m = s_cnt;                                   // <= mprime
-        // ---- 1c. order by key: rank counting when small (no barriers), bitonic otherwise ----------------
-        if (m <= kFinalThreads) {
-            // TPE threads share one element: each counts a strided part of the buffer, shuffles add up
-            const uint32_t tpe = min(32u, (uint32_t)kFinalThreads / next_pow2(m < 2 ? 2 : m));
-            const uint32_t e = tid / tpe, sub = tid - e * tpe;
-            const u64 me = e < m ? buf[e] : 0ull;
-            uint32_t rank = 0;
-            for (uint32_t j = sub; j < m; j += tpe) rank += (buf[j] > me) ? 1u : 0u;
-            for (uint32_t off = tpe >> 1; off; off >>= 1) rank += __shfl_xor_sync(0xFFFFFFFFu, rank, off);
-            if (e < m && sub == 0) sorted[rank] = me;
-            __syncthreads();
-        } else if (m <= 2 * kFinalThreads) {
-            for (uint32_t t = tid; t < m; t += blockDim.x) {
-                const u64 me = buf[t];
-                uint32_t rank = 0;
-                for (uint32_t j = 0; j < m; ++j) rank += (buf[j] > me) ? 1u : 0u;
-                sorted[rank] = me;
             }
             __syncthreads();
+            PBX_FIN_STAMP(3);
+            const uint32_t m = s_cnt;                                   // <= mprime
+            // ---- 1c. order by key ------------------------------------------------------------------------
+            block_order_keys(buf, sorted, m);
+            nc = m < p.keep ? m : p.keep;
         } else {
-            const uint32_t m2 = next_pow2(m);
-            for (uint32_t i = m + tid; i < m2; i += blockDim.x) buf[i] = 0ull;
-            __syncthreads();
-            block_sort_desc<u64>(buf, m2);
-            for (uint32_t i = tid; i < m; i += blockDim.x) sorted[i] = buf[i];
+            // ---- 1'. fallback: more ties in one bin than the buffer holds ----------------------------------
+            TopBuf<u64> tb{buf, &s_cnt, &s_tau, p.cap, p.keep};
+            merge_rounds(p, tb, s_listcnt, s_maxcnt, &s_pushed);
+            nc = s_cnt < p.keep ? s_cnt : p.keep;
+            for (uint32_t i = tid; i < nc; i += blockDim.x) sorted[i] = buf[i];
             __syncthreads();
         }
-        nc = m < p.keep ? m : p.keep;
     } else {
-        // ---- 1'. fallback: more ties in one bin than the buffer holds ----------------------------------
-        TopBuf<u64> tb{buf, &s_cnt, &s_tau, p.cap, p.keep};
-        merge_rounds(p, tb, s_listcnt, s_maxcnt, &s_pushed);
-        nc = s_cnt < p.keep ? s_cnt : p.keep;
-        for (uint32_t i = tid; i < nc; i += blockDim.x) sorted[i] = buf[i];
+        // ---- 1 (batched). this query's candidate buffer: kappa' -> kappa, cut to `keep`, order ---------------
         __syncthreads();
+        const uint32_t c = min(p.bcnt[q], p.bcap);
+        const float inv_q = qh_g->inv_q;
+        const u64* src = p.bcand + (size_t)q * p.bcap;
+        for (uint32_t i = tid; i < c; i += blockDim.x) {
+            const u64 e = src[i];
+            buf[i] = make_key64(__fmul_rn(key64_kappa(e), inv_q), key64_row(e));
+        }
+        if (tid == 0) s_cnt = c;
+        __syncthreads();
+        if (c > p.keep) {
+            TopBuf<u64> tb{buf, &s_cnt, &s_tau, p.cap, p.keep};
+            block_select_top(tb, &s_sel);
+        }
+        const uint32_t m = s_cnt;
+        block_order_keys(buf, sorted, m);
+        nc = m < p.keep ? m : p.keep;
     }
     if (tid == 0) {
         s_kappa_k = (nc >= p.k && p.k > 0) ? key64_kappa(sorted[p.k - 1]) : 0.0f;
@@ -314,11 +358,11 @@ finalize_kernel(const FinalizeParams p) {
         float sa = 0.0f;
         for (uint32_t i = 0; i < p.dim; ++i) { const float a = s_qa[i]; sa = ref_fold(sa, a, a); }
         s_sa = sa;
-        p.qh->sa = sa;
+        qh_g->sa = sa;
     }
     const uint32_t pitch16 = p.pitch / 16, srow = p.pitch + 16;     // staged row stride: odd number of 16-byte units
     const uint32_t full = p.dim >> 4;
-    const int sum_cq = p.qh->sum_cq;
+    const int sum_cq = qh_g->sum_cq;
     for (uint32_t c0 = 0; c0 < nc; c0 += p.stage_rows) {
         const uint32_t cb = min(p.stage_rows, nc - c0);
         // all threads: one 16-byte load per (candidate, chunk)
@@ -419,7 +463,7 @@ finalize_kernel(const FinalizeParams p) {
                 pbx_hit hh;
                 if (ok) { hh.image_id = me.id; hh.dist = dist; hh.dot = dots[c]; hh.norm2 = norms[c]; hh.flags = 0; }
                 else { hh.image_id = INT64_MAX; hh.dist = __int_as_float(0x7f800000); hh.dot = 0; hh.norm2 = 0; hh.flags = 0; }
-                p.hits[pos] = hh;
+                hits_g[pos] = hh;
             }
         }
     } else {
@@ -433,13 +477,13 @@ finalize_kernel(const FinalizeParams p) {
                 pbx_hit hh;
                 if (ok) { hh.image_id = e.id; hh.dist = dist; hh.dot = dots[e.slot]; hh.norm2 = norms[e.slot]; hh.flags = 0; }
                 else { hh.image_id = INT64_MAX; hh.dist = __int_as_float(0x7f800000); hh.dot = 0; hh.norm2 = 0; hh.flags = 0; }
-                p.hits[c] = hh;
+                hits_g[c] = hh;
             }
         }
     }
     for (uint32_t c = nc + tid; c < p.k; c += blockDim.x) {
         pbx_hit hh; hh.image_id = INT64_MAX; hh.dist = __int_as_float(0x7f800000); hh.dot = 0; hh.norm2 = 0; hh.flags = 0;
-        p.hits[c] = hh;
+        hits_g[c] = hh;
     }
     if (local) atomicAdd(&s_cnt, local);
     __syncthreads();
@@ -448,7 +492,7 @@ finalize_kernel(const FinalizeParams p) {
     // ---- certificate ------------------------------------------------------------------
     if (tid == 0) {
         const uint32_t passing = s_cnt;
-        *p.count = passing < p.k ? passing : p.k;
+        *count_g = passing < p.k ? passing : p.k;
         SearchStatus st;
         st.n_candidates = nc;
         st.reserved = 0;
@@ -460,12 +504,40 @@ finalize_kernel(const FinalizeParams p) {
             if (plateau_reachable) { st.need_exact = 1; st.theta = -__int_as_float(0x7f800000); }
             else if (!separated) { st.need_exact = 1; st.theta = (float)((double)s_kappa_k - (double)p.margin - 1e-7); }
         }
-        *p.status = st;
-        p.tile_counter[0] = 0;                            // chunk scheduler
-        p.tile_counter[32] = 0;                           // global bin threshold of the scan
+        if constexpr (BATCH) {
+            if (p.boverflow[q]) { st.need_exact = 1; st.theta = -__int_as_float(0x7f800000); }   // candidates were dropped
+        }
+        *status_g = st;
+        if constexpr (!BATCH) {
+            p.tile_counter[0] = 0;                        // chunk scheduler
+            p.tile_counter[32] = 0;                       // global bin threshold of the scan
 #ifdef PBX_USE_CDP
-        if (st.need_exact) { __threadfence(); launch_exact_tail(p.x); }
+            if (st.need_exact) { __threadfence(); launch_exact_tail(p.x); }
 #endif
+        } else {
+            // the last CTA to finish tail-launches the exact pass of every query that needs one, one after the
+            // other (they share the scan scratch), from a single thread so that their order is well defined
+            __threadfence();
+            if (atomicAdd(p.bticket, 1u) == gridDim.x - 1) {
+                *p.bticket = 0;
+#ifdef PBX_USE_CDP
+                __threadfence();
+                for (uint32_t qq = 0; qq < p.nq; ++qq) {
+                    if (*reinterpret_cast<volatile uint32_t*>(&p.status[qq].need_exact) == 0) continue;
+                    ExactLaunch x = p.x;
+                    x.scan.q16 += (size_t)qq * p.pitch;
+                    x.scan.qbytes += (size_t)qq * p.pitch;
+                    x.scan.qh += qq;
+                    x.scan.status += qq;
+                    x.fin.qbytes += (size_t)qq * p.pitch;
+                    x.fin.hits += (size_t)qq * p.k;
+                    x.fin.count += qq;
+                    x.fin.status += qq;
+                    launch_exact_tail(x);
+                }
+#endif
+            }
+        }
     }
 }
 

@@ -1,0 +1,65 @@
+"""The batched-query (tensor-core) path against the oracle and against the single-query path:
+identical ids, f32 distance bits and integer terms, for every row pitch it supports."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from pixelbox_b200.corpus import Corpus
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.asarray(a, np.float32).view(np.uint32)
+
+
+def clustered(rng, n, d, ncent, noise):
+    cent = rng.integers(0, 256, size=(ncent, d))
+    x = cent[rng.integers(0, ncent, size=n)] + rng.integers(-noise, noise + 1, size=(n, d))
+    return np.clip(x, 0, 255).astype(np.uint8)
+
+
+def check(corpus, ids, queries, k, md, c, oracle_every=1):
+    got = c.search(queries, k, md)
+    for qi in range(0, len(queries), oracle_every):
+        o_ids, o_dist, o_dot, o_n2 = oracle.topk(corpus, ids, queries[qi], k, md, threads=4)
+        assert list(got[qi].ids) == list(o_ids), f"ids differ q={qi}"
+        assert np.array_equal(bits(got[qi].dist), bits(o_dist)), f"dist bits differ q={qi}"
+        assert np.array_equal(got[qi].dot, o_dot) and np.array_equal(got[qi].norm2, o_n2)
+    return got
+
+
+@pytest.mark.parametrize("d,n,nq", [(256, 60_000, 40), (256, 150_001, 700), (128, 50_000, 64), (512, 40_000, 300), (1024, 30_000, 130)])
+def test_batched_equals_oracle_and_single_path(d, n, nq):
+    rng = np.random.default_rng(d + nq)
+    corpus = rng.integers(0, 256, size=(n, d), dtype=np.uint8)
+    ids = rng.permutation(np.arange(1, n + 1)).astype(np.int64)
+    queries = rng.integers(0, 256, size=(nq, d), dtype=np.uint8)
+    queries[: nq // 2] = np.clip(corpus[rng.integers(0, n, nq // 2)].astype(int) + rng.integers(-20, 21, size=(nq // 2, d)), 0, 255)
+    with Corpus(d) as c:
+        c.load(ids, corpus)
+        before = c.stats().batched_queries
+        batched = check(corpus, ids, queries, 100, 1e3, c, oracle_every=max(1, nq // 24))
+        assert c.stats().batched_queries == before + nq, "the tensor-core path did not run"
+        c.set_batch_min(0xFFFFFFFF)
+        single = c.search(queries, 100, 1e3)
+        assert c.stats().batched_queries == before + nq
+        for a, b in zip(batched, single):
+            assert list(a.ids) == list(b.ids) and np.array_equal(bits(a.dist), bits(b.dist))
+            assert np.array_equal(a.dot, b.dot) and np.array_equal(a.norm2, b.norm2)
+
+
+def test_batched_with_ties_filters_and_small_k():
+    """Duplicates force the exact pass (tail-launched by the batched finalize kernel) for some queries only."""
+    rng = np.random.default_rng(9)
+    n, d = 80_000, 256
+    corpus = clustered(rng, n, d, 2000, 1)
+    corpus[1000:1600] = corpus[1000]                    # 600 identical rows
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    queries = np.concatenate([corpus[[1000, 1001, 5, 77_777]], rng.integers(0, 256, size=(28, d), dtype=np.uint8)])
+    with Corpus(d) as c:
+        c.load(ids, corpus)
+        for k, md in ((100, 1e3), (10, 1e3), (300, 0.05), (100, 1e7)):
+            check(corpus, ids, queries, k, md, c)
+        st = c.stats()
+        assert st.batched_queries == 4 * len(queries) and st.exact_passes > 0
