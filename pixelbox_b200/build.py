@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "libpixelbox_b200.so")
 SOURCES = ["api.cu"]
-HEADERS = ["common.cuh", "scan.cuh", "rerank.cuh", "finalize.cuh",os.path.join("..", "..", "include", "pixelbox_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "pixelbox_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -109,6 +109,7 @@ struct pbx_corpus {
     uint32_t map_q_pad = 0, map_q_box = 0;
     uint32_t batch_min = 16;          // batches at least this large use the tensor-core path
     uint64_t batched_queries = 0;
+    bool scan_timed = false;          // ev_s0/ev_s1 were recorded by the last enqueue
 };
 
 static uint32_t default_keep(uint32_t k, uint32_t slack) {
@@ -695,6 +696,7 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
 static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, uint32_t k, double max_dist, pbx_hit* d_hits,
                           uint32_t* d_count, cudaStream_t s, bool timed) {
     const uint32_t n = (uint32_t)c->n.load();
+    c->scan_timed = false;
     if (c->chain_valid) CU_TRY(cudaStreamWaitEvent(s, c->ev_chain, 0));
     if (timed) CU_TRY(cudaEventRecord(c->ev_t0, s));
     if (n == 0) {
@@ -770,7 +772,7 @@ static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, 
             const bool time_scan = timed && q + 1 == nq;
             if (time_scan) CU_TRY(cudaEventRecord(c->ev_s0, s));
             CU_TRY(launch_scan<false>(c, sp, grid, (size_t)cap_scan * sizeof(u64), s));
-            if (time_scan) CU_TRY(cudaEventRecord(c->ev_s1, s));
+            if (time_scan) { CU_TRY(cudaEventRecord(c->ev_s1, s)); c->scan_timed = true; }
 
             FinalizeParams fp;
             fp.cand = reinterpret_cast<const u64*>(c->d_cand);
@@ -896,7 +898,7 @@ extern "C" int pbx_search_hits(pbx_corpus* c, const uint8_t* queries, uint32_t n
         CU_TRY(cudaStreamSynchronize(c->stream));
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1) == cudaSuccess) total_ms += ms;
-        if (c->n.load() == 0 || cudaEventElapsedTime(&c->last_scan_ms, c->ev_s0, c->ev_s1) != cudaSuccess) { c->last_scan_ms = 0.f; cudaGetLastError(); }
+        if (!c->scan_timed || cudaEventElapsedTime(&c->last_scan_ms, c->ev_s0, c->ev_s1) != cudaSuccess) { c->last_scan_ms = 0.f; cudaGetLastError(); }
         total_bytes += c->last_bytes;
         memcpy(out_hits + (size_t)q0 * k, c->h_hits, (size_t)b * k * sizeof(pbx_hit));
         memcpy(out_count + q0, c->h_counts, (size_t)b * sizeof(uint32_t));

@@ -17,6 +17,7 @@
 // single-query path (finalize_kernel<true>).
 #pragma once
 #include <cuda.h>
+#include <cstdio>
 #include "rerank.cuh"
 
 namespace pbx {
@@ -152,7 +153,10 @@ struct BatchMmaParams {
 
 __global__ void __launch_bounds__(kBatchThreads, 1)
 batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
-    extern __shared__ __align__(1024) uint8_t bsm[];
+    extern __shared__ __align__(16) uint8_t bsm_raw[];     // NOT declared 1024-aligned: the compiler would fold the fix-up below away
+    // the 128-byte swizzle of TMA and UMMA is a function of the shared-memory address: tiles must sit on 1024-byte
+    // boundaries, and dynamic shared memory only starts after the static variables (the host adds 1 KB of slack)
+    uint8_t* bsm = bsm_raw + ((1024u - (smem_u32(bsm_raw) & 1023u)) & 1023u);
     const uint32_t QG = p.qg, KC = p.kc;
     const uint32_t NMMA = QG < 256 ? QG : 256;          // queries per MMA instruction
     const uint32_t NB = QG / NMMA;                      // accumulators per tile (1 or 2)
@@ -189,6 +193,10 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
+#ifdef PBX_DEBUG_BATCH
+            if (blockIdx.x == 0) printf("bsm_raw %x bsm %x sQ %x sA %x q_full %x map_q %p map_rows %p QG %u KC %u NMMA %u\n", smem_u32(bsm_raw), smem_u32(bsm),
+                                        smem_u32(sQ), smem_u32(sA), smem_u32(&q_full), (const void*)&p.map_q, (const void*)&p.map_rows, QG, KC, NMMA);
+#endif
             mbar_expect_tx(&q_full, QG * KC * 128);
             for (uint32_t kc = 0; kc < KC; ++kc)
                 for (uint32_t h = 0; h < QG; h += NMMA)

@@ -52,7 +52,8 @@ __device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64
 constexpr int M = 128, N = 256, K = 256;
 
 __global__ void __launch_bounds__(128) umma_test(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int* out) {
-    extern __shared__ __align__(1024) uint8_t smem[];
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzled tiles need 1024-byte alignment
     uint8_t* sa = smem;                         // 2 x [128][128]
     uint8_t* sb = smem + 2 * M * 128;           // 2 x [256][128]
     __shared__ uint64_t bar_full, bar_mma;
