@@ -22,7 +22,8 @@
 
 namespace pbx {
 
-constexpr int kBatchThreads = 192;           // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int kBatchEpiWarps = 8;            // two per TMEM lane quarter, each takes half of an accumulator's columns
+constexpr int kBatchThreads = 64 + 32 * kBatchEpiWarps;   // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr int kBatchStages = 4;              // corpus K-chunk ring: 4 x 16 KB
 constexpr int kBatchTileRows = 128;          // UMMA M
 constexpr uint32_t kBatchCap = 4096;         // candidate buffer entries per query
@@ -143,6 +144,7 @@ struct BatchMmaParams {
     u64* cand;                  // [nq_pad][kBatchCap]
     uint32_t* cand_cnt;         // [nq_pad]
     uint32_t* overflow;         // [nq_pad]
+    const uint32_t* inv_bounds; // [2] min / max inv_norm over the corpus (float bits)
     uint32_t n;                 // rows visible to this search
     uint32_t dim;
     uint32_t kc;                // K-chunks of 128 bytes per row (pitch / 128)
@@ -164,6 +166,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
     uint8_t* sA = bsm + (size_t)QG * KC * 128;          // [stages][128][128]
     int* s_colterm = reinterpret_cast<int*>(sA + kBatchStages * kBatchTileRows * 128);
     float* s_thr = reinterpret_cast<float*>(s_colterm + QG);
+    int* s_u = reinterpret_cast<int*>(s_thr + QG);      // integer pre-test bound per query
     __shared__ __align__(8) uint64_t q_full, a_full[kBatchStages], a_empty[kBatchStages], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base;
 
@@ -178,12 +181,31 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
     if (threadIdx.x == 0) {
         mbar_init(&q_full, 1);
         for (int i = 0; i < kBatchStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kBatchEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (uint32_t i = threadIdx.x; i < QG; i += blockDim.x) {
-        s_colterm[i] = p.colterm[g * QG + i];
-        s_thr[i] = p.thr[g * QG + i];
+    {
+        // Integer pre-test.  A score passes when fl(fl(dot_i) * inv_r) >= thr, dot_i = x + colterm with x = 4 S + rowterm
+        // known per (row, query).  With norm = 1 / inv_r in [norm_lo, norm_hi] over the whole corpus this implies
+        //   x >= thr * (thr >= 0 ? norm_lo : norm_hi) * (1 -+ 2^-20) - 2 - colterm =: u[q]
+        // so "x >= u[q]" (one integer compare) never rejects a passing score; the few survivors take the exact test.
+        const double norm_lo = 1.0 / (double)__uint_as_float(p.inv_bounds[1]);
+        const double norm_hi = 1.0 / (double)__uint_as_float(p.inv_bounds[0]);
+        for (uint32_t i = threadIdx.x; i < QG; i += blockDim.x) {
+            const int ct = p.colterm[g * QG + i];
+            const float th = p.thr[g * QG + i];
+            s_colterm[i] = ct;
+            s_thr[i] = th;
+            int u;
+            if (th == -__int_as_float(0x7f800000)) u = INT_MIN;
+            else if (th == __int_as_float(0x7f800000)) u = INT_MAX;
+            else {
+                double t = (double)th * (th >= 0.0f ? norm_lo * (1.0 - 9.6e-7) : norm_hi * (1.0 + 9.6e-7)) - 2.0 - (double)ct;
+                t = floor(t);
+                u = t <= -2147483648.0 ? INT_MIN : t >= 2147483647.0 ? INT_MAX : (int)t;
+            }
+            s_u[i] = u;
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -219,12 +241,12 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
             mbar_wait(&q_full, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t it = 0, tile_iter = 0;
-            uint32_t acc_uses[2] = {0, 0};
+            uint32_t uses0 = 0, uses1 = 0;
             for (uint32_t t = p.tile_begin + ci; t < p.tile_end; t += cstride, ++tile_iter) {
                 const uint32_t it0 = it;
                 for (uint32_t nb = 0; nb < NB; ++nb) {
                     const uint32_t ab = (NB == 2) ? nb : (tile_iter & 1u);       // accumulator buffer
-                    mbar_wait(&acc_empty[ab], (acc_uses[ab] & 1u) ^ 1u);          // the epilogue has drained its previous use
+                    mbar_wait(&acc_empty[ab], ((ab ? uses1 : uses0) & 1u) ^ 1u);  // the epilogue has drained its previous use
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t d_tmem = tmem + ab * 256u;
                     for (uint32_t kc = 0; kc < KC; ++kc) {
@@ -242,16 +264,18 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                         if (nb == NB - 1) umma_commit(&a_empty[st]);              // the stage is free once these MMAs retire
                     }
                     umma_commit(&acc_full[ab]);
-                    acc_uses[ab]++;
+                    if (ab) ++uses1; else ++uses0;
                 }
                 it = it0 + KC;
             }
         }
     } else {
-        // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
+        // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 (a hardware rule) and half of the columns =====
         const uint32_t quarter = (uint32_t)warp & 3u;
+        const uint32_t half = (uint32_t)(warp - 2) >> 2;             // 0 or 1
+        const uint32_t cols_per_warp = NMMA / 2;
         uint32_t tile_iter = 0;
-        uint32_t acc_uses[2] = {0, 0};
+        uint32_t uses0 = 0, uses1 = 0;
         const int dterm = 65025 * (int)p.dim;
         for (uint32_t t = p.tile_begin + ci; t < p.tile_end; t += cstride, ++tile_iter) {
             const uint32_t row = t * kBatchTileRows + quarter * 32u + (uint32_t)lane;
@@ -260,25 +284,42 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
             const int rowterm = row_ok ? (dterm - 510 * __ldg(p.row_sum + row)) : 0;
             for (uint32_t nb = 0; nb < NB; ++nb) {
                 const uint32_t ab = (NB == 2) ? nb : (tile_iter & 1u);
-                mbar_wait(&acc_full[ab], acc_uses[ab] & 1u);
-                acc_uses[ab]++;
+                const uint32_t uses = ab ? uses1 : uses0;
+                mbar_wait(&acc_full[ab], uses & 1u);
+                if (ab) ++uses1; else ++uses0;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                for (uint32_t c0 = 0; c0 < NMMA; c0 += 32) {
+                const uint32_t tbase = tmem + ((quarter * 32u) << 16) + ab * 256u;
+                for (uint32_t c0 = half * cols_per_warp; c0 < (half + 1) * cols_per_warp; c0 += 32) {
                     uint32_t r[32];
-                    tmem_ld32(tmem + ((quarter * 32u) << 16) + ab * 256u + c0, r);
+                    tmem_ld32(tbase + c0, r);
                     const uint32_t colbase = nb * NMMA + c0;
+                    uint32_t mask = 0;
 #pragma unroll
                     for (int i4 = 0; i4 < 8; ++i4) {
-                        const int4 ct = *reinterpret_cast<const int4*>(s_colterm + colbase + 4 * i4);
-                        const float4 th = *reinterpret_cast<const float4*>(s_thr + colbase + 4 * i4);
-                        const int cts[4] = {ct.x, ct.y, ct.z, ct.w};
-                        const float ths[4] = {th.x, th.y, th.z, th.w};
+                        const int4 u4 = *reinterpret_cast<const int4*>(s_u + colbase + 4 * i4);
+                        const int us[4] = {u4.x, u4.y, u4.z, u4.w};
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const int dot_i = 4 * (int)r[4 * i4 + j] + rowterm + cts[j];
+                            const int x = 4 * (int)r[4 * i4 + j] + rowterm;
+                            if (x >= us[j]) mask |= 1u << (4 * i4 + j);
+                        }
+                    }
+                    if (!row_ok) mask = 0;
+                    // rare: columns in which some lane survived the pre-test are re-read one at a time (warp-uniform
+                    // tcgen05.ld) and take the exact test
+                    uint32_t any = __reduce_or_sync(0xFFFFFFFFu, mask);
+                    while (any) {
+                        const uint32_t i = (uint32_t)__ffs(any) - 1u;
+                        any &= any - 1u;
+                        uint32_t sv;
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(sv) : "r"(tbase + c0 + i));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (mask & (1u << i)) {
+                            const uint32_t col = colbase + i;
+                            const int dot_i = 4 * (int)sv + rowterm + s_colterm[col];
                             const float kf = __fmul_rn((float)dot_i, inv_r);
-                            if (kf >= ths[j] && row_ok) {
-                                const uint32_t qi = g * QG + colbase + 4 * i4 + j;
+                            if (kf >= s_thr[col]) {
+                                const uint32_t qi = g * QG + col;
                                 const uint32_t slot = atomicAdd(p.cand_cnt + qi, 1u);
                                 if (slot < kBatchCap) p.cand[(size_t)qi * kBatchCap + slot] = make_key64(kf, row);
                                 else p.overflow[qi] = 1u;
