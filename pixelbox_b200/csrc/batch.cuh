@@ -167,6 +167,10 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
     int* s_colterm = reinterpret_cast<int*>(sA + kBatchStages * kBatchTileRows * 128);
     float* s_thr = reinterpret_cast<float*>(s_colterm + QG);
     int* s_u = reinterpret_cast<int*>(s_thr + QG);      // integer pre-test bound per query
+    // per-epilogue-warp staging of accepted candidates: pushes to global memory go out 32 at a time, so the
+    // ~1 us round trip of the slot atomic is paid once per 32 candidates instead of once per candidate
+    __shared__ u64 st_key[kBatchEpiWarps][64];
+    __shared__ uint32_t st_q[kBatchEpiWarps][64];
     __shared__ __align__(8) uint64_t q_full, a_full[kBatchStages], a_empty[kBatchStages], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base;
 
@@ -277,6 +281,24 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
         uint32_t tile_iter = 0;
         uint32_t uses0 = 0, uses1 = 0;
         const int dterm = 65025 * (int)p.dim;
+        u64* my_key = st_key[warp - 2];
+        uint32_t* my_q = st_q[warp - 2];
+        uint32_t staged = 0;                                         // warp-uniform
+        auto flush = [&]() {
+            __syncwarp();
+            for (uint32_t base = 0; base < staged; base += 32) {
+                const uint32_t e = base + (uint32_t)lane;
+                if (e < staged) {
+                    const uint32_t qi = my_q[e];
+                    const u64 key = my_key[e];
+                    const uint32_t slot = atomicAdd(p.cand_cnt + qi, 1u);
+                    if (slot < kBatchCap) p.cand[(size_t)qi * kBatchCap + slot] = key;
+                    else p.overflow[qi] = 1u;
+                }
+            }
+            staged = 0;
+            __syncwarp();
+        };
         for (uint32_t t = p.tile_begin + ci; t < p.tile_end; t += cstride, ++tile_iter) {
             const uint32_t row = t * kBatchTileRows + quarter * 32u + (uint32_t)lane;
             const bool row_ok = row < p.n;
@@ -314,17 +336,22 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                         uint32_t sv;
                         asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(sv) : "r"(tbase + c0 + i));
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        const uint32_t col = colbase + i;
+                        bool hit = false;
+                        float kf = 0.0f;
                         if (mask & (1u << i)) {
-                            const uint32_t col = colbase + i;
                             const int dot_i = 4 * (int)sv + rowterm + s_colterm[col];
-                            const float kf = __fmul_rn((float)dot_i, inv_r);
-                            if (kf >= s_thr[col]) {
-                                const uint32_t qi = g * QG + col;
-                                const uint32_t slot = atomicAdd(p.cand_cnt + qi, 1u);
-                                if (slot < kBatchCap) p.cand[(size_t)qi * kBatchCap + slot] = make_key64(kf, row);
-                                else p.overflow[qi] = 1u;
-                            }
+                            kf = __fmul_rn((float)dot_i, inv_r);
+                            hit = kf >= s_thr[col];
                         }
+                        const uint32_t hb = __ballot_sync(0xFFFFFFFFu, hit);
+                        if (hit) {
+                            const uint32_t pos = staged + (uint32_t)__popc(hb & ((1u << lane) - 1u));
+                            my_key[pos] = make_key64(kf, row);
+                            my_q[pos] = g * QG + col;
+                        }
+                        staged += (uint32_t)__popc(hb);
+                        if (staged >= 32) flush();
                     }
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -332,6 +359,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                 if (lane == 0) mbar_arrive(&acc_empty[ab]);
             }
         }
+        flush();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

@@ -147,8 +147,11 @@ __global__ void row_meta_kernel(const uint4* __restrict__ rows, uint32_t pitch16
         row_sum[r] = (int)s1;                      // sum of the raw bytes: the batched (u8 x u8) path needs it per row
         // corpus-wide bounds of inv_norm (positive floats order like their bit patterns): the batched epilogue's
         // integer pre-test is derived from them
-        atomicMin(inv_bounds + 0, __float_as_uint(inv));
-        atomicMax(inv_bounds + 1, __float_as_uint(inv));
+        // (read first: after the first few rows the bounds almost never move, and two contended atomics per row
+        // would dominate this kernel)
+        const uint32_t ib = __float_as_uint(inv);
+        if (ib < *reinterpret_cast<volatile uint32_t*>(inv_bounds + 0)) atomicMin(inv_bounds + 0, ib);
+        if (ib > *reinterpret_cast<volatile uint32_t*>(inv_bounds + 1)) atomicMax(inv_bounds + 1, ib);
     }
 }
 
