@@ -124,12 +124,6 @@ static float certificate_margin(uint32_t dim) {
     return (float)((4.0 * dim + 3232.0) * std::ldexp(1.0, -24));
 }
 
-// [104] = min, [105] = max of inv_norm over the rows ever written (as float bit patterns)
-static cudaError_t reset_inv_bounds(pbx_corpus* c) {
-    const uint32_t init[2] = {0x7f800000u, 0u};
-    return cudaMemcpy(c->d_tile_counter + 104, init, sizeof(init), cudaMemcpyHostToDevice);
-}
-
 static int free_corpus_buffers(pbx_corpus* c) {
     cudaFree(c->d_rows); cudaFree(c->d_inv); cudaFree(c->d_ids); cudaFree(c->d_rsum);
     c->d_rows = nullptr; c->d_inv = nullptr; c->d_ids = nullptr; c->d_rsum = nullptr;
@@ -303,7 +297,6 @@ extern "C" int pbx_corpus_create(uint32_t dim, uint64_t capacity_hint, int devic
     if (e == cudaSuccess) e = cudaMalloc(&c->d_cand_cnt, kMaxScanGrid * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_tile_counter, 512);      // [0] chunk counter, [32] global bin, +256 B exact-pass count
     if (e == cudaSuccess) e = cudaMemset(c->d_tile_counter, 0, 512);
-    if (e == cudaSuccess) e = reset_inv_bounds(c);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_hist, 2 * kHistBins * sizeof(uint32_t));     // scan histogram | seed histogram
     if (e == cudaSuccess) e = cudaMemset(c->d_hist, 0, 2 * kHistBins * sizeof(uint32_t));
     if (e == cudaSuccess) { c->d_exact_passes = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(c->d_tile_counter) + 256); }
@@ -392,7 +385,7 @@ static int upload_rows(pbx_corpus* c, uint64_t at, const int64_t* ids, const uin
             const unsigned warps_per_block = 8;
             const unsigned blocks = (unsigned)((m + warps_per_block - 1) / warps_per_block);
             row_meta_kernel<<<blocks, warps_per_block * 32, 0, c->copy_stream>>>(reinterpret_cast<const uint4*>(c->d_rows), c->pitch16, c->dim,
-                                                                                at + off, m, c->d_inv, c->d_rsum, c->d_tile_counter + 104);
+                                                                                at + off, m, c->d_inv, c->d_rsum);
             e = cudaGetLastError();
         }
         if (e == cudaSuccess) e = cudaEventRecord(done[slot], c->copy_stream);
@@ -436,7 +429,6 @@ extern "C" int pbx_corpus_load(pbx_corpus* c, const int64_t* image_ids, const ui
         CU_TRY(cudaSetDevice(c->device));
         CU_TRY(cudaDeviceSynchronize());
         c->n.store(0);
-        CU_TRY(reset_inv_bounds(c));
     }
     return pbx_corpus_append(c, image_ids, hashes, n);
 }
@@ -448,7 +440,6 @@ extern "C" int pbx_corpus_fill_synthetic(pbx_corpus* c, uint64_t n, uint64_t see
     CU_TRY(cudaSetDevice(c->device));
     CU_TRY(cudaDeviceSynchronize());
     c->n.store(0);
-    CU_TRY(reset_inv_bounds(c));
     int rc = reserve_rows(c, std::max<uint64_t>(n, 1));
     if (rc != PBX_OK) return rc;
     if (n == 0) return PBX_OK;
@@ -457,7 +448,7 @@ extern "C" int pbx_corpus_fill_synthetic(pbx_corpus* c, uint64_t n, uint64_t see
         const uint64_t m = std::min<uint64_t>(step, n - off);
         synth_fill_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_rows, c->pitch, c->dim, off, m, seed, first_row + off, c->d_ids);
         const unsigned blocks = (unsigned)((m + 7) / 8);
-        row_meta_kernel<<<blocks, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_rows), c->pitch16, c->dim, off, m, c->d_inv, c->d_rsum, c->d_tile_counter + 104);
+        row_meta_kernel<<<blocks, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_rows), c->pitch16, c->dim, off, m, c->d_inv, c->d_rsum);
     }
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaStreamSynchronize(c->stream));
@@ -630,9 +621,8 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
     mp.inv_norm = c->d_inv; mp.row_sum = c->d_rsum; mp.colterm = c->d_colterm; mp.thr = c->d_thr;
     mp.cand = c->d_bcand; mp.cand_cnt = c->d_bcnt; mp.overflow = c->d_boverflow;
     mp.n = n; mp.dim = c->dim; mp.kc = kc; mp.qg = qg; mp.groups = groups;
-    mp.inv_bounds = c->d_tile_counter + 104;
     const int grid = std::max<int>((int)groups, (c->sm_count / (int)groups) * (int)groups);
-    const size_t mma_smem = (size_t)qg * pitch + (size_t)kBatchStages * kBatchTileRows * 128 + (size_t)qg * 12 + 1024;
+    const size_t mma_smem = (size_t)qg * pitch + (size_t)kBatchStages * kBatchTileRows * 128 + (size_t)qg * 8 + (size_t)kBatchEpiWarps * 128 * 4 + 1024;
     BatchTightenParams tp;
     tp.cand = c->d_bcand; tp.cand_cnt = c->d_bcnt; tp.thr = c->d_thr; tp.keep = keep; tp.nq = nq;
 
@@ -640,7 +630,7 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
     // query; afterwards the threshold is the keep-th best of everything seen, so a round over 8x the rows seen adds
     // about 8 * keep candidates -- the buffers (kBatchCap entries) are cut back to keep between rounds
     const uint32_t tiles = (n + kBatchTileRows - 1) / kBatchTileRows;
-    const uint32_t grow = std::max<uint32_t>(2u, (kBatchCap / 2) / std::max<uint32_t>(keep, 1u));
+    const uint32_t grow = std::min<uint32_t>(4u, std::max<uint32_t>(2u, (kBatchCap / 2) / std::max<uint32_t>(keep, 1u)));
     uint32_t begin = 0, end = std::min<uint32_t>(tiles, 16u);
     while (begin < tiles) {
         mp.tile_begin = begin; mp.tile_end = end;

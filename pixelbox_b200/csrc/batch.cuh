@@ -22,7 +22,7 @@
 
 namespace pbx {
 
-constexpr int kBatchEpiWarps = 8;            // two per TMEM lane quarter, each takes half of an accumulator's columns
+constexpr int kBatchEpiWarps = 16;           // four per TMEM lane quarter, each takes a quarter of an accumulator's columns
 constexpr int kBatchThreads = 64 + 32 * kBatchEpiWarps;   // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr int kBatchStages = 4;              // corpus K-chunk ring: 4 x 16 KB
 constexpr int kBatchTileRows = 128;          // UMMA M
@@ -144,7 +144,6 @@ struct BatchMmaParams {
     u64* cand;                  // [nq_pad][kBatchCap]
     uint32_t* cand_cnt;         // [nq_pad]
     uint32_t* overflow;         // [nq_pad]
-    const uint32_t* inv_bounds; // [2] min / max inv_norm over the corpus (float bits)
     uint32_t n;                 // rows visible to this search
     uint32_t dim;
     uint32_t kc;                // K-chunks of 128 bytes per row (pitch / 128)
@@ -166,7 +165,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
     uint8_t* sA = bsm + (size_t)QG * KC * 128;          // [stages][128][128]
     int* s_colterm = reinterpret_cast<int*>(sA + kBatchStages * kBatchTileRows * 128);
     float* s_thr = reinterpret_cast<float*>(s_colterm + QG);
-    int* s_u = reinterpret_cast<int*>(s_thr + QG);      // integer pre-test bound per query
+    int* s_uw = reinterpret_cast<int*>(s_thr + QG);     // [epilogue warp][2 * 64] integer pre-test bounds, rebuilt per tile
     // per-epilogue-warp staging of accepted candidates: pushes to global memory go out 32 at a time, so the
     // ~1 us round trip of the slot atomic is paid once per 32 candidates instead of once per candidate
     __shared__ u64 st_key[kBatchEpiWarps][64];
@@ -188,28 +187,9 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kBatchEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    {
-        // Integer pre-test.  A score passes when fl(fl(dot_i) * inv_r) >= thr, dot_i = x + colterm with x = 4 S + rowterm
-        // known per (row, query).  With norm = 1 / inv_r in [norm_lo, norm_hi] over the whole corpus this implies
-        //   x >= thr * (thr >= 0 ? norm_lo : norm_hi) * (1 -+ 2^-20) - 2 - colterm =: u[q]
-        // so "x >= u[q]" (one integer compare) never rejects a passing score; the few survivors take the exact test.
-        const double norm_lo = 1.0 / (double)__uint_as_float(p.inv_bounds[1]);
-        const double norm_hi = 1.0 / (double)__uint_as_float(p.inv_bounds[0]);
-        for (uint32_t i = threadIdx.x; i < QG; i += blockDim.x) {
-            const int ct = p.colterm[g * QG + i];
-            const float th = p.thr[g * QG + i];
-            s_colterm[i] = ct;
-            s_thr[i] = th;
-            int u;
-            if (th == -__int_as_float(0x7f800000)) u = INT_MIN;
-            else if (th == __int_as_float(0x7f800000)) u = INT_MAX;
-            else {
-                double t = (double)th * (th >= 0.0f ? norm_lo * (1.0 - 9.6e-7) : norm_hi * (1.0 + 9.6e-7)) - 2.0 - (double)ct;
-                t = floor(t);
-                u = t <= -2147483648.0 ? INT_MIN : t >= 2147483647.0 ? INT_MAX : (int)t;
-            }
-            s_u[i] = u;
-        }
+    for (uint32_t i = threadIdx.x; i < QG; i += blockDim.x) {
+        s_colterm[i] = p.colterm[g * QG + i];
+        s_thr[i] = p.thr[g * QG + i];
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -274,15 +254,16 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
             }
         }
     } else {
-        // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 (a hardware rule) and half of the columns =====
+        // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 (a hardware rule) and a quarter of the columns =====
         const uint32_t quarter = (uint32_t)warp & 3u;
-        const uint32_t half = (uint32_t)(warp - 2) >> 2;             // 0 or 1
-        const uint32_t cols_per_warp = NMMA / 2;
+        const uint32_t slice = (uint32_t)(warp - 2) >> 2;            // 0..3
+        const uint32_t cols_per_warp = NMMA / 4;                     // 64 or 32
         uint32_t tile_iter = 0;
         uint32_t uses0 = 0, uses1 = 0;
         const int dterm = 65025 * (int)p.dim;
         u64* my_key = st_key[warp - 2];
         uint32_t* my_q = st_q[warp - 2];
+        int* my_u = s_uw + (size_t)(warp - 2) * 128;
         uint32_t staged = 0;                                         // warp-uniform
         auto flush = [&]() {
             __syncwarp();
@@ -304,6 +285,35 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
             const bool row_ok = row < p.n;
             const float inv_r = row_ok ? __ldg(p.inv_norm + row) : 0.0f;
             const int rowterm = row_ok ? (dterm - 510 * __ldg(p.row_sum + row)) : 0;
+            // Integer pre-test.  A score passes when fl(fl(dot_i) * inv_r) >= thr, dot_i = x + colterm with
+            // x = 4 S + rowterm.  With norm = 1 / inv_r inside [norm_lo, norm_hi] for the 32 rows of this warp that
+            // implies  x >= thr * (thr >= 0 ? norm_lo : norm_hi) - slack - colterm =: u[col]  (slack covers every
+            // rounding), so one integer compare per score never rejects a passing one; survivors take the exact test.
+            float inv_lo = row_ok ? inv_r : __int_as_float(0x7f800000), inv_hi = row_ok ? inv_r : 0.0f;
+#pragma unroll
+            for (int off = 16; off; off >>= 1) {
+                inv_lo = fminf(inv_lo, __shfl_xor_sync(0xFFFFFFFFu, inv_lo, off));
+                inv_hi = fmaxf(inv_hi, __shfl_xor_sync(0xFFFFFFFFu, inv_hi, off));
+            }
+            const float norm_lo = inv_hi > 0.0f ? 1.0f / inv_hi : 0.0f;
+            const float norm_hi = inv_hi > 0.0f ? 1.0f / inv_lo : 0.0f;
+            __syncwarp();
+            for (uint32_t cc = (uint32_t)lane; cc < NB * cols_per_warp; cc += 32) {
+                const uint32_t nb = cc / cols_per_warp, cw = cc - nb * cols_per_warp;
+                const uint32_t col = nb * NMMA + slice * cols_per_warp + cw;
+                const float th = s_thr[col];
+                int u;
+                if (th == -__int_as_float(0x7f800000)) u = INT_MIN;
+                else if (th == __int_as_float(0x7f800000)) u = INT_MAX;
+                else {
+                    const float tt = th * (th >= 0.0f ? norm_lo : norm_hi);
+                    const float lo = floorf(tt - fabsf(tt) * 2.0e-6f - 4.0f);
+                    const float uu = lo - (float)s_colterm[col];
+                    u = uu <= -2.0e9f ? INT_MIN : uu >= 2.0e9f ? INT_MAX : (int)floorf(uu - fabsf(uu) * 2.0e-7f - 1.0f);
+                }
+                my_u[nb * 64 + cw] = u;
+            }
+            __syncwarp();
             for (uint32_t nb = 0; nb < NB; ++nb) {
                 const uint32_t ab = (NB == 2) ? nb : (tile_iter & 1u);
                 const uint32_t uses = ab ? uses1 : uses0;
@@ -311,14 +321,18 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                 if (ab) ++uses1; else ++uses0;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tbase = tmem + ((quarter * 32u) << 16) + ab * 256u;
-                for (uint32_t c0 = half * cols_per_warp; c0 < (half + 1) * cols_per_warp; c0 += 32) {
+#ifdef PBX_EXP_BATCH_NOEPI
+                if (false)
+#endif
+                for (uint32_t cw0 = 0; cw0 < cols_per_warp; cw0 += 32) {
+                    const uint32_t c0 = slice * cols_per_warp + cw0;
                     uint32_t r[32];
                     tmem_ld32(tbase + c0, r);
                     const uint32_t colbase = nb * NMMA + c0;
                     uint32_t mask = 0;
 #pragma unroll
                     for (int i4 = 0; i4 < 8; ++i4) {
-                        const int4 u4 = *reinterpret_cast<const int4*>(s_u + colbase + 4 * i4);
+                        const int4 u4 = *reinterpret_cast<const int4*>(my_u + nb * 64 + cw0 + 4 * i4);
                         const int us[4] = {u4.x, u4.y, u4.z, u4.w};
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
@@ -327,15 +341,23 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                         }
                     }
                     if (!row_ok) mask = 0;
-                    // rare: columns in which some lane survived the pre-test are re-read one at a time (warp-uniform
-                    // tcgen05.ld) and take the exact test
+#ifdef PBX_EXP_BATCH_NOSLOW
+                    if (mask != 0x12345u) mask = 0;
+#endif
+                    // rare: for every column in which some lane survived the pre-test, those lanes take the exact test
                     uint32_t any = __reduce_or_sync(0xFFFFFFFFu, mask);
                     while (any) {
-                        const uint32_t i = (uint32_t)__ffs(any) - 1u;
+                        const uint32_t i = (uint32_t)__ffs(any) - 1u;       // warp-uniform
                         any &= any - 1u;
-                        uint32_t sv;
-                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(sv) : "r"(tbase + c0 + i));
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        uint32_t sv = 0;
+                        switch (i) {
+#define PBX_SEL(n) case n: sv = r[n]; break;
+                            PBX_SEL(0) PBX_SEL(1) PBX_SEL(2) PBX_SEL(3) PBX_SEL(4) PBX_SEL(5) PBX_SEL(6) PBX_SEL(7)
+                            PBX_SEL(8) PBX_SEL(9) PBX_SEL(10) PBX_SEL(11) PBX_SEL(12) PBX_SEL(13) PBX_SEL(14) PBX_SEL(15)
+                            PBX_SEL(16) PBX_SEL(17) PBX_SEL(18) PBX_SEL(19) PBX_SEL(20) PBX_SEL(21) PBX_SEL(22) PBX_SEL(23)
+                            PBX_SEL(24) PBX_SEL(25) PBX_SEL(26) PBX_SEL(27) PBX_SEL(28) PBX_SEL(29) PBX_SEL(30) PBX_SEL(31)
+#undef PBX_SEL
+                        }
                         const uint32_t col = colbase + i;
                         bool hit = false;
                         float kf = 0.0f;

@@ -126,7 +126,7 @@ prep_seed_kernel(const PrepSeedParams p) {
 
 // ---- per-row metadata: inv_norm[r] = 1/sqrt(sum c(r_i)^2) and row_sum[r] = sum r_i, one warp per row ----------------------
 __global__ void row_meta_kernel(const uint4* __restrict__ rows, uint32_t pitch16, uint32_t dim, uint64_t first, uint64_t n,
-                                float* __restrict__ inv_norm, int* __restrict__ row_sum, uint32_t* __restrict__ inv_bounds) {
+                                float* __restrict__ inv_norm, int* __restrict__ row_sum) {
     const uint64_t r = first + (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= first + n) return;
@@ -142,16 +142,8 @@ __global__ void row_meta_kernel(const uint4* __restrict__ rows, uint32_t pitch16
     if (lane == 0) {
         // sum (2v-255)^2 = 4 sum v^2 - 1020 sum v + 65025 d   (padding bytes are zero and excluded through d)
         long long n2 = 4ll * s2 - 1020ll * s1 + 65025ll * dim;
-        const float inv = (float)(1.0 / sqrt((double)n2));
-        inv_norm[r] = inv;
+        inv_norm[r] = (float)(1.0 / sqrt((double)n2));
         row_sum[r] = (int)s1;                      // sum of the raw bytes: the batched (u8 x u8) path needs it per row
-        // corpus-wide bounds of inv_norm (positive floats order like their bit patterns): the batched epilogue's
-        // integer pre-test is derived from them
-        // (read first: after the first few rows the bounds almost never move, and two contended atomics per row
-        // would dominate this kernel)
-        const uint32_t ib = __float_as_uint(inv);
-        if (ib < *reinterpret_cast<volatile uint32_t*>(inv_bounds + 0)) atomicMin(inv_bounds + 0, ib);
-        if (ib > *reinterpret_cast<volatile uint32_t*>(inv_bounds + 1)) atomicMax(inv_bounds + 1, ib);
     }
 }
 
