@@ -244,7 +244,7 @@ static cudaError_t init_kernel_attributes() {
     if (e == cudaSuccess) e = allow_smem(prep_seed_kernel, PBX_MAX_DIM * 2 + 1024);
     if (e == cudaSuccess) e = allow_smem(finalize_kernel<false>, fin_cap);
     if (e == cudaSuccess) e = allow_smem(finalize_kernel<true>, fin_cap);
-    if (e == cudaSuccess) e = allow_smem(batch_mma_kernel, 220 * 1024);
+    if (e == cudaSuccess) e = allow_smem(batch_mma_kernel, 210 * 1024);
     if (e == cudaSuccess) e = allow_smem(batch_tighten_kernel, kBatchCap * sizeof(u64));
     if (e == cudaSuccess) e = allow_smem(finalize_exact_kernel, fin_cap);
     return e;
