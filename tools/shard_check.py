@@ -56,6 +56,9 @@ def main():
     sc.fill_synthetic(per, 42)
     queries = synth.synth_queries(5, 4, d, per * world, 42)
     res = sc.search(queries, k)
+    # a batch large enough for the tensor-core path on every shard, then the all-gather + merge of [nq][k] records
+    bq = synth.synth_queries(6, 48, d, per * world, 42)
+    bres = sc.search(bq, k)
     dq = torch.from_numpy(queries).cuda()
     d_hits, d_cnt = sc.search_device(dq, len(queries), k)
     torch.cuda.synchronize()
@@ -70,6 +73,13 @@ def main():
             if not good:
                 print(f"MISMATCH synthetic q={qi}")
             ok &= good
+        for qi in range(0, len(bq), 5):
+            o_ids, o_dist, _, _ = oracle.topk(full, f_ids, bq[qi], k, 1e3, threads=oracle.max_threads())
+            good = list(bres[qi].ids) == list(o_ids) and np.array_equal(bres[qi].dist.view(np.uint32), o_dist.view(np.uint32))
+            if not good:
+                print(f"MISMATCH batched q={qi}")
+            ok &= good
+        ok &= sc.local.stats().batched_queries >= len(bq)
     sc.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
