@@ -73,8 +73,8 @@ typedef struct pbx_stats {
     uint32_t row_pitch;        /* bytes between rows in HBM (dim rounded up to 16) */
     uint64_t queries;          /* queries answered since create                    */
     uint64_t exact_passes;     /* queries that needed the exact tie-resolving pass */
-    float last_search_ms;      /* device time of the last pbx_search (CUDA events) */
-    float last_scan_ms;        /* ... of its scan kernels alone                    */
+    float last_search_ms;      /* device time of the last pbx_search (CUDA events); needs pbx_set_profiling */
+    float last_scan_ms;        /* ... of the scan kernel of its last query; needs pbx_set_profiling        */
     uint64_t last_bytes_scanned; /* rows * dim * nq of the last pbx_search         */
     int32_t device;
     int32_t sm_count;
@@ -172,6 +172,10 @@ PBX_API int pbx_get_stats(const pbx_corpus* c, pbx_stats* out);
 /* Tuning knob for tests: candidate slack of the fast pass (candidates = k + slack); 0 restores
  * the default.  A tiny slack forces the exact pass and must not change any result. */
 PBX_API int pbx_set_candidate_slack(pbx_corpus* c, uint32_t slack);
+/* Profiling: when enabled, pbx_search / pbx_search_hits record CUDA events around the whole search and around the
+ * scan kernel of its last query (pbx_stats.last_search_ms / last_scan_ms).  Off by default: an event between two
+ * kernels serialises launches that otherwise overlap (programmatic dependent launch). */
+PBX_API int pbx_set_profiling(pbx_corpus* c, int enabled);
 /* Batches of at least `min_queries` queries (per call) take the tensor-core path (tcgen05 kind::i8 contraction with
  * the top-k fused into the epilogue) when the row pitch allows it (dim a multiple of 128, <= 1024); smaller batches loop
  * over the single-query scan.  0 restores the default (16); UINT32_MAX disables the batched path.  Results are identical

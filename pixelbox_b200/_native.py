@@ -28,7 +28,7 @@ EXPORTS = [
     "pbx_corpus_create", "pbx_corpus_destroy", "pbx_corpus_load", "pbx_corpus_append", "pbx_corpus_fill_synthetic",
     "pbx_corpus_size", "pbx_corpus_dim", "pbx_corpus_read_rows", "pbx_corpus_synchronize", "pbx_search", "pbx_search_hits", "pbx_search_device",
     "pbx_merge_hits", "pbx_merge_hits_device", "pbx_cosine_distance_pairs", "pbx_get_stats", "pbx_set_candidate_slack",
-    "pbx_set_batch_min", "pbx_set_scan_ctas_per_sm", "pbx_last_error", "pbx_version", "pbx_device_count",
+    "pbx_set_profiling", "pbx_set_batch_min", "pbx_set_scan_ctas_per_sm", "pbx_last_error", "pbx_version", "pbx_device_count",
 ]
 
 HIT_DTYPE = np.dtype([("image_id", "<i8"), ("dist", "<f4"), ("dot", "<i4"), ("norm2", "<i4"), ("flags", "<u4")], align=True)
@@ -84,6 +84,7 @@ def lib() -> ctypes.CDLL:
         "pbx_cosine_distance_pairs": (i32, [i32, u8p, u8p, u64, u32, vp, vp, vp, vp]),
         "pbx_get_stats": (i32, [vp, ctypes.POINTER(PbxStats)]),
         "pbx_set_candidate_slack": (i32, [vp, u32]),
+        "pbx_set_profiling": (i32, [vp, i32]),
         "pbx_set_batch_min": (i32, [vp, u32]),
         "pbx_set_scan_ctas_per_sm": (i32, [vp, u32]),
         "pbx_last_error": (ctypes.c_char_p, []),

@@ -141,6 +141,10 @@ class Corpus:
     def set_candidate_slack(self, slack: int) -> None:
         nat.check(nat.lib().pbx_set_candidate_slack(self._h, int(slack)))
 
+    def set_profiling(self, enabled: bool) -> None:
+        """Record CUDA events around searches (stats().last_search_ms / last_scan_ms); off by default."""
+        nat.check(nat.lib().pbx_set_profiling(self._h, 1 if enabled else 0))
+
     def set_batch_min(self, n: int) -> None:
         """Batches of at least n queries per call use the tensor-core path (0 = default 16, 0xFFFFFFFF = never)."""
         nat.check(nat.lib().pbx_set_batch_min(self._h, int(n)))

@@ -68,7 +68,6 @@ struct pbx_corpus {
     QueryHeader* d_qh = nullptr;
     SearchStatus* d_status = nullptr;
     pbx_hit* d_hits = nullptr;
-    uint32_t* d_counts = nullptr;
     size_t hits_cap = 0;
     // scan scratch
     void* d_cand = nullptr;
@@ -81,7 +80,6 @@ struct pbx_corpus {
     uint8_t* h_queries = nullptr;
     size_t h_queries_cap = 0;
     pbx_hit* h_hits = nullptr;
-    uint32_t* h_counts = nullptr;
     size_t h_hits_cap = 0;
     uint8_t* h_stage = nullptr;       // append staging
     size_t h_stage_cap = 0;
@@ -110,6 +108,7 @@ struct pbx_corpus {
     uint32_t batch_min = 16;          // batches at least this large use the tensor-core path
     uint64_t batched_queries = 0;
     bool scan_timed = false;          // ev_s0/ev_s1 were recorded by the last enqueue
+    bool profiling = false;           // record CUDA events around the search / the scan (pbx_set_profiling)
 };
 
 static uint32_t default_keep(uint32_t k, uint32_t slack) {
@@ -194,22 +193,20 @@ static int ensure_query_scratch(pbx_corpus* c, uint32_t nq) {
 }
 
 static int ensure_hits(pbx_corpus* c, size_t n_hits, uint32_t nq) {
-    if (n_hits > c->hits_cap) {
+    // [n_hits] records followed by [nq] counts, in units of records (24 bytes each)
+    const size_t need = n_hits + ((size_t)nq * sizeof(uint32_t) + sizeof(pbx_hit) - 1) / sizeof(pbx_hit) + 1;
+    if (need > c->hits_cap) {
         CU_TRY(cudaDeviceSynchronize());
         cudaFree(c->d_hits); c->d_hits = nullptr; c->hits_cap = 0;
-        cudaFree(c->d_counts); c->d_counts = nullptr;
-        CU_TRY(cudaMalloc(&c->d_hits, n_hits * sizeof(pbx_hit)));
-        CU_TRY(cudaMalloc(&c->d_counts, std::max<size_t>(n_hits, 1024) * sizeof(uint32_t)));
-        c->hits_cap = n_hits;
+        CU_TRY(cudaMalloc(&c->d_hits, need * sizeof(pbx_hit)));
+        c->hits_cap = need;
     }
-    if (n_hits > c->h_hits_cap) {
-        cudaFreeHost(c->h_hits); cudaFreeHost(c->h_counts);
-        c->h_hits = nullptr; c->h_counts = nullptr; c->h_hits_cap = 0;
-        CU_TRY(cudaMallocHost(&c->h_hits, n_hits * sizeof(pbx_hit)));
-        CU_TRY(cudaMallocHost(&c->h_counts, std::max<size_t>(n_hits, 1024) * sizeof(uint32_t)));
-        c->h_hits_cap = n_hits;
+    if (need > c->h_hits_cap) {
+        cudaFreeHost(c->h_hits);
+        c->h_hits = nullptr; c->h_hits_cap = 0;
+        CU_TRY(cudaMallocHost(&c->h_hits, need * sizeof(pbx_hit)));
+        c->h_hits_cap = need;
     }
-    (void)nq;
     return PBX_OK;
 }
 
@@ -321,8 +318,8 @@ extern "C" void pbx_corpus_destroy(pbx_corpus* c) {
     free_corpus_buffers(c);
     cudaFree(c->d_queries); cudaFree(c->d_q16); cudaFree(c->d_qbytes); cudaFree(c->d_qh); cudaFree(c->d_status);
     cudaFree(c->d_qpad); cudaFree(c->d_colterm); cudaFree(c->d_thr); cudaFree(c->d_bcnt); cudaFree(c->d_boverflow); cudaFree(c->d_bcand);
-    cudaFree(c->d_hits); cudaFree(c->d_counts); cudaFree(c->d_cand); cudaFree(c->d_cand_cnt); cudaFree(c->d_tile_counter); cudaFree(c->d_hist);
-    cudaFreeHost(c->h_queries); cudaFreeHost(c->h_hits); cudaFreeHost(c->h_counts); cudaFreeHost(c->h_stage);
+    cudaFree(c->d_hits); cudaFree(c->d_cand); cudaFree(c->d_cand_cnt); cudaFree(c->d_tile_counter); cudaFree(c->d_hist);
+    cudaFreeHost(c->h_queries); cudaFreeHost(c->h_hits); cudaFreeHost(c->h_stage);
     if (c->ev_chain) cudaEventDestroy(c->ev_chain);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
@@ -891,17 +888,21 @@ extern "C" int pbx_search_hits(pbx_corpus* c, const uint8_t* queries, uint32_t n
         }
         memcpy(c->h_queries, queries + (size_t)q0 * c->dim, qbytes);
         CU_TRY(cudaMemcpyAsync(c->d_queries, c->h_queries, qbytes, cudaMemcpyHostToDevice, c->stream));
-        rc = enqueue_search(c, c->d_queries, b, k, max_dist, c->d_hits, c->d_counts, c->stream, true);
+        // hits and counts share one device buffer ([b*k] records, then [b] counts): one copy back
+        uint32_t* d_cnt = reinterpret_cast<uint32_t*>(c->d_hits + (size_t)b * k);
+        const uint32_t* h_cnt = reinterpret_cast<const uint32_t*>(c->h_hits + (size_t)b * k);
+        rc = enqueue_search(c, c->d_queries, b, k, max_dist, c->d_hits, d_cnt, c->stream, c->profiling);
         if (rc != PBX_OK) return rc;
-        CU_TRY(cudaMemcpyAsync(c->h_hits, c->d_hits, (size_t)b * k * sizeof(pbx_hit), cudaMemcpyDeviceToHost, c->stream));
-        CU_TRY(cudaMemcpyAsync(c->h_counts, c->d_counts, (size_t)b * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaMemcpyAsync(c->h_hits, c->d_hits, (size_t)b * k * sizeof(pbx_hit) + (size_t)b * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         CU_TRY(cudaStreamSynchronize(c->stream));
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1) == cudaSuccess) total_ms += ms;
-        if (!c->scan_timed || cudaEventElapsedTime(&c->last_scan_ms, c->ev_s0, c->ev_s1) != cudaSuccess) { c->last_scan_ms = 0.f; cudaGetLastError(); }
+        if (c->profiling) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1) == cudaSuccess) total_ms += ms;
+            if (!c->scan_timed || cudaEventElapsedTime(&c->last_scan_ms, c->ev_s0, c->ev_s1) != cudaSuccess) { c->last_scan_ms = 0.f; cudaGetLastError(); }
+        }
         total_bytes += c->last_bytes;
         memcpy(out_hits + (size_t)q0 * k, c->h_hits, (size_t)b * k * sizeof(pbx_hit));
-        memcpy(out_count + q0, c->h_counts, (size_t)b * sizeof(uint32_t));
+        memcpy(out_count + q0, h_cnt, (size_t)b * sizeof(uint32_t));
     }
     c->last_search_ms = total_ms;
     c->last_bytes = total_bytes;
@@ -1032,6 +1033,13 @@ extern "C" int pbx_set_candidate_slack(pbx_corpus* c, uint32_t slack) {
     if (!c) return fail(PBX_E_INVALID, "corpus is NULL");
     std::lock_guard<std::mutex> lk(c->mu);
     c->slack = slack;
+    return PBX_OK;
+}
+
+extern "C" int pbx_set_profiling(pbx_corpus* c, int enabled) {
+    if (!c) return fail(PBX_E_INVALID, "corpus is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->profiling = enabled != 0;
     return PBX_OK;
 }
 

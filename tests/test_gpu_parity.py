@@ -314,3 +314,49 @@ def test_async_back_to_back_with_forced_exact_passes():
                 assert np.array_equal(bits(hits[qi]["dist"][:cnt[qi]]), bits(o_dist))
                 assert np.array_equal(hits[qi]["dot"][:cnt[qi]], o_dot)
         assert c.stats().exact_passes >= 3 * nq
+
+
+def test_search_concurrent_with_append_sees_a_committed_prefix():
+    """The writer thread of Engine::start_indexing (src/engine.rs:186-203) appends while the UI thread searches
+    (src/ui/search.rs:22): every answer must be the reference's answer over some committed prefix of the rows."""
+    import threading
+    rng = np.random.default_rng(2024)
+    n, d, k, block = 60_000, 64, 25, 2_000
+    corpus = clustered(rng, n, d, 400, 3)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    queries = [corpus[int(rng.integers(0, n))] for _ in range(6)]
+    with Corpus(d, capacity_hint=block) as c:           # small hint: the buffers are re-allocated many times
+        c.append(ids[:block], corpus[:block])
+        errors, seen = [], []
+
+        def writer():
+            try:
+                for lo in range(block, n, block):
+                    c.append(ids[lo:lo + block], corpus[lo:lo + block])
+            except Exception as e:                      # pragma: no cover
+                errors.append(e)
+
+        t = threading.Thread(target=writer)
+        t.start()
+        while t.is_alive() or len(seen) < 12:
+            q = queries[len(seen) % len(queries)]
+            n0 = len(c)
+            r = c.search(q, k)[0]
+            n1 = len(c)
+            seen.append((q, n0, n1, r))
+            if len(seen) > 400:
+                break
+        t.join()
+        assert not errors
+        assert len(c) == n
+        prefixes = set()
+        for q, n0, n1, r in seen:
+            ok = False
+            for m in range(n0, n1 + 1, block):
+                o_ids, o_dist, _, _ = oracle.topk(corpus[:m], ids[:m], q, k, 1e3, threads=4)
+                if list(r.ids) == list(o_ids) and np.array_equal(bits(r.dist), bits(o_dist)):
+                    ok = True
+                    prefixes.add(m)
+                    break
+            assert ok, f"answer matches no committed prefix in [{n0}, {n1}]"
+        assert len(prefixes) >= 1

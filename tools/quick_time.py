@@ -47,9 +47,11 @@ for cps in cps_list:
     ms = e0.elapsed_time(e1) / iters
     gbs = rows * dim / ms / 1e6
     scan = []
+    c.set_profiling(True)
     for i in range(20):
         c.search(queries[i % nq], k)
         scan.append(c.stats().last_scan_ms)
+    c.set_profiling(False)
     scan_ms = float(np.median(scan))
     st = c.stats()
     print(f"rows={rows} dim={dim} k={k} ctas/sm={cps} grid={st.scan_grid} ms/query={ms:.4f} qps={1000/ms:.1f} "

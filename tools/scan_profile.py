@@ -17,6 +17,7 @@ L = nat.lib()
 L.pbx_debug_scan_profile.argtypes = [ctypes.c_void_p, ctypes.c_int]
 c = Corpus(dim, capacity_hint=rows)
 c.fill_synthetic(rows, 42, 0)
+c.set_profiling(True)
 q = synth.synth_queries(7, 8, dim, rows, 42)
 for i in range(3):
     c.search(q[i], k)
