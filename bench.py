@@ -167,6 +167,24 @@ def run_reference(args):
     return 0
 
 
+def ncu_traffic(rows: int, dim: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the scan kernel per launch, from the committed ncu --set full
+    capture of this workload (profiles/); None for any other workload."""
+    if rows != 10_000_000 or dim != 256:
+        return None
+    path = os.path.join(ROOT, "profiles", "r1c_scan_kernel_ncu_full_summary.csv")
+    try:
+        import csv
+        with open(path) as f:
+            r = list(csv.reader(f))
+        hdr, units, first = r[0], r[1], r[2]
+        rd = float(first[hdr.index("dram__bytes_read.sum")]) * (1e9 if units[hdr.index("dram__bytes_read.sum")].startswith("G") else 1e6)
+        wr = float(first[hdr.index("dram__bytes_write.sum")]) * (1e9 if units[hdr.index("dram__bytes_write.sum")].startswith("G") else 1e6)
+        return rd + wr
+    except Exception:
+        return None
+
+
 def workload_config(args):
     return {"workload": f"{args.rows_per_gpu // 1_000_000}M x {args.dim}-byte corpus per GPU, single query top-{args.k} "
                         f"(BASELINE configs[1]); row-sharded x{args.gpus}",
@@ -344,7 +362,8 @@ def run_ours(args):
                     "api": "pbx_search (C ABI, host buffers)" if world == 1 else "ShardedCorpus.search (host buffers, NCCL all-gather)"},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "kernel": "scan_kernel<16,1,false,3>" if dim == 256 else "scan_kernel", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(rows, dim),
+                         "traffic_source": "profiles/r1c_scan_kernel_ncu_full_summary.csv (ncu --set full, bytes per launch)",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": rows * dim, "launch_ms": scan_ms,
                          "share_of_step": scan_ms / ms_step},
             "clocks": clocks,

@@ -167,6 +167,12 @@ PBX_API int pbx_merge_hits_device(int device, const pbx_hit* d_gathered, const u
 PBX_API int pbx_cosine_distance_pairs(int device, const uint8_t* a, const uint8_t* b, uint64_t n, uint32_t dim,
                                       float* out_dist, int32_t* out_dot, int32_t* out_norm2_a, int32_t* out_norm2_b);
 
+/* ---- the ingest quantizer ---------------------------------------------------------------------
+ * Replaces: the f32 -> u8 map of mlhash, `128u8.saturating_add_signed((f*128.0).max(-128.0).min(128.0) as i8)`
+ * (src/image_hashes/efficientnet.rs:39; README.md:54 example [-1, 1, 0, 0.1] -> [0x00, 0xFF, 0x80, 0x8C]), for a batch
+ * of n floats in host memory, so embeddings produced elsewhere can be appended in the table's encoding. */
+PBX_API int pbx_quantize(int device, const float* embeddings, uint64_t n, uint8_t* out);
+
 /* ---- diagnostics ------------------------------------------------------------------------- */
 PBX_API int pbx_get_stats(const pbx_corpus* c, pbx_stats* out);
 /* Tuning knob for tests: candidate slack of the fast pass (candidates = k + slack); 0 restores

@@ -182,3 +182,11 @@ def cosine_distance_pairs(a, b, device: int = 0):
     nat.check(nat.lib().pbx_cosine_distance_pairs(int(device), nat.ptr(a), nat.ptr(b), n, d, nat.ptr(dist), nat.ptr(dot),
                                                   nat.ptr(na), nat.ptr(nb)))
     return dist, dot, na, nb
+
+
+def quantize(embeddings, device: int = 0) -> np.ndarray:
+    """pbx_quantize: the reference's f32 -> u8 encoder (src/image_hashes/efficientnet.rs:39) on the GPU."""
+    f = np.ascontiguousarray(np.asarray(embeddings, dtype=np.float32))
+    out = np.zeros(f.shape, np.uint8)
+    nat.check(nat.lib().pbx_quantize(int(device), nat.ptr(f), f.size, nat.ptr(out)))
+    return out

@@ -1005,6 +1005,26 @@ extern "C" int pbx_cosine_distance_pairs(int device, const uint8_t* a, const uin
     return rc;
 }
 
+extern "C" int pbx_quantize(int device, const float* embeddings, uint64_t n, uint8_t* out) {
+    if (n == 0) return PBX_OK;
+    if (!embeddings || !out) return fail(PBX_E_INVALID, "NULL argument");
+    if (pbx_device_count() == 0) return fail(PBX_E_NO_DEVICE, "no sm_100 device: pixelbox_b200 has no CPU fallback");
+    CU_TRY(cudaSetDevice(device));
+    float* din = nullptr;
+    uint8_t* dout = nullptr;
+    cudaError_t e = cudaMalloc(&din, n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&dout, n);
+    if (e == cudaSuccess) e = cudaMemcpy(din, embeddings, n * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        quantize_kernel<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 65535), 256>>>(din, n, dout);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout, n, cudaMemcpyDeviceToHost);
+    cudaFree(din); cudaFree(dout);
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? PBX_E_OOM : PBX_E_CUDA, "quantize failed: %s", cudaGetErrorString(e));
+    return PBX_OK;
+}
+
 extern "C" int pbx_get_stats(const pbx_corpus* cc, pbx_stats* out) {
     pbx_corpus* c = const_cast<pbx_corpus*>(cc);
     if (!c || !out) return fail(PBX_E_INVALID, "NULL argument");

@@ -286,6 +286,21 @@ __global__ void merge_hits_kernel(const pbx_hit* __restrict__ gathered, const ui
     if (threadIdx.x == 0) out_count[q] = n_out;
 }
 
+// ---- the ingest quantizer (src/image_hashes/efficientnet.rs:39), SURVEY.md 8f N3 --------------------------
+//   128u8.saturating_add_signed((f * 128.0f32).max(-128.0f32).min(128.0f32) as i8)
+// `as i8` truncates toward zero and saturates (so +128.0 -> 127); f32::max returns the other operand for a NaN,
+// so NaN -> -128 -> byte 0.  Note the asymmetry the reference lives with: this encoder is centred on 128, the
+// decoder of cosine_distance on 127.5 (src/engine.rs:576); both are kept bit-compatible, not "fixed".
+__global__ void quantize_kernel(const float* __restrict__ in, uint64_t n, uint8_t* __restrict__ out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        float x = __fmul_rn(in[i], 128.0f);
+        x = fmaxf(x, -128.0f);              // fmaxf(NaN, a) == a, like f32::max
+        x = fminf(x, 128.0f);
+        const int v = x >= 127.0f ? 127 : (x <= -128.0f ? -128 : (int)x);      // (int) truncates toward zero
+        out[i] = (uint8_t)(128 + v);
+    }
+}
+
 // ---- cosine_distance for explicit pairs (src/engine.rs:572-588 as a batch) -------------------------
 __global__ void pair_distance_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint64_t n, uint32_t dim,
                                      float* __restrict__ out_dist, int* __restrict__ out_dot, int* __restrict__ out_na,

@@ -96,3 +96,47 @@ def test_hash_without_image_row_is_dropped_like_the_inner_join(tmp_path):
     finally:
         eng.close()
         conn.close()
+
+
+def test_baseline_config0_100k_table_top50(tmp_path):
+    """BASELINE configs[0]: a 100k-image semantic_hashes table (256-byte hashes) in SQLite, single query, top-50.
+    Reference path = the verbatim SQL with the oracle UDF (one UDF call per scanned row, as upstream); GPU path =
+    Engine.open -> device corpus -> search; identical ids and f64 distances, for a right-click query and a dropped image."""
+    import time
+    from pixelbox_b200 import synth
+    n, d = 100_000, 256
+    rows = synth.synth_rows(1, 0, n, d)
+    rng = np.random.default_rng(2)
+    rows[5000:5040] = rows[5000]                                # a few exact duplicates: ties by image_id
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    path = str(tmp_path / "config0.db")
+    conn = sqlite_oracle.make_db(path, ids, rows)
+    eng = Engine.open(path)
+    try:
+        for q in (rows[12345], rows[5000], rng.integers(0, 256, d, dtype=np.uint8)):
+            t0 = time.perf_counter()
+            want = sqlite_oracle.query(conn, bytes(q), 1e3, 50)
+            t_sql = time.perf_counter() - t0
+            res = eng.corpus.search(q, 50, 1e3)[0]
+            assert list(res.ids) == [w[0] for w in want]
+            assert [float(x) for x in res.dist] == [w[1] for w in want]
+            assert t_sql > 0
+        eng.query_by_image_hash_from_image(IndexedImage(visual_hash=bytes(rows[12345])))
+        got = eng.get_query_results()
+        want100 = sqlite_oracle.query(conn, bytes(rows[12345]), 1e3, 100)
+        assert [g.id for g in got] == [w[0] for w in want100] and got[0].id == 12346 and got[0].distance_from_query <= 1e-6
+    finally:
+        eng.close()
+        conn.close()
+
+
+def test_quantizer_matches_reference_encoder():
+    """src/image_hashes/efficientnet.rs:39 on the GPU against the oracle, including the README example and the edges."""
+    from oracle import oracle
+    from pixelbox_b200.corpus import quantize
+    assert list(quantize([-1.0, 1.0, 0.0, 0.1])) == [0x00, 0xFF, 0x80, 0x8C]            # README.md:54
+    special = np.array([np.nan, np.inf, -np.inf, 2.0, -2.0, 0.999, -0.999, 0.9921875, 0.99218, -0.0, 1e-9, -1e-9,
+                        127.0 / 128.0, 126.9999 / 128.0, -127.5 / 128.0, 0.0078125, 0.00781249], np.float32)
+    rng = np.random.default_rng(5)
+    x = np.concatenate([special, rng.uniform(-1.2, 1.2, 20000).astype(np.float32), np.tanh(rng.normal(0, 1, 20000)).astype(np.float32)])
+    assert np.array_equal(quantize(x), oracle.quantize(x))
