@@ -102,6 +102,8 @@ struct pbx_corpus {
     uint32_t* d_bcnt = nullptr;
     uint32_t* d_boverflow = nullptr;
     u64* d_bcand = nullptr;           // [batch_pad][kBatchCap]
+    uint32_t* d_bhist = nullptr;      // [batch_pad][kBatchHistBins]
+    float* d_binvq = nullptr;         // [batch_pad]
     CUtensorMap map_rows, map_q;
     uint64_t map_rows_gen = ~0ull;
     uint32_t map_q_pad = 0, map_q_box = 0;
@@ -318,6 +320,7 @@ extern "C" void pbx_corpus_destroy(pbx_corpus* c) {
     free_corpus_buffers(c);
     cudaFree(c->d_queries); cudaFree(c->d_q16); cudaFree(c->d_qbytes); cudaFree(c->d_qh); cudaFree(c->d_status);
     cudaFree(c->d_qpad); cudaFree(c->d_colterm); cudaFree(c->d_thr); cudaFree(c->d_bcnt); cudaFree(c->d_boverflow); cudaFree(c->d_bcand);
+    cudaFree(c->d_bhist); cudaFree(c->d_binvq);
     cudaFree(c->d_hits); cudaFree(c->d_cand); cudaFree(c->d_cand_cnt); cudaFree(c->d_tile_counter); cudaFree(c->d_hist);
     cudaFreeHost(c->h_queries); cudaFreeHost(c->h_hits); cudaFreeHost(c->h_stage);
     if (c->ev_chain) cudaEventDestroy(c->ev_chain);
@@ -568,6 +571,7 @@ static int ensure_batch_scratch(pbx_corpus* c, uint32_t nq_pad) {
     if (nq_pad <= c->batch_pad) return PBX_OK;
     CU_TRY(cudaDeviceSynchronize());
     cudaFree(c->d_qpad); cudaFree(c->d_colterm); cudaFree(c->d_thr); cudaFree(c->d_bcnt); cudaFree(c->d_boverflow); cudaFree(c->d_bcand);
+    cudaFree(c->d_bhist); cudaFree(c->d_binvq); c->d_bhist = nullptr; c->d_binvq = nullptr;
     c->d_qpad = nullptr; c->d_colterm = nullptr; c->d_thr = nullptr; c->d_bcnt = nullptr; c->d_boverflow = nullptr; c->d_bcand = nullptr;
     c->batch_pad = 0; c->map_q_pad = 0;
     CU_TRY(cudaMalloc(&c->d_qpad, (size_t)nq_pad * c->pitch));
@@ -576,6 +580,8 @@ static int ensure_batch_scratch(pbx_corpus* c, uint32_t nq_pad) {
     CU_TRY(cudaMalloc(&c->d_bcnt, (size_t)nq_pad * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&c->d_boverflow, (size_t)nq_pad * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&c->d_bcand, (size_t)nq_pad * kBatchCap * sizeof(u64)));
+    CU_TRY(cudaMalloc(&c->d_bhist, (size_t)nq_pad * kBatchHistBins * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&c->d_binvq, (size_t)nq_pad * sizeof(float)));
     c->batch_pad = nq_pad;
     return PBX_OK;
 }
@@ -610,6 +616,7 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
     bp.queries = d_queries; bp.nq = nq; bp.dim = c->dim; bp.pitch = pitch;
     bp.qpad = c->d_qpad; bp.q16 = c->d_q16; bp.qbytes = c->d_qbytes; bp.qh = c->d_qh;
     bp.colterm = c->d_colterm; bp.thr = c->d_thr; bp.cand_cnt = c->d_bcnt; bp.overflow = c->d_boverflow;
+    bp.bhist = c->d_bhist; bp.inv_q = c->d_binvq;
     batch_prep_kernel<<<nq_pad, 128, 0, s>>>(bp);
     CU_TRY(cudaGetLastError());
 
@@ -617,9 +624,10 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
     mp.map_rows = c->map_rows; mp.map_q = c->map_q;
     mp.inv_norm = c->d_inv; mp.row_sum = c->d_rsum; mp.colterm = c->d_colterm; mp.thr = c->d_thr;
     mp.cand = c->d_bcand; mp.cand_cnt = c->d_bcnt; mp.overflow = c->d_boverflow;
+    mp.bhist = c->d_bhist; mp.inv_q = c->d_binvq; mp.thr_live = c->d_thr; mp.keep = keep;
     mp.n = n; mp.dim = c->dim; mp.kc = kc; mp.qg = qg; mp.groups = groups;
     const int grid = std::max<int>((int)groups, (c->sm_count / (int)groups) * (int)groups);
-    const size_t mma_smem = (size_t)qg * pitch + (size_t)kBatchStages * kBatchTileRows * 128 + (size_t)qg * 8 + (size_t)kBatchEpiWarps * 128 * 4 + 1024;
+    const size_t mma_smem = (size_t)qg * pitch + (size_t)kBatchStages * kBatchTileRows * 128 + (size_t)qg * 12 + (size_t)kBatchEpiWarps * 128 * 4 + 1024;
     BatchTightenParams tp;
     tp.cand = c->d_bcand; tp.cand_cnt = c->d_bcnt; tp.thr = c->d_thr; tp.keep = keep; tp.nq = nq;
 
@@ -627,7 +635,8 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
     // query; afterwards the threshold is the keep-th best of everything seen, so a round over 8x the rows seen adds
     // about 8 * keep candidates -- the buffers (kBatchCap entries) are cut back to keep between rounds
     const uint32_t tiles = (n + kBatchTileRows - 1) / kBatchTileRows;
-    const uint32_t grow = std::min<uint32_t>(4u, std::max<uint32_t>(2u, (kBatchCap / 2) / std::max<uint32_t>(keep, 1u)));
+    // (thresholds also tighten inside a round, from per-query histograms: the growth factor can be generous)
+    const uint32_t grow = std::min<uint32_t>(16u, std::max<uint32_t>(2u, (kBatchCap / 2) / std::max<uint32_t>(keep, 1u)) * 2u);
     uint32_t begin = 0, end = std::min<uint32_t>(tiles, 16u);
     while (begin < tiles) {
         mp.tile_begin = begin; mp.tile_end = end;

@@ -28,6 +28,7 @@ constexpr int kBatchStages = 4;              // corpus K-chunk ring: 4 x 16 KB
 constexpr int kBatchTileRows = 128;          // UMMA M
 constexpr uint32_t kBatchCap = 4096;         // candidate buffer entries per query
 constexpr uint32_t kBatchQueryBytes = 128 * 1024;   // resident queries per CTA
+constexpr uint32_t kBatchHistBins = 256;            // per-query histogram of accepted keys over kappa in [-1, 1]
 
 // ---- PTX helpers -------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -98,6 +99,8 @@ struct BatchPrepParams {
     float* thr;                 // [nq_pad]  -inf for real queries, +inf for padding
     uint32_t* cand_cnt;         // [nq_pad]
     uint32_t* overflow;         // [nq_pad]
+    uint32_t* bhist;            // [nq_pad][kBatchHistBins], zeroed here
+    float* inv_q;               // [nq_pad]
 };
 
 __global__ void batch_prep_kernel(const BatchPrepParams p) {
@@ -130,7 +133,9 @@ __global__ void batch_prep_kernel(const BatchPrepParams p) {
         p.thr[q] = real ? -__int_as_float(0x7f800000) : __int_as_float(0x7f800000);
         p.cand_cnt[q] = 0;
         p.overflow[q] = 0;
+        p.inv_q[q] = real ? (float)(1.0 / sqrt((double)N)) : 0.0f;
     }
+    for (uint32_t i = threadIdx.x; i < kBatchHistBins; i += blockDim.x) p.bhist[(size_t)q * kBatchHistBins + i] = 0;
 }
 
 // ---- the contraction + selection kernel ---------------------------------------------------------------------
@@ -144,6 +149,10 @@ struct BatchMmaParams {
     u64* cand;                  // [nq_pad][kBatchCap]
     uint32_t* cand_cnt;         // [nq_pad]
     uint32_t* overflow;         // [nq_pad]
+    uint32_t* bhist;            // [nq_pad][kBatchHistBins] accepted keys per query and kappa bin (in-round tightening)
+    const float* inv_q;         // [nq_pad] 1 / |c(q)|  (0 for padding queries)
+    float* thr_live;            // == thr, written: thresholds tightened while the round runs
+    uint32_t keep;
     uint32_t n;                 // rows visible to this search
     uint32_t dim;
     uint32_t kc;                // K-chunks of 128 bytes per row (pitch / 128)
@@ -165,7 +174,8 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
     uint8_t* sA = bsm + (size_t)QG * KC * 128;          // [stages][128][128]
     int* s_colterm = reinterpret_cast<int*>(sA + kBatchStages * kBatchTileRows * 128);
     float* s_thr = reinterpret_cast<float*>(s_colterm + QG);
-    int* s_uw = reinterpret_cast<int*>(s_thr + QG);     // [epilogue warp][2 * 64] integer pre-test bounds, rebuilt per tile
+    float* s_invq = s_thr + QG;
+    int* s_uw = reinterpret_cast<int*>(s_invq + QG);    // [epilogue warp][2 * 64] integer pre-test bounds, rebuilt per tile
     // per-epilogue-warp staging of accepted candidates: pushes to global memory go out 32 at a time, so the
     // ~1 us round trip of the slot atomic is paid once per 32 candidates instead of once per candidate
     __shared__ u64 st_key[kBatchEpiWarps][64];
@@ -190,6 +200,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
     for (uint32_t i = threadIdx.x; i < QG; i += blockDim.x) {
         s_colterm[i] = p.colterm[g * QG + i];
         s_thr[i] = p.thr[g * QG + i];
+        s_invq[i] = p.inv_q[g * QG + i];
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -275,12 +286,59 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                     const uint32_t slot = atomicAdd(p.cand_cnt + qi, 1u);
                     if (slot < kBatchCap) p.cand[(size_t)qi * kBatchCap + slot] = key;
                     else p.overflow[qi] = 1u;
+                    // every accepted key is counted once in its query's kappa histogram
+                    const float kap = __fmul_rn(key64_kappa(key), p.inv_q[qi]);
+                    const int bin = min(max(__float2int_rd(__fmul_rn(__fadd_rn(kap, 1.0f), (float)(kBatchHistBins / 2))), 0), (int)kBatchHistBins - 1);
+                    atomicAdd(p.bhist + (size_t)qi * kBatchHistBins + bin, 1u);
                 }
             }
             staged = 0;
             __syncwarp();
         };
+        // In-round tightening.  At refresh points this CTA turns the histograms of the queries it is responsible for
+        // (column j with j % CTAs-in-group == its index) into thresholds -- the lower edge of the highest bin with at
+        // least `keep` accepted keys at or above it, a valid bound because those keys are real rows -- publishes them
+        // with an atomic max, and every epilogue thread re-reads the published threshold of one column.
+        const uint32_t ethread = (uint32_t)threadIdx.x - 64u;          // 0 .. 32 * kBatchEpiWarps - 1
+        auto refresh = [&]() {
+            flush();
+            for (uint32_t j = ethread; j < QG; j += 32u * kBatchEpiWarps) {
+                const uint32_t qi = g * QG + j;
+                if (j % cstride == ci % cstride && s_invq[j] > 0.0f) {
+                    const uint4* hp = reinterpret_cast<const uint4*>(p.bhist + (size_t)qi * kBatchHistBins);
+                    uint32_t run = 0;
+                    int bstar = -1;
+                    for (int c4 = (int)kBatchHistBins / 4 - 1; c4 >= 0 && bstar < 0; --c4) {
+                        const uint4 v = __ldcg(hp + c4);
+                        const uint32_t h[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int i = 3; i >= 0; --i) {
+                            run += h[i];
+                            if (bstar < 0 && run >= p.keep) bstar = 4 * c4 + i;
+                        }
+                    }
+                    if (bstar > 0) {
+                        // kappa-bin edge back to kappa' units, nudged down so that no key of bin >= b* falls below it
+                        const float edge = (float)bstar * (2.0f / (float)kBatchHistBins) - 1.0f;
+                        float t = edge / s_invq[j];
+                        t = t - fabsf(t) * 4.0e-6f - 1.0e-3f;
+                        // float atomic max (thresholds may be negative): compare-and-swap on the bit pattern
+                        float* addr = p.thr_live + qi;
+                        float old = *reinterpret_cast<volatile float*>(addr);
+                        while (t > old) {
+                            const uint32_t prev = atomicCAS(reinterpret_cast<uint32_t*>(addr), __float_as_uint(old), __float_as_uint(t));
+                            if (prev == __float_as_uint(old)) break;
+                            old = __uint_as_float(prev);
+                        }
+                    }
+                }
+                const float live = *reinterpret_cast<volatile float*>(p.thr_live + qi);
+                if (live > s_thr[j]) s_thr[j] = live;
+            }
+            __syncwarp();
+        };
         for (uint32_t t = p.tile_begin + ci; t < p.tile_end; t += cstride, ++tile_iter) {
+            if (tile_iter >= 4 && ((tile_iter & (tile_iter - 1)) == 0 || (tile_iter & 63u) == 0)) refresh();
             const uint32_t row = t * kBatchTileRows + quarter * 32u + (uint32_t)lane;
             const bool row_ok = row < p.n;
             const float inv_r = row_ok ? __ldg(p.inv_norm + row) : 0.0f;
