@@ -635,8 +635,10 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
     // query; afterwards the threshold is the keep-th best of everything seen, so a round over 8x the rows seen adds
     // about 8 * keep candidates -- the buffers (kBatchCap entries) are cut back to keep between rounds
     const uint32_t tiles = (n + kBatchTileRows - 1) / kBatchTileRows;
-    // (thresholds also tighten inside a round, from per-query histograms: the growth factor can be generous)
-    const uint32_t grow = std::min<uint32_t>(16u, std::max<uint32_t>(2u, (kBatchCap / 2) / std::max<uint32_t>(keep, 1u)) * 2u);
+    // A round over g times the rows seen so far adds about g * keep candidates per query before any tightening; the
+    // buffers hold kBatchCap, so g = cap / (4 keep) + 1 leaves a wide margin.  Inside long rounds the thresholds also
+    // tighten from per-query histograms, which is what keeps the last rounds cheap.
+    const uint32_t grow = std::max<uint32_t>(2u, kBatchCap / (4u * std::max<uint32_t>(keep, 1u))) + 1u;
     uint32_t begin = 0, end = std::min<uint32_t>(tiles, 16u);
     while (begin < tiles) {
         mp.tile_begin = begin; mp.tile_end = end;
