@@ -563,8 +563,11 @@ static int make_u8_map(CUtensorMap* m, void* base, uint64_t rows, uint32_t pitch
     return PBX_OK;
 }
 
-static bool batch_eligible(const pbx_corpus* c, uint32_t nq, uint32_t n) {
-    return nq >= c->batch_min && c->pitch % 128 == 0 && c->pitch <= 1024 && n >= 16u * kBatchTileRows;
+static bool batch_eligible(const pbx_corpus* c, uint32_t nq, uint32_t n, uint32_t k) {
+    // per-query candidate buffers hold kBatchCap keys and are cut back to keep = k + slack between rounds: the scheme
+    // needs keep well below the capacity, larger k loops over the single-query scan
+    const uint32_t keep = default_keep(k, c->slack);
+    return nq >= c->batch_min && c->pitch % 128 == 0 && c->pitch <= 1024 && n >= 16u * kBatchTileRows && keep * 8u <= kBatchCap;
 }
 
 static int ensure_batch_scratch(pbx_corpus* c, uint32_t nq_pad) {
@@ -710,7 +713,7 @@ static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, 
     if (n == 0) {
         empty_result_kernel<<<64, 256, 0, s>>>(d_hits, d_count, nq, k);
         CU_TRY(cudaGetLastError());
-    } else if (batch_eligible(c, nq, n)) {
+    } else if (batch_eligible(c, nq, n, k)) {
         for (uint32_t q0 = 0; q0 < nq; q0 += 1024) {
             const uint32_t b = std::min<uint32_t>(1024u, nq - q0);
             int rc = enqueue_search_batched(c, d_queries + (size_t)q0 * c->dim, b, k, max_dist, d_hits + (size_t)q0 * k, d_count + q0, s, n);
