@@ -204,6 +204,63 @@ __device__ inline void block_order_keys(u64* buf, u64* sorted, uint32_t m) {
     }
 }
 
+// Smallest key of a[0..n) (n >= 1), all threads; barrier before; ends with a barrier.  Result in *s_out (shared).
+__device__ inline void block_min_key(const u64* a, uint32_t n, u64* s_out, u64* s_scratch /* [32] shared */) {
+    u64 m = ~0ull;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) m = a[i] < m ? a[i] : m;
+    for (int off = 16; off; off >>= 1) {
+        const u64 o = __shfl_xor_sync(0xFFFFFFFFu, m, off);
+        m = o < m ? o : m;
+    }
+    if ((threadIdx.x & 31) == 0) s_scratch[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u64 r = ~0ull;
+        for (uint32_t w = 0; w < (blockDim.x + 31) / 32; ++w) r = s_scratch[w] < r ? s_scratch[w] : r;
+        *s_out = r;
+    }
+    __syncthreads();
+}
+
+// From m unique keys in buf to the candidate set: the best min(m, keep) keys in sorted[0..nc) plus the kappa of
+// the k-th and of the last of them (what the certificate needs).  Small sets are fully ordered by rank counting;
+// large ones (large k) only go through two radix selects and two min-reductions -- the order by kappa is never
+// needed downstream.  All threads; barrier before; ends with a barrier.  buf is clobbered.
+__device__ inline uint32_t block_candidates(u64* buf, u64* sorted, uint32_t m, uint32_t keep, uint32_t k, uint32_t cap,
+                                            uint32_t* s_cnt, u64* s_tau, SelectScratch* s_sel, u64* s_scratch,
+                                            float* s_kappa_k, float* s_kappa_last) {
+    if (m <= kFinalThreads) {
+        block_order_keys(buf, sorted, m);
+        const uint32_t nc = m < keep ? m : keep;
+        if (threadIdx.x == 0) {
+            *s_kappa_k = (nc >= k && k > 0) ? key64_kappa(sorted[k - 1]) : 0.0f;
+            *s_kappa_last = nc > 0 ? key64_kappa(sorted[nc - 1]) : 0.0f;
+        }
+        __syncthreads();
+        return nc;
+    }
+    TopBuf<u64> tb{buf, s_cnt, s_tau, cap, keep};
+    if (threadIdx.x == 0) *s_cnt = m;
+    __syncthreads();
+    if (m > keep) block_select_top(tb, s_sel);
+    const uint32_t nc = *s_cnt;
+    for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) sorted[i] = buf[i];
+    __syncthreads();
+    __shared__ u64 s_min;
+    block_min_key(sorted, nc, &s_min, s_scratch);
+    if (threadIdx.x == 0) *s_kappa_last = key64_kappa(s_min);
+    if (nc > k && k > 0) {
+        TopBuf<u64> tk{buf, s_cnt, s_tau, cap, k};
+        block_select_top(tk, s_sel);                       // buf is scratch from here on
+        block_min_key(buf, k, &s_min, s_scratch);
+        if (threadIdx.x == 0) *s_kappa_k = key64_kappa(s_min);
+    } else if (threadIdx.x == 0) {
+        *s_kappa_k = (nc == k && k > 0) ? key64_kappa(s_min) : 0.0f;
+    }
+    __syncthreads();
+    return nc;
+}
+
 template <bool BATCH>
 __global__ void __launch_bounds__(kFinalThreads, 1)
 finalize_kernel(const FinalizeParams p) {
@@ -227,6 +284,7 @@ finalize_kernel(const FinalizeParams p) {
     __shared__ float s_kappa_k, s_kappa_last, s_sa;
     __shared__ uint32_t s_listcnt[kMaxScanGrid];
     __shared__ uint32_t s_warp[32];
+    __shared__ u64 s_scratch64[32];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t q = BATCH ? blockIdx.x : 0u;
@@ -315,15 +373,19 @@ finalize_kernel(const FinalizeParams p) {
             __syncthreads();
             PBX_FIN_STAMP(3);
             const uint32_t m = s_cnt;                                   // <= mprime
-            // ---- 1c. order by key ------------------------------------------------------------------------
-            block_order_keys(buf, sorted, m);
-            nc = m < p.keep ? m : p.keep;
+            // ---- 1c. candidate set + the two kappas of the certificate ------------------------------------
+            nc = block_candidates(buf, sorted, m, p.keep, p.k, p.cap, &s_cnt, &s_tau, &s_sel, s_scratch64, &s_kappa_k, &s_kappa_last);
         } else {
             // ---- 1'. fallback: more ties in one bin than the buffer holds ----------------------------------
             TopBuf<u64> tb{buf, &s_cnt, &s_tau, p.cap, p.keep};
             merge_rounds(p, tb, s_listcnt, s_maxcnt, &s_pushed);
             nc = s_cnt < p.keep ? s_cnt : p.keep;
             for (uint32_t i = tid; i < nc; i += blockDim.x) sorted[i] = buf[i];
+            __syncthreads();
+            if (tid == 0) {                                   // merge_rounds leaves the buffer sorted best first
+                s_kappa_k = (nc >= p.k && p.k > 0) ? key64_kappa(sorted[p.k - 1]) : 0.0f;
+                s_kappa_last = nc > 0 ? key64_kappa(sorted[nc - 1]) : 0.0f;
+            }
             __syncthreads();
         }
     } else {
@@ -343,12 +405,7 @@ finalize_kernel(const FinalizeParams p) {
             block_select_top(tb, &s_sel);
         }
         const uint32_t m = s_cnt;
-        block_order_keys(buf, sorted, m);
-        nc = m < p.keep ? m : p.keep;
-    }
-    if (tid == 0) {
-        s_kappa_k = (nc >= p.k && p.k > 0) ? key64_kappa(sorted[p.k - 1]) : 0.0f;
-        s_kappa_last = nc > 0 ? key64_kappa(sorted[nc - 1]) : 0.0f;
+        nc = block_candidates(buf, sorted, m, p.keep, p.k, p.cap, &s_cnt, &s_tau, &s_sel, s_scratch64, &s_kappa_k, &s_kappa_last);
     }
 
     PBX_FIN_STAMP(4);
