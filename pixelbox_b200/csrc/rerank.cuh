@@ -182,7 +182,10 @@ __device__ inline void block_order_keys(u64* buf, u64* sorted, uint32_t m) {
         const uint32_t e = tid / tpe, sub = tid - e * tpe;
         const u64 me = e < m ? buf[e] : 0ull;
         uint32_t rank = 0;
-        for (uint32_t j = sub; j < m; j += tpe) rank += (buf[j] > me) ? 1u : 0u;
+        if (e < m) {                                       // idle groups only take part in the shuffles
+#pragma unroll 4
+            for (uint32_t j = sub; j < m; j += tpe) rank += (buf[j] > me) ? 1u : 0u;
+        }
         for (uint32_t off = tpe >> 1; off; off >>= 1) rank += __shfl_xor_sync(0xFFFFFFFFu, rank, off);
         if (e < m && sub == 0) sorted[rank] = me;
         __syncthreads();
@@ -510,7 +513,10 @@ finalize_kernel(const FinalizeParams p) {
         RerankEntry me; me.od = 0; me.slot = 0; me.id = 0;
         if (c < nc) me = ent[c];
         uint32_t pos = 0;
-        for (uint32_t j = sub; j < nc; j += tpe) pos += rerank_before(ent[j], me) ? 1u : 0u;
+        if (c < nc) {
+#pragma unroll 4
+            for (uint32_t j = sub; j < nc; j += tpe) pos += rerank_before(ent[j], me) ? 1u : 0u;
+        }
         for (uint32_t off = tpe >> 1; off; off >>= 1) pos += __shfl_xor_sync(0xFFFFFFFFu, pos, off);
         if (c < nc && sub == 0) {
             const float dist = dists[c];
