@@ -159,6 +159,24 @@ PBX_API int pbx_merge_hits(const pbx_hit* gathered, const uint32_t* counts, uint
 PBX_API int pbx_merge_hits_device(int device, const pbx_hit* d_gathered, const uint32_t* d_counts, uint32_t n_shards,
                                   uint32_t nq, uint32_t k, pbx_hit* d_out_hits, uint32_t* d_out_count, void* cuda_stream);
 
+/* ---- the exchange step over NVLink peer memory (one process per GPU) ---------------------------------
+ * Replaces: nothing upstream (PixelBox is single-process); it is the one exchange step of the row-sharded path
+ * (SURVEY.md section 8e).  Each rank creates an exchange (a device mailbox for [world][nq][k] records, double
+ * buffered, plus sequence flags), publishes its 64-byte CUDA IPC handle, receives everybody's handles by whatever
+ * means the host has (the Python driver all-gathers them with torch.distributed once) and connects.  After that
+ * pbx_exchange_allgather_merge is ONE kernel on `cuda_stream`: it writes this rank's d_local hits ([nq][k], as left
+ * by pbx_search_device) into every peer's mailbox, signals, waits for all peers' records of the same call and merges
+ * them under (dist, image_id) into d_out / d_out_count.  All ranks must make the same sequence of calls with the
+ * same nq and k.  nq * k <= max_records and nq <= max_queries. */
+typedef struct pbx_exchange pbx_exchange;
+PBX_API int pbx_exchange_create(int device, uint32_t rank, uint32_t world, uint32_t max_records, uint32_t max_queries,
+                                pbx_exchange** out);
+PBX_API int pbx_exchange_handle(pbx_exchange* x, void* out_handle_64_bytes);
+PBX_API int pbx_exchange_connect(pbx_exchange* x, const void* all_handles /* [world][64] */);
+PBX_API int pbx_exchange_allgather_merge(pbx_exchange* x, const pbx_hit* d_local, uint32_t nq, uint32_t k, pbx_hit* d_out,
+                                         uint32_t* d_out_count, void* cuda_stream);
+PBX_API void pbx_exchange_destroy(pbx_exchange* x);
+
 /* ---- the scalar function, for external users of the DB -----------------------------------
  * Replaces: `pub fn cosine_distance(&Vec<u8>, &Vec<u8>) -> f32` (src/engine.rs:572-588) for a
  * batch of pairs: a and b are [n][dim] u8 in host memory; out_dist[n] receives the reference's

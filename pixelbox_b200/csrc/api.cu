@@ -989,6 +989,105 @@ extern "C" int pbx_merge_hits_device(int device, const pbx_hit* d_gathered, cons
     return PBX_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// peer-memory exchange (multi-GPU merge step)
+// ------------------------------------------------------------------------------------------------
+struct pbx_exchange {
+    int device = 0;
+    uint32_t rank = 0, world = 1;
+    uint32_t max_records = 0, max_queries = 0;
+    uint32_t slot_records = 0, slot_flags = 0;
+    size_t mail_bytes = 0, bytes = 0;
+    void* base = nullptr;                          // [2 slots][world][max_records] records, then [2][max_queries][world] flags
+    void* peer_base[PBX_MAX_SHARDS] = {};
+    bool connected = false;
+    uint32_t seq = 0;
+};
+
+extern "C" int pbx_exchange_create(int device, uint32_t rank, uint32_t world, uint32_t max_records, uint32_t max_queries, pbx_exchange** out) {
+    if (!out) return fail(PBX_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (world == 0 || world > PBX_MAX_SHARDS || rank >= world || max_records == 0 || max_queries == 0)
+        return fail(PBX_E_INVALID, "bad exchange geometry (rank %u of %u)", rank, world);
+    if (pbx_device_count() == 0) return fail(PBX_E_NO_DEVICE, "no sm_100 device: pixelbox_b200 has no CPU fallback");
+    CU_TRY(cudaSetDevice(device));
+    pbx_exchange* x = new (std::nothrow) pbx_exchange();
+    if (!x) return fail(PBX_E_OOM, "host allocation failed");
+    x->device = device; x->rank = rank; x->world = world; x->max_records = max_records; x->max_queries = max_queries;
+    x->slot_records = world * max_records;
+    x->slot_flags = max_queries * world;
+    x->mail_bytes = ((size_t)2 * x->slot_records * sizeof(pbx_hit) + 255) & ~(size_t)255;
+    x->bytes = x->mail_bytes + (size_t)2 * x->slot_flags * sizeof(uint32_t);
+    cudaError_t e = cudaMalloc(&x->base, x->bytes);
+    if (e == cudaSuccess) e = cudaMemset(x->base, 0, x->bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { delete x; return fail(e == cudaErrorMemoryAllocation ? PBX_E_OOM : PBX_E_CUDA, "exchange allocation failed: %s", cudaGetErrorString(e)); }
+    *out = x;
+    return PBX_OK;
+}
+
+extern "C" int pbx_exchange_handle(pbx_exchange* x, void* out_handle) {
+    if (!x || !out_handle) return fail(PBX_E_INVALID, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU_TRY(cudaSetDevice(x->device));
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, x->base));
+    memcpy(out_handle, &h, sizeof(h));
+    return PBX_OK;
+}
+
+extern "C" int pbx_exchange_connect(pbx_exchange* x, const void* all_handles) {
+    if (!x || !all_handles) return fail(PBX_E_INVALID, "NULL argument");
+    if (x->connected) return PBX_OK;
+    CU_TRY(cudaSetDevice(x->device));
+    for (uint32_t r = 0; r < x->world; ++r) {
+        if (r == x->rank) { x->peer_base[r] = x->base; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char*>(all_handles) + (size_t)r * sizeof(h), sizeof(h));
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(PBX_E_CUDA, "cannot map the mailbox of rank %u (peer access over NVLink required): %s", r, cudaGetErrorString(e));
+        x->peer_base[r] = ptr;
+    }
+    x->connected = true;
+    return PBX_OK;
+}
+
+extern "C" int pbx_exchange_allgather_merge(pbx_exchange* x, const pbx_hit* d_local, uint32_t nq, uint32_t k, pbx_hit* d_out,
+                                            uint32_t* d_out_count, void* cuda_stream) {
+    if (!x || !d_local || !d_out || !d_out_count) return fail(PBX_E_INVALID, "NULL argument");
+    if (!x->connected) return fail(PBX_E_INVALID, "exchange is not connected");
+    if (nq == 0) return PBX_OK;
+    if (k == 0 || (uint64_t)nq * k > x->max_records || nq > x->max_queries)
+        return fail(PBX_E_INVALID, "exchange sized for %u records / %u queries per call, got %u x %u", x->max_records, x->max_queries, nq, k);
+    CU_TRY(cudaSetDevice(x->device));
+    ExchangeParams p;
+    memset(&p, 0, sizeof(p));
+    for (uint32_t r = 0; r < x->world; ++r) {
+        p.peer_mail[r] = static_cast<pbx_hit*>(x->peer_base[r]);
+        p.peer_flag[r] = reinterpret_cast<uint32_t*>(static_cast<char*>(x->peer_base[r]) + x->mail_bytes);
+    }
+    p.local = d_local; p.out = d_out; p.out_count = d_out_count;
+    p.rank = x->rank; p.world = x->world; p.nq = nq; p.k = k;
+    x->seq += 1;
+    p.seq = x->seq; p.slot = x->seq & 1u;
+    p.slot_records = x->slot_records; p.slot_flags = x->slot_flags;
+    exchange_merge_kernel<<<nq, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(p);
+    CU_TRY(cudaGetLastError());
+    return PBX_OK;
+}
+
+extern "C" void pbx_exchange_destroy(pbx_exchange* x) {
+    if (!x) return;
+    cudaSetDevice(x->device);
+    cudaDeviceSynchronize();
+    for (uint32_t r = 0; r < x->world; ++r)
+        if (r != x->rank && x->peer_base[r]) cudaIpcCloseMemHandle(x->peer_base[r]);
+    cudaFree(x->base);
+    cudaGetLastError();
+    delete x;
+}
+
 extern "C" int pbx_cosine_distance_pairs(int device, const uint8_t* a, const uint8_t* b, uint64_t n, uint32_t dim, float* out_dist,
                                          int32_t* out_dot, int32_t* out_norm2_a, int32_t* out_norm2_b) {
     if (dim == 0 || dim > PBX_MAX_DIM) return fail(PBX_E_DIM, "dim %u outside [1, %u]", dim, PBX_MAX_DIM);

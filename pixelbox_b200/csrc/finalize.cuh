@@ -241,9 +241,22 @@ __device__ __forceinline__ bool hit_before(const pbx_hit& a, uint32_t sa, const 
     if (a.image_id != b.image_id) return a.image_id < b.image_id;
     return sa < sb;
 }
-__global__ void merge_hits_kernel(const pbx_hit* __restrict__ gathered, const uint32_t* __restrict__ counts, uint32_t n_shards,
-                                  uint32_t nq, uint32_t k, pbx_hit* __restrict__ out, uint32_t* __restrict__ out_count) {
-    const uint32_t q = blockIdx.x;
+// L2-coherent read of a record: used for mailboxes that peer GPUs write over NVLink (L1 is not coherent with them)
+__device__ __forceinline__ pbx_hit ld_hit_cg(const pbx_hit* p) {
+    const unsigned long long* w = reinterpret_cast<const unsigned long long*>(p);
+    const unsigned long long a = __ldcg(w), b = __ldcg(w + 1), c = __ldcg(w + 2);
+    pbx_hit h;
+    h.image_id = (int64_t)a;
+    h.dist = __uint_as_float((uint32_t)(b & 0xFFFFFFFFull));
+    h.dot = (int32_t)(b >> 32);
+    h.norm2 = (int32_t)(c & 0xFFFFFFFFull);
+    h.flags = (uint32_t)(c >> 32);
+    return h;
+}
+
+// One CTA merges the n_shards lists of query q (gathered is [n_shards][nq][k]); counts may be NULL.
+__device__ inline void merge_hits_block(const pbx_hit* gathered, const uint32_t* counts, uint32_t n_shards, uint32_t nq, uint32_t k,
+                                        uint32_t q, pbx_hit* out, uint32_t* out_count) {
     __shared__ uint32_t s_cnt[PBX_MAX_SHARDS];
     __shared__ uint32_t s_total;
     if (threadIdx.x == 0) s_total = 0;
@@ -255,7 +268,7 @@ __global__ void merge_hits_kernel(const pbx_hit* __restrict__ gathered, const ui
         } else {                                    // unused tail slots carry dist = +inf: count the finite prefix
             const pbx_hit* list = gathered + ((size_t)s * nq + q) * k;
             uint32_t lo = 0, hi = k;
-            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (list[mid].dist < __int_as_float(0x7f800000)) lo = mid + 1; else hi = mid; }
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (ld_hit_cg(list + mid).dist < __int_as_float(0x7f800000)) lo = mid + 1; else hi = mid; }
             c = lo;
         }
         s_cnt[s] = c;
@@ -266,14 +279,14 @@ __global__ void merge_hits_kernel(const pbx_hit* __restrict__ gathered, const ui
     for (uint32_t e = threadIdx.x; e < n_shards * k; e += blockDim.x) {
         const uint32_t s = e / k, i = e - s * k;
         if (i >= s_cnt[s]) continue;
-        const pbx_hit me = gathered[((size_t)s * nq + q) * k + i];
+        const pbx_hit me = ld_hit_cg(gathered + ((size_t)s * nq + q) * k + i);
         uint32_t rank = 0;
         for (uint32_t t = 0; t < n_shards; ++t) {
             const pbx_hit* list = gathered + ((size_t)t * nq + q) * k;
             uint32_t lo = 0, hi = s_cnt[t];
             while (lo < hi) {                       // first element of list t that does not precede `me`
                 const uint32_t mid = (lo + hi) >> 1;
-                if (hit_before(list[mid], t, me, s)) lo = mid + 1; else hi = mid;
+                if (hit_before(ld_hit_cg(list + mid), t, me, s)) lo = mid + 1; else hi = mid;
             }
             rank += lo;
         }
@@ -284,6 +297,69 @@ __global__ void merge_hits_kernel(const pbx_hit* __restrict__ gathered, const ui
         out[(size_t)q * k + i] = h;
     }
     if (threadIdx.x == 0) out_count[q] = n_out;
+}
+
+__global__ void merge_hits_kernel(const pbx_hit* __restrict__ gathered, const uint32_t* __restrict__ counts, uint32_t n_shards,
+                                  uint32_t nq, uint32_t k, pbx_hit* __restrict__ out, uint32_t* __restrict__ out_count) {
+    merge_hits_block(gathered, counts, n_shards, nq, k, blockIdx.x, out, out_count);
+}
+
+// ---- the exchange step fused with the merge, over NVLink peer memory -----------------------
+// Every rank owns a mailbox (two slots of [world][nq][k] records) and a flag array, both mapped into its peers'
+// address spaces (CUDA IPC).  One CTA per query: it posts this rank's k records straight into the mailbox of every
+// peer (plain stores to peer addresses), publishes them with a system-scope release of a per-(query, source)
+// sequence flag, spins with acquire loads until all `world` flags of its own mailbox carry this call's sequence
+// number, and merges the lists under (dist, image_id).  No NCCL call, no host step: post, signal, wait and merge
+// are one kernel on the search stream.  Slots alternate per call: a rank can be at most one call ahead of its
+// slowest peer (it cannot finish call i+1 before that peer has posted i+1, i.e. finished reading call i).
+struct ExchangeParams {
+    pbx_hit* peer_mail[PBX_MAX_SHARDS];   // mailbox base of every rank (slot 0), as mapped in this process
+    uint32_t* peer_flag[PBX_MAX_SHARDS];  // flag base of every rank
+    const pbx_hit* local;                 // [nq][k] this rank's hits
+    pbx_hit* out;                         // [nq][k]
+    uint32_t* out_count;                  // [nq]
+    uint32_t rank, world, nq, k;
+    uint32_t slot, seq;
+    uint32_t slot_records;                // records per mailbox slot
+    uint32_t slot_flags;                  // flags per slot (max_queries * world)
+};
+
+__global__ void __launch_bounds__(256)
+exchange_merge_kernel(const __grid_constant__ ExchangeParams p) {
+    const uint32_t q = blockIdx.x;
+    __shared__ uint32_t s_timeout;
+    if (threadIdx.x == 0) s_timeout = 0;
+    __syncthreads();
+    // 1. post
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(p.local + (size_t)q * p.k);
+    const uint32_t words = p.k * 3u;                                            // 24-byte records as 8-byte words
+    for (uint32_t peer = 0; peer < p.world; ++peer) {
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(
+            p.peer_mail[peer] + (size_t)p.slot * p.slot_records + ((size_t)p.rank * p.nq + q) * p.k);
+        for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < p.world) {
+        uint32_t* f = p.peer_flag[threadIdx.x] + (size_t)p.slot * p.slot_flags + (size_t)q * p.world + p.rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(p.seq) : "memory");
+    }
+    // 2. wait for the records of all ranks for this query
+    if (threadIdx.x < p.world) {
+        const uint32_t* f = p.peer_flag[p.rank] + (size_t)p.slot * p.slot_flags + (size_t)q * p.world + threadIdx.x;
+        uint32_t v;
+        const long long t0 = clock64();
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            // a peer that died must not hang this GPU for ever: give up after ~10 s and flag the result
+            if (v != p.seq && clock64() - t0 > (20ll << 30)) { atomicOr(&s_timeout, 1u); break; }
+        } while (v != p.seq);
+    }
+    __syncthreads();
+    // 3. merge from this rank's own mailbox (records were written by peers: read through L2)
+    merge_hits_block(p.peer_mail[p.rank] + (size_t)p.slot * p.slot_records, nullptr, p.world, p.nq, p.k, q, p.out, p.out_count);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_timeout) p.out_count[q] = 0xFFFFFFFFu;          // "exchange timed out" marker for the host
 }
 
 // ---- the ingest quantizer (src/image_hashes/efficientnet.rs:39), SURVEY.md 8f N3 --------------------------

@@ -33,7 +33,8 @@ class ShardedCorpus:
     """`local` is this rank's shard.  Tests on CPU (gloo) inject an object with the same
     `search_hits(queries, k, max_dist) -> (hits[nq][k], counts[nq])` method; on GPUs it is a Corpus."""
 
-    def __init__(self, dim: int, local=None, capacity_hint: int = 0, device: Optional[int] = None, group=None):
+    def __init__(self, dim: int, local=None, capacity_hint: int = 0, device: Optional[int] = None, group=None,
+                 use_peer_exchange: bool = True):
         if not dist.is_initialized():
             raise RuntimeError("ShardedCorpus needs an initialised torch.distributed process group")
         self.group = group
@@ -51,6 +52,36 @@ class ShardedCorpus:
         self.local = local
         self.device = device if device is not None else 0
         self._bufs = {}
+        self._exchange = None
+        if self.on_gpu and self.world > 1 and use_peer_exchange:
+            self._connect_exchange()
+
+    # -- exchange over NVLink peer memory ----------------------------------------------------------------
+    MAX_RECORDS = 131072            # nq * k per call the mailboxes are sized for
+    MAX_QUERIES = 1024
+
+    def _connect_exchange(self) -> None:
+        """Creates this rank's mailbox, all-gathers the CUDA IPC handles once (NCCL) and maps the peers' mailboxes.
+        If peer mapping is not possible the NCCL all-gather + merge kernel path stays in use (same results)."""
+        import ctypes
+        L = nat.lib()
+        h = ctypes.c_void_p(0)
+        nat.check(L.pbx_exchange_create(self.device, self.rank, self.world, self.MAX_RECORDS, self.MAX_QUERIES, ctypes.byref(h)))
+        mine = np.zeros(64, np.uint8)
+        nat.check(L.pbx_exchange_handle(h, nat.ptr(mine)))
+        dev = self._dev()
+        t_mine = torch.from_numpy(mine).to(dev)
+        t_all = torch.empty(self.world * 64, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(t_all, t_mine, group=self.group)
+        handles = np.ascontiguousarray(t_all.cpu().numpy())
+        rc = L.pbx_exchange_connect(h, nat.ptr(handles))
+        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)        # all ranks or none
+        if int(ok.item()) == 1:
+            self._exchange = h
+        else:
+            L.pbx_exchange_destroy(h)
+        dist.barrier(group=self.group)
 
     # -- contents ----------------------------------------------------------------------------------
     def load_table(self, image_ids, hashes) -> None:
@@ -99,6 +130,11 @@ class ShardedCorpus:
         self.local.search_device(d_queries.data_ptr(), nq, k, max_dist, b["local"].data_ptr(), b["cnt"].data_ptr(), stream)
         if self.world == 1:
             return b["local"], b["cnt"]
+        if self._exchange is not None and nq * k <= self.MAX_RECORDS and nq <= self.MAX_QUERIES:
+            # one kernel: post to every peer's mailbox over NVLink, signal, wait, merge
+            nat.check(nat.lib().pbx_exchange_allgather_merge(self._exchange, b["local"].data_ptr(), nq, k, b["out"].data_ptr(),
+                                                             b["out_cnt"].data_ptr(), stream if stream else 1))
+            return b["out"], b["out_cnt"]
         dist.all_gather_into_tensor(b["gathered"], b["local"], group=self.group)
         nat.check(nat.lib().pbx_merge_hits_device(self.device, b["gathered"].data_ptr(), None, self.world, nq, k,
                                                   b["out"].data_ptr(), b["out_cnt"].data_ptr(), stream if stream else 1))
@@ -122,6 +158,8 @@ class ShardedCorpus:
             torch.cuda.current_stream().synchronize()
             hits = b["h_out"].numpy().view(nat.HIT_DTYPE).reshape(nq, k)
             cnt = b["h_cnt"].numpy().astype(np.uint32)
+            if (cnt == 0xFFFFFFFF).any():
+                raise nat.PbxError(-8, "peer exchange timed out: a rank did not post its records")
         else:
             l_hits, l_cnt = self.local.search_hits(q, k, max_dist)
             mine = torch.from_numpy(np.ascontiguousarray(l_hits).view(np.uint8).reshape(-1).copy())
@@ -137,5 +175,10 @@ class ShardedCorpus:
                              hits[i]["dot"][:cnt[i]].copy(), hits[i]["norm2"][:cnt[i]].copy()) for i in range(nq)]
 
     def close(self) -> None:
+        if self._exchange is not None:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)                 # nobody may still be writing into a mailbox that goes away
+            nat.lib().pbx_exchange_destroy(self._exchange)
+            self._exchange = None
         if isinstance(self.local, Corpus):
             self.local.close()
