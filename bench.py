@@ -224,7 +224,7 @@ def run_ours(args):
     queries = synth.synth_queries(7, NQ, dim, total_rows, SEED)
 
     if world > 1:
-        sc = ShardedCorpus(dim, capacity_hint=rows, device=local_rank)
+        sc = ShardedCorpus(dim, capacity_hint=rows, device=local_rank, use_peer_exchange=os.environ.get("PBX_NO_PEER_EXCHANGE") is None)
         sc.fill_synthetic(rows, SEED)
         corpus = sc.local
     else:
@@ -368,6 +368,8 @@ def run_ours(args):
                          "share_of_step": scan_ms / ms_step},
             "clocks": clocks,
             "exact_passes": int(st.exact_passes), "scan_grid": int(st.scan_grid), "parity_check": check,
+            "exchange": None if sc is None else ("one kernel over NVLink peer memory (post + signal + wait + merge)" if sc._exchange is not None
+                                                 else "NCCL all-gather + merge kernel"),
         }
         if batched is not None:
             line["batched"] = batched
