@@ -359,7 +359,7 @@ def run_ours(args):
             "config": workload_config(args),
             "e2e": {"value": bytes_step / (e2e_step * 1e-3) / 1e9, "unit": "GB/s", "queries_per_sec": 1e3 / e2e_step,
                     "ms_per_query": e2e_step, "h2d_bytes_per_step": dim, "d2h_bytes_per_step": k * 24 + 4,
-                    "api": "pbx_search (C ABI, host buffers)" if world == 1 else "ShardedCorpus.search (host buffers, NCCL all-gather)"},
+                    "api": "pbx_search (C ABI, host buffers)" if world == 1 else "ShardedCorpus.search (host buffers; exchange as in 'exchange')"},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "kernel": "scan_kernel<16,1,false,3>" if dim == 256 else "scan_kernel", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(rows, dim),

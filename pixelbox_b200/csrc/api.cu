@@ -984,7 +984,16 @@ extern "C" int pbx_merge_hits_device(int device, const pbx_hit* d_gathered, cons
     if (k == 0 || n_shards == 0 || n_shards > PBX_MAX_SHARDS) return fail(PBX_E_INVALID, "k >= 1 and 1 <= n_shards <= %u required", PBX_MAX_SHARDS);
     if (nq == 0) return PBX_OK;
     CU_TRY(cudaSetDevice(device));
-    merge_hits_kernel<<<nq, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(d_gathered, d_counts, n_shards, nq, k, d_out_hits, d_out_count);
+    const uint32_t stage = merge_smem_bytes(n_shards, k);
+    static std::atomic<uint64_t> attr_done{0};                   // one bit per device: the attribute is per device context
+    if (device >= 0 && device < 64 && !((attr_done.load(std::memory_order_acquire) >> device) & 1ull)) {
+        CU_TRY(cudaFuncSetAttribute(merge_hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMergeSmemKeys * 12u)));
+        attr_done.fetch_or(1ull << device, std::memory_order_release);
+    } else if (device < 0 || device >= 64) {
+        CU_TRY(cudaFuncSetAttribute(merge_hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMergeSmemKeys * 12u)));
+    }
+    merge_hits_kernel<<<nq, kMergeThreads, stage, static_cast<cudaStream_t>(cuda_stream)>>>(d_gathered, d_counts, n_shards, nq, k, d_out_hits,
+                                                                                           d_out_count, stage);
     CU_TRY(cudaGetLastError());
     return PBX_OK;
 }
@@ -1011,6 +1020,7 @@ extern "C" int pbx_exchange_create(int device, uint32_t rank, uint32_t world, ui
         return fail(PBX_E_INVALID, "bad exchange geometry (rank %u of %u)", rank, world);
     if (pbx_device_count() == 0) return fail(PBX_E_NO_DEVICE, "no sm_100 device: pixelbox_b200 has no CPU fallback");
     CU_TRY(cudaSetDevice(device));
+    CU_TRY(cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMergeSmemKeys * 12u)));
     pbx_exchange* x = new (std::nothrow) pbx_exchange();
     if (!x) return fail(PBX_E_OOM, "host allocation failed");
     x->device = device; x->rank = rank; x->world = world; x->max_records = max_records; x->max_queries = max_queries;
@@ -1072,7 +1082,8 @@ extern "C" int pbx_exchange_allgather_merge(pbx_exchange* x, const pbx_hit* d_lo
     x->seq += 1;
     p.seq = x->seq; p.slot = x->seq & 1u;
     p.slot_records = x->slot_records; p.slot_flags = x->slot_flags;
-    exchange_merge_kernel<<<nq, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(p);
+    p.stage_bytes = merge_smem_bytes(x->world, k);
+    exchange_merge_kernel<<<nq, kMergeThreads, p.stage_bytes, static_cast<cudaStream_t>(cuda_stream)>>>(p);
     CU_TRY(cudaGetLastError());
     return PBX_OK;
 }

@@ -360,3 +360,46 @@ def test_search_concurrent_with_append_sees_a_committed_prefix():
                     break
             assert ok, f"answer matches no committed prefix in [{n0}, {n1}]"
         assert len(prefixes) >= 1
+
+
+@pytest.mark.parametrize("n_shards,k,nq", [(2, 100, 3), (8, 100, 5), (8, 1000, 2), (40, 100, 2), (64, 2048, 1), (3, 1, 4)])
+def test_device_merge_equals_host_merge(n_shards, k, nq):
+    """pbx_merge_hits_device (shared-memory staged keys when n_shards*k <= 8192, L2 probes above) against
+    pbx_merge_hits: ties in dist across shards, duplicate (dist, id) pairs, short and empty lists, counts
+    passed explicitly and implied by +inf tails."""
+    import torch
+    from pixelbox_b200.corpus import merge_hits
+    rng = np.random.default_rng(n_shards * 1000 + k)
+    gathered = np.zeros((n_shards, nq, k), nat.HIT_DTYPE)
+    counts = np.zeros((n_shards, nq), np.uint32)
+    for s in range(n_shards):
+        for q in range(nq):
+            c = int(rng.integers(0, k + 1)) if (s + q) % 3 else k
+            if s == 1 and q == 0:
+                c = 0
+            dist = np.sort(rng.integers(0, 40, size=c).astype(np.float32) * 0.125 - 0.25)        # many ties, some negative
+            ids = rng.integers(1, 50, size=c).astype(np.int64)
+            order = np.lexsort((ids, dist))
+            h = gathered[s, q]
+            h["dist"][:c], h["image_id"][:c] = dist[order], ids[order]
+            h["dot"][:c] = rng.integers(-1000, 1000, size=c)
+            h["norm2"][:c] = s
+            h["dist"][c:], h["image_id"][c:] = np.inf, np.iinfo(np.int64).max
+            counts[s, q] = c
+    want_hits, want_cnt = merge_hits(gathered, counts, k)
+    d_g = torch.from_numpy(gathered.view(np.uint8).reshape(-1)).cuda()
+    d_c = torch.from_numpy(counts.astype(np.int32).reshape(-1)).cuda()
+    for with_counts in (True, False):
+        d_out = torch.zeros(nq * k * 24, dtype=torch.uint8, device="cuda")
+        d_cnt = torch.zeros(nq, dtype=torch.int32, device="cuda")
+        nat.check(nat.lib().pbx_merge_hits_device(0, d_g.data_ptr(), d_c.data_ptr() if with_counts else None, n_shards, nq, k,
+                                                  d_out.data_ptr(), d_cnt.data_ptr(), torch.cuda.current_stream().cuda_stream or 1))
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy().view(nat.HIT_DTYPE).reshape(nq, k)
+        got_cnt = d_cnt.cpu().numpy().astype(np.uint32)
+        assert np.array_equal(got_cnt, want_cnt)
+        for q in range(nq):
+            n = int(want_cnt[q])
+            for f in ("image_id", "dot"):
+                assert np.array_equal(got[q][f][:n], want_hits[q][f][:n]), (f, q, with_counts)
+            assert np.array_equal(bits(got[q]["dist"][:n]), bits(want_hits[q]["dist"][:n]))
