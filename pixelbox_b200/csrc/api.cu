@@ -243,7 +243,8 @@ static cudaError_t init_kernel_attributes() {
     if (e == cudaSuccess) e = allow_smem(prep_seed_kernel, PBX_MAX_DIM * 2 + 1024);
     if (e == cudaSuccess) e = allow_smem(finalize_kernel<false>, fin_cap);
     if (e == cudaSuccess) e = allow_smem(finalize_kernel<true>, fin_cap);
-    if (e == cudaSuccess) e = allow_smem(batch_mma_kernel, 210 * 1024);
+    if (e == cudaSuccess) e = allow_smem(batch_mma_kernel<false>, 212 * 1024);
+    if (e == cudaSuccess) e = allow_smem(batch_mma_kernel<true>, 212 * 1024);
     if (e == cudaSuccess) e = allow_smem(batch_tighten_kernel, kBatchCap * sizeof(u64));
     if (e == cudaSuccess) e = allow_smem(finalize_exact_kernel, fin_cap);
     return e;
@@ -620,6 +621,7 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
     bp.qpad = c->d_qpad; bp.q16 = c->d_q16; bp.qbytes = c->d_qbytes; bp.qh = c->d_qh;
     bp.colterm = c->d_colterm; bp.thr = c->d_thr; bp.cand_cnt = c->d_bcnt; bp.overflow = c->d_boverflow;
     bp.bhist = c->d_bhist; bp.inv_q = c->d_binvq;
+    bp.flood_rows = std::min<uint32_t>(n, 16u * kBatchTileRows);          // round 0 below
     batch_prep_kernel<<<nq_pad, 128, 0, s>>>(bp);
     CU_TRY(cudaGetLastError());
 
@@ -630,7 +632,7 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
     mp.bhist = c->d_bhist; mp.inv_q = c->d_binvq; mp.thr_live = c->d_thr; mp.keep = keep;
     mp.n = n; mp.dim = c->dim; mp.kc = kc; mp.qg = qg; mp.groups = groups;
     const int grid = std::max<int>((int)groups, (c->sm_count / (int)groups) * (int)groups);
-    const size_t mma_smem = (size_t)qg * pitch + (size_t)kBatchStages * kBatchTileRows * 128 + (size_t)qg * 12 + (size_t)kBatchEpiWarps * 128 * 4 + 1024;
+    const size_t mma_smem = (size_t)qg * pitch + (size_t)kBatchStages * kBatchTileRows * 128 + (size_t)qg * 20 + (size_t)kBatchEpiWarps * 128 * 4 + 1024;
     BatchTightenParams tp;
     tp.cand = c->d_bcand; tp.cand_cnt = c->d_bcnt; tp.thr = c->d_thr; tp.keep = keep; tp.nq = nq;
 
@@ -645,7 +647,9 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
     uint32_t begin = 0, end = std::min<uint32_t>(tiles, 16u);
     while (begin < tiles) {
         mp.tile_begin = begin; mp.tile_end = end;
-        batch_mma_kernel<<<grid, kBatchThreads, mma_smem, s>>>(mp);
+        // round 0 runs the flood variant: thresholds are -inf, every score is a candidate and its slot is its row
+        if (begin == 0) batch_mma_kernel<true><<<grid, kBatchThreads, mma_smem, s>>>(mp);
+        else batch_mma_kernel<false><<<grid, kBatchThreads, mma_smem, s>>>(mp);
         CU_TRY(cudaGetLastError());
         begin = end;
         if (begin < tiles) {

@@ -45,10 +45,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "PBX_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra PBX_DONE;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"      // %2: suspend-time hint (ns): the thread sleeps in
+        "@p bra PBX_DONE;\n\t"                                                // hardware instead of spinning on the issue port
         "bra PBX_WAIT;\n\t"
-        "PBX_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "PBX_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -101,6 +101,7 @@ struct BatchPrepParams {
     uint32_t* overflow;         // [nq_pad]
     uint32_t* bhist;            // [nq_pad][kBatchHistBins], zeroed here
     float* inv_q;               // [nq_pad]
+    uint32_t flood_rows;        // rows of round 0: every real query starts with exactly these candidates (slot = row)
 };
 
 __global__ void batch_prep_kernel(const BatchPrepParams p) {
@@ -131,7 +132,7 @@ __global__ void batch_prep_kernel(const BatchPrepParams p) {
         }
         p.colterm[q] = -510 * R;
         p.thr[q] = real ? -__int_as_float(0x7f800000) : __int_as_float(0x7f800000);
-        p.cand_cnt[q] = 0;
+        p.cand_cnt[q] = real ? p.flood_rows : 0u;
         p.overflow[q] = 0;
         p.inv_q[q] = real ? (float)(1.0 / sqrt((double)N)) : 0.0f;
     }
@@ -161,6 +162,7 @@ struct BatchMmaParams {
     uint32_t tile_begin, tile_end;   // 128-row tiles of this round
 };
 
+template <bool FLOOD>
 __global__ void __launch_bounds__(kBatchThreads, 1)
 batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
     extern __shared__ __align__(16) uint8_t bsm_raw[];     // NOT declared 1024-aligned: the compiler would fold the fix-up below away
@@ -175,7 +177,8 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
     int* s_colterm = reinterpret_cast<int*>(sA + kBatchStages * kBatchTileRows * 128);
     float* s_thr = reinterpret_cast<float*>(s_colterm + QG);
     float* s_invq = s_thr + QG;
-    int* s_uw = reinterpret_cast<int*>(s_invq + QG);    // [epilogue warp][2 * 64] integer pre-test bounds, rebuilt per tile
+    float2* s_pre = reinterpret_cast<float2*>(s_invq + QG);   // per column {threshold clamped to +-1e30, (float)colterm}: inputs of the pre-test bound
+    int* s_uw = reinterpret_cast<int*>(s_pre + QG);     // [epilogue warp][2 * 64] integer pre-test bounds, rebuilt per tile
     // per-epilogue-warp staging of accepted candidates: pushes to global memory go out 32 at a time, so the
     // ~1 us round trip of the slot atomic is paid once per 32 candidates instead of once per candidate
     __shared__ u64 st_key[kBatchEpiWarps][64];
@@ -201,6 +204,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
         s_colterm[i] = p.colterm[g * QG + i];
         s_thr[i] = p.thr[g * QG + i];
         s_invq[i] = p.inv_q[g * QG + i];
+        s_pre[i] = make_float2(fminf(fmaxf(s_thr[i], -1.0e30f), 1.0e30f), (float)s_colterm[i]);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -333,7 +337,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                     }
                 }
                 const float live = *reinterpret_cast<volatile float*>(p.thr_live + qi);
-                if (live > s_thr[j]) s_thr[j] = live;
+                if (live > s_thr[j]) { s_thr[j] = live; s_pre[j].x = fminf(fmaxf(live, -1.0e30f), 1.0e30f); }
             }
             __syncwarp();
         };
@@ -356,20 +360,16 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
             const float norm_lo = inv_hi > 0.0f ? 1.0f / inv_hi : 0.0f;
             const float norm_hi = inv_hi > 0.0f ? 1.0f / inv_lo : 0.0f;
             __syncwarp();
+            // u = floor(thr * norm - colterm - slack): a handful of float ops per column; the float -> int conversion
+            // saturates, so the clamped +-1e30 thresholds (-inf: nothing seen yet, +inf: padding column) become INT_MIN / INT_MAX
             for (uint32_t cc = (uint32_t)lane; cc < NB * cols_per_warp; cc += 32) {
                 const uint32_t nb = cc / cols_per_warp, cw = cc - nb * cols_per_warp;
                 const uint32_t col = nb * NMMA + slice * cols_per_warp + cw;
-                const float th = s_thr[col];
-                int u;
-                if (th == -__int_as_float(0x7f800000)) u = INT_MIN;
-                else if (th == __int_as_float(0x7f800000)) u = INT_MAX;
-                else {
-                    const float tt = th * (th >= 0.0f ? norm_lo : norm_hi);
-                    const float lo = floorf(tt - fabsf(tt) * 2.0e-6f - 4.0f);
-                    const float uu = lo - (float)s_colterm[col];
-                    u = uu <= -2.0e9f ? INT_MIN : uu >= 2.0e9f ? INT_MAX : (int)floorf(uu - fabsf(uu) * 2.0e-7f - 1.0f);
-                }
-                my_u[nb * 64 + cw] = u;
+                const float2 pc = s_pre[col];
+                const float tt = pc.x * (pc.x >= 0.0f ? norm_lo : norm_hi);
+                const float y = tt - pc.y;
+                const float m = fabsf(tt) + fabsf(pc.y);            // every rounding above is relative to one of these
+                my_u[nb * 64 + cw] = __float2int_rd(fmaf(m, -4.0e-6f, y) - 8.0f);
             }
             __syncwarp();
             for (uint32_t nb = 0; nb < NB; ++nb) {
@@ -387,14 +387,41 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                     uint32_t r[32];
                     tmem_ld32(tbase + c0, r);
                     const uint32_t colbase = nb * NMMA + c0;
-                    uint32_t mask = 0;
+                    if constexpr (FLOOD) {
+                        // round 0: every score of a real query is a candidate; its slot in the query's buffer is its row
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const uint32_t col = colbase + (uint32_t)i;
+                            const int dot_i = 4 * (int)r[i] + rowterm + s_colterm[col];
+                            const float kf = __fmul_rn((float)dot_i, inv_r);
+                            if (row_ok && s_invq[col] > 0.0f) p.cand[(size_t)(g * QG + col) * kBatchCap + row] = make_key64(kf, row);
+                        }
+                        continue;
+                    }
+                    // one multiply-add and one compare per score, OR-ed into two predicates (two dependency chains)
+                    bool some = false, some2 = false;
 #pragma unroll
                     for (int i4 = 0; i4 < 8; ++i4) {
                         const int4 u4 = *reinterpret_cast<const int4*>(my_u + nb * 64 + cw0 + 4 * i4);
+                        some |= (4 * (int)r[4 * i4 + 0] + rowterm >= u4.x);
+                        some2 |= (4 * (int)r[4 * i4 + 1] + rowterm >= u4.y);
+                        some |= (4 * (int)r[4 * i4 + 2] + rowterm >= u4.z);
+                        some2 |= (4 * (int)r[4 * i4 + 3] + rowterm >= u4.w);
+                    }
+                    if (!__any_sync(0xFFFFFFFFu, (some || some2) && row_ok)) continue;
+                    // some lane passed the pre-test in some column: find which (recomputed from opaque copies, so that
+                    // the compiler does not keep the 32 sums and 32 bounds of the fast pass alive across the branch)
+                    uint32_t mask = 0;
+                    int rowterm_s = rowterm;
+                    const int* u_s = my_u + nb * 64 + cw0;
+                    asm volatile("" : "+r"(rowterm_s), "+l"(u_s));
+#pragma unroll
+                    for (int i4 = 0; i4 < 8; ++i4) {
+                        const int4 u4 = *reinterpret_cast<const int4*>(u_s + 4 * i4);
                         const int us[4] = {u4.x, u4.y, u4.z, u4.w};
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const int x = 4 * (int)r[4 * i4 + j] + rowterm;
+                            const int x = 4 * (int)r[4 * i4 + j] + rowterm_s;
                             if (x >= us[j]) mask |= 1u << (4 * i4 + j);
                         }
                     }
