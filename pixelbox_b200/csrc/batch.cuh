@@ -3,7 +3,10 @@
 // (tcgen05.mma.kind::i8, accumulators in TMEM), with the top-k selection fused into the epilogue so the
 // N x Q score matrix (10^10 entries for 10M x 1024) never exists in memory.
 //
-//   exact integers:  dot_i = sum c(q)c(r) = 4 S - 510 (sum q + sum r) + 65025 d      (c(v) = 2v - 255)
+//   operands       :  A = corpus bytes r (u8), B = query bytes centred on 128, q' = q - 128 = q ^ 0x80 (s8);  S = sum r q'
+//   exact integers:  dot_i = sum c(q)c(r) = 4 S + (2 sum r - 255 d) + (-510 sum q')   (c(v) = 2v - 255)
+//                    the per-row term varies little across rows (it is 2 sum r, not 510 sum r), so the epilogue
+//                    can pre-test the RAW accumulator against a per-column integer bound: one compare per score
 //   ranking key   :  kappa' = fl(fl(dot_i) * inv_norm_r)      (the per-query factor 1/|c(q)| is applied later)
 //
 // One CTA = one query group (QG <= 512 queries resident in shared memory, loaded once by TMA) x a strided set of
@@ -95,7 +98,7 @@ struct BatchPrepParams {
     int16_t* q16;               // [nq][pitch] centred (re-rank)
     uint8_t* qbytes;            // [nq][pitch]
     QueryHeader* qh;            // [nq]
-    int* colterm;               // [nq_pad]  -510 * sum q_i
+    int* colterm;               // [nq_pad]  -510 * sum (q_i - 128)
     float* thr;                 // [nq_pad]  -inf for real queries, +inf for padding
     uint32_t* cand_cnt;         // [nq_pad]
     uint32_t* overflow;         // [nq_pad]
@@ -112,7 +115,7 @@ __global__ void batch_prep_kernel(const BatchPrepParams p) {
         uint32_t v = 0;
         int c = 0;
         if (real && i < p.dim) { v = p.queries[(size_t)q * p.dim + i]; c = centre(v); }
-        p.qpad[(size_t)q * p.pitch + i] = (uint8_t)v;
+        p.qpad[(size_t)q * p.pitch + i] = (real && i < p.dim) ? (uint8_t)(v ^ 0x80u) : (uint8_t)0;   // q - 128 as s8
         if (real) { p.q16[(size_t)q * p.pitch + i] = (int16_t)c; p.qbytes[(size_t)q * p.pitch + i] = (uint8_t)v; }
         s += c; n2 += c * c; raw += (int)v;
     }
@@ -130,7 +133,7 @@ __global__ void batch_prep_kernel(const BatchPrepParams p) {
             h.sum_cq = S; h.norm2_q = N; h.inv_q = (float)(1.0 / sqrt((double)N)); h.sa = 0.0f;
             p.qh[q] = h;
         }
-        p.colterm[q] = -510 * R;
+        p.colterm[q] = -510 * (R - 128 * (int)p.dim);          // -510 * sum (q_i - 128)   (R = 0 for padding queries)
         p.thr[q] = real ? -__int_as_float(0x7f800000) : __int_as_float(0x7f800000);
         p.cand_cnt[q] = real ? p.flood_rows : 0u;
         p.overflow[q] = 0;
@@ -235,8 +238,9 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            // instruction descriptor: D = s32 (2 << 4), A = B = u8 (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-            const uint32_t idesc = (2u << 4) | ((NMMA >> 3) << 17) | ((uint32_t)(kBatchTileRows >> 4) << 24);
+            // instruction descriptor: D = s32 (2 << 4), A = u8 (0 at bit 7), B = s8 (1 at bit 10), both K-major,
+            // N >> 3 at bit 17, M >> 4 at bit 24
+            const uint32_t idesc = (2u << 4) | (1u << 10) | ((NMMA >> 3) << 17) | ((uint32_t)(kBatchTileRows >> 4) << 24);
             mbar_wait(&q_full, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t it = 0, tile_iter = 0;
@@ -275,7 +279,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
         const uint32_t cols_per_warp = NMMA / 4;                     // 64 or 32
         uint32_t tile_iter = 0;
         uint32_t uses0 = 0, uses1 = 0;
-        const int dterm = 65025 * (int)p.dim;
+        const int dterm = -255 * (int)p.dim;
         u64* my_key = st_key[warp - 2];
         uint32_t* my_q = st_q[warp - 2];
         int* my_u = s_uw + (size_t)(warp - 2) * 128;
@@ -341,37 +345,60 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
             }
             __syncwarp();
         };
+        // per-row metadata of a tile: fetched one tile ahead, so its L2 round trip hides behind the current tile
+        auto fetch_meta = [&](uint32_t tile, float& inv, int& rs) {
+            const uint32_t rw = tile * kBatchTileRows + quarter * 32u + (uint32_t)lane;
+            const bool ok = tile < p.tile_end && rw < p.n;
+            inv = ok ? __ldg(p.inv_norm + rw) : 0.0f;
+            rs = ok ? __ldg(p.row_sum + rw) : 0;
+        };
+        float inv_next;
+        int rs_next;
+        fetch_meta(p.tile_begin + ci, inv_next, rs_next);
         for (uint32_t t = p.tile_begin + ci; t < p.tile_end; t += cstride, ++tile_iter) {
             if (tile_iter >= 4 && ((tile_iter & (tile_iter - 1)) == 0 || (tile_iter & 63u) == 0)) refresh();
             const uint32_t row = t * kBatchTileRows + quarter * 32u + (uint32_t)lane;
             const bool row_ok = row < p.n;
-            const float inv_r = row_ok ? __ldg(p.inv_norm + row) : 0.0f;
-            const int rowterm = row_ok ? (dterm - 510 * __ldg(p.row_sum + row)) : 0;
-            // Integer pre-test.  A score passes when fl(fl(dot_i) * inv_r) >= thr, dot_i = x + colterm with
-            // x = 4 S + rowterm.  With norm = 1 / inv_r inside [norm_lo, norm_hi] for the 32 rows of this warp that
-            // implies  x >= thr * (thr >= 0 ? norm_lo : norm_hi) - slack - colterm =: u[col]  (slack covers every
-            // rounding), so one integer compare per score never rejects a passing one; survivors take the exact test.
-            float inv_lo = row_ok ? inv_r : __int_as_float(0x7f800000), inv_hi = row_ok ? inv_r : 0.0f;
+            const float inv_r = inv_next;
+            const int rowterm = dterm + 2 * rs_next;
+            fetch_meta(t + cstride, inv_next, rs_next);
+            if constexpr (!FLOOD) {
+                // Integer pre-test on the raw accumulator.  A score passes when fl(fl(dot_i) * inv_r) >= thr with
+                // dot_i = 4 S + rowterm + colterm.  With norm = 1 / inv_r inside [norm_lo, norm_hi] and rowterm <= rt_max
+                // over the 32 rows of this warp, passing implies
+                //     S >= (thr * (thr >= 0 ? norm_lo : norm_hi) - colterm - rt_max - slack) / 4 =: v[col]
+                // (slack covers every rounding), so ONE integer compare per score never rejects a passing one; the
+                // survivors take the exact test.  rowterm = 2 sum r - 255 d moves little from row to row, so the bound
+                // loses almost nothing to rt_max; what it loses to the norm spread is the price of a per-warp bound.
+                float inv_lo = row_ok ? inv_r : __int_as_float(0x7f800000), inv_hi = row_ok ? inv_r : 0.0f;
+                int rt_max = row_ok ? rowterm : INT_MIN;
 #pragma unroll
-            for (int off = 16; off; off >>= 1) {
-                inv_lo = fminf(inv_lo, __shfl_xor_sync(0xFFFFFFFFu, inv_lo, off));
-                inv_hi = fmaxf(inv_hi, __shfl_xor_sync(0xFFFFFFFFu, inv_hi, off));
+                for (int off = 16; off; off >>= 1) {
+                    inv_lo = fminf(inv_lo, __shfl_xor_sync(0xFFFFFFFFu, inv_lo, off));
+                    inv_hi = fmaxf(inv_hi, __shfl_xor_sync(0xFFFFFFFFu, inv_hi, off));
+                    rt_max = max(rt_max, __shfl_xor_sync(0xFFFFFFFFu, rt_max, off));
+                }
+                const float norm_lo = inv_hi > 0.0f ? 1.0f / inv_hi : 0.0f;
+                const float norm_hi = inv_hi > 0.0f ? 1.0f / inv_lo : 0.0f;
+                const float rt_f = (float)rt_max;                       // |rowterm| < 2^24: exact
+                __syncwarp();
+                // a handful of float ops per column; the float -> int conversion saturates, so the clamped +-1e30
+                // thresholds (-inf: nothing seen yet, +inf: padding column) become INT_MIN / INT_MAX
+#pragma unroll
+                for (uint32_t it = 0; it < 4; ++it) {
+                    const uint32_t cc = (uint32_t)lane + 32u * it;
+                    if (cc < NB * cols_per_warp) {
+                        const uint32_t nb = cc / cols_per_warp, cw = cc - nb * cols_per_warp;
+                        const uint32_t col = nb * NMMA + slice * cols_per_warp + cw;
+                        const float2 pc = s_pre[col];
+                        const float tt = pc.x * (pc.x >= 0.0f ? norm_lo : norm_hi);
+                        const float y = (tt - pc.y) - rt_f;
+                        const float m = fabsf(tt) + fabsf(pc.y) + fabsf(rt_f);   // every rounding above is relative to one of these
+                        my_u[nb * 64 + cw] = __float2int_rd(0.25f * (fmaf(m, -4.0e-6f, y) - 8.0f));
+                    }
+                }
+                __syncwarp();
             }
-            const float norm_lo = inv_hi > 0.0f ? 1.0f / inv_hi : 0.0f;
-            const float norm_hi = inv_hi > 0.0f ? 1.0f / inv_lo : 0.0f;
-            __syncwarp();
-            // u = floor(thr * norm - colterm - slack): a handful of float ops per column; the float -> int conversion
-            // saturates, so the clamped +-1e30 thresholds (-inf: nothing seen yet, +inf: padding column) become INT_MIN / INT_MAX
-            for (uint32_t cc = (uint32_t)lane; cc < NB * cols_per_warp; cc += 32) {
-                const uint32_t nb = cc / cols_per_warp, cw = cc - nb * cols_per_warp;
-                const uint32_t col = nb * NMMA + slice * cols_per_warp + cw;
-                const float2 pc = s_pre[col];
-                const float tt = pc.x * (pc.x >= 0.0f ? norm_lo : norm_hi);
-                const float y = tt - pc.y;
-                const float m = fabsf(tt) + fabsf(pc.y);            // every rounding above is relative to one of these
-                my_u[nb * 64 + cw] = __float2int_rd(fmaf(m, -4.0e-6f, y) - 8.0f);
-            }
-            __syncwarp();
             for (uint32_t nb = 0; nb < NB; ++nb) {
                 const uint32_t ab = (NB == 2) ? nb : (tile_iter & 1u);
                 const uint32_t uses = ab ? uses1 : uses0;
@@ -398,32 +425,29 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                         }
                         continue;
                     }
-                    // one multiply-add and one compare per score, OR-ed into two predicates (two dependency chains)
+                    // one compare per score against the raw accumulator, OR-ed into two predicates (two dependency chains)
                     bool some = false, some2 = false;
 #pragma unroll
                     for (int i4 = 0; i4 < 8; ++i4) {
                         const int4 u4 = *reinterpret_cast<const int4*>(my_u + nb * 64 + cw0 + 4 * i4);
-                        some |= (4 * (int)r[4 * i4 + 0] + rowterm >= u4.x);
-                        some2 |= (4 * (int)r[4 * i4 + 1] + rowterm >= u4.y);
-                        some |= (4 * (int)r[4 * i4 + 2] + rowterm >= u4.z);
-                        some2 |= (4 * (int)r[4 * i4 + 3] + rowterm >= u4.w);
+                        some |= ((int)r[4 * i4 + 0] >= u4.x);
+                        some2 |= ((int)r[4 * i4 + 1] >= u4.y);
+                        some |= ((int)r[4 * i4 + 2] >= u4.z);
+                        some2 |= ((int)r[4 * i4 + 3] >= u4.w);
                     }
                     if (!__any_sync(0xFFFFFFFFu, (some || some2) && row_ok)) continue;
-                    // some lane passed the pre-test in some column: find which (recomputed from opaque copies, so that
-                    // the compiler does not keep the 32 sums and 32 bounds of the fast pass alive across the branch)
+                    // some lane passed the pre-test in some column: find which (bounds re-read through an opaque pointer,
+                    // so that the compiler does not keep the 32 bounds of the fast pass alive across the branch)
                     uint32_t mask = 0;
-                    int rowterm_s = rowterm;
                     const int* u_s = my_u + nb * 64 + cw0;
-                    asm volatile("" : "+r"(rowterm_s), "+l"(u_s));
+                    asm volatile("" : "+l"(u_s));
 #pragma unroll
                     for (int i4 = 0; i4 < 8; ++i4) {
                         const int4 u4 = *reinterpret_cast<const int4*>(u_s + 4 * i4);
                         const int us[4] = {u4.x, u4.y, u4.z, u4.w};
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int x = 4 * (int)r[4 * i4 + j] + rowterm_s;
-                            if (x >= us[j]) mask |= 1u << (4 * i4 + j);
-                        }
+                        for (int j = 0; j < 4; ++j)
+                            if ((int)r[4 * i4 + j] >= us[j]) mask |= 1u << (4 * i4 + j);
                     }
                     if (!row_ok) mask = 0;
 #ifdef PBX_EXP_BATCH_NOSLOW
