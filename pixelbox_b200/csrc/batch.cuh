@@ -1,5 +1,5 @@
 // batch.cuh -- kernel B: the batched-query path.  A batch of queries against the corpus is a dense
-// u8 x u8 -> s32 contraction  S[r, q] = sum_i r_i q_i,  run on the 5th-generation tensor cores
+// u8 x s8 -> s32 contraction  S[r, q] = sum_i r_i (q_i - 128),  run on the 5th-generation tensor cores
 // (tcgen05.mma.kind::i8, accumulators in TMEM), with the top-k selection fused into the epilogue so the
 // N x Q score matrix (10^10 entries for 10M x 1024) never exists in memory.
 //
@@ -11,13 +11,17 @@
 //
 // One CTA = one query group (QG <= 512 queries resident in shared memory, loaded once by TMA) x a strided set of
 // 128-row corpus tiles.  Warp 0 streams corpus tiles with TMA (128-byte swizzle, 16 KB K-chunks, 4-stage
-// mbarrier ring), one thread of warp 1 issues the MMAs (M = 128 rows, N = up to 256 queries, K = 32 bytes per
-// instruction), warps 2..5 are the epilogue: tcgen05.ld of their TMEM lane quarter, two integer adds, one
-// int->float, one multiply and a compare per score; the few scores that beat the query's current threshold are
-// pushed into that query's candidate buffer in global memory.  Thresholds start at -inf and are tightened
-// between rounds over geometrically growing row ranges (batch_tighten_kernel), so each round adds ~2k
-// candidates per query.  The final candidates go through the same bit-exact re-rank and certificate as the
-// single-query path (finalize_kernel<true>).
+// mbarrier ring); one thread of warp 1 issues the MMAs (M = 128 rows, N = 128 queries, K = 32 bytes per
+// instruction) into a ring of four TMEM accumulators; warps 2..17 are the epilogue: each owns 32 TMEM lanes (rows)
+// and 32 columns of every accumulator, reads them with one tcgen05.ld.32x32b.x32, hands the accumulator straight
+// back to the MMA warp, and tests every score with ONE integer compare against a per-(warp, column) bound that is
+// rebuilt per tile from the query's current threshold and the norm / row-term range of the warp's 32 rows.  Only
+// columns in which some lane passes take the exact test (int -> float, one multiply, one compare); the few that
+// beat the threshold are staged in shared memory and pushed 32 at a time into the query's candidate buffer.
+// Round 0 (2048 rows) has no threshold yet: a flood variant writes every score to slot = row, no atomics.  Later
+// rounds cover geometrically growing row ranges; between rounds batch_tighten_kernel cuts the buffers back to
+// `keep`, inside a round the thresholds tighten from per-query histograms of the accepted keys.  The final
+// candidates go through the same bit-exact re-rank and certificate as the single-query path (finalize_kernel<true>).
 #pragma once
 #include <cuda.h>
 #include <cstdio>
@@ -29,6 +33,8 @@ constexpr int kBatchEpiWarps = 16;           // four per TMEM lane quarter, each
 constexpr int kBatchThreads = 64 + 32 * kBatchEpiWarps;   // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr int kBatchStages = 4;              // corpus K-chunk ring: 4 x 16 KB
 constexpr int kBatchTileRows = 128;          // UMMA M
+constexpr int kBatchAccStages = 4;           // TMEM: 4 accumulators of 128 rows x 128 queries (512 columns), a ring between MMA and epilogue
+constexpr uint32_t kBatchAccCols = 128;      // UMMA N
 constexpr uint32_t kBatchCap = 4096;         // candidate buffer entries per query
 constexpr uint32_t kBatchQueryBytes = 128 * 1024;   // resident queries per CTA
 constexpr uint32_t kBatchHistBins = 256;            // per-query histogram of accepted keys over kappa in [-1, 1]
@@ -44,12 +50,14 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: the waiting thread sleeps in hardware between polls instead of spinning on the
+// issue port.  (Measured against a tight spin and against try_wait + nanosleep(32): within 2.5 % of each other.)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "PBX_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"      // %2: suspend-time hint (ns): the thread sleeps in
-        "@p bra PBX_DONE;\n\t"                                                // hardware instead of spinning on the issue port
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra PBX_DONE;\n\t"
         "bra PBX_WAIT;\n\t"
         "PBX_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
@@ -173,8 +181,8 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
     // boundaries, and dynamic shared memory only starts after the static variables (the host adds 1 KB of slack)
     uint8_t* bsm = bsm_raw + ((1024u - (smem_u32(bsm_raw) & 1023u)) & 1023u);
     const uint32_t QG = p.qg, KC = p.kc;
-    const uint32_t NMMA = QG < 256 ? QG : 256;          // queries per MMA instruction
-    const uint32_t NB = QG / NMMA;                      // accumulators per tile (1 or 2)
+    const uint32_t NMMA = QG < 256 ? QG : 256;          // rows of one TMA box of the query operand
+    const uint32_t NS = QG / kBatchAccCols;             // accumulator stages per tile (4, 2 or 1): 128 queries each
     uint8_t* sQ = bsm;                                  // [KC][QG][128]
     uint8_t* sA = bsm + (size_t)QG * KC * 128;          // [stages][128][128]
     int* s_colterm = reinterpret_cast<int*>(sA + kBatchStages * kBatchTileRows * 128);
@@ -186,7 +194,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
     // ~1 us round trip of the slot atomic is paid once per 32 candidates instead of once per candidate
     __shared__ u64 st_key[kBatchEpiWarps][64];
     __shared__ uint32_t st_q[kBatchEpiWarps][64];
-    __shared__ __align__(8) uint64_t q_full, a_full[kBatchStages], a_empty[kBatchStages], acc_full[2], acc_empty[2];
+    __shared__ __align__(8) uint64_t q_full, a_full[kBatchStages], a_empty[kBatchStages], acc_full[kBatchAccStages], acc_empty[kBatchAccStages];
     __shared__ uint32_t tmem_base;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -200,7 +208,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
     if (threadIdx.x == 0) {
         mbar_init(&q_full, 1);
         for (int i = 0; i < kBatchStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kBatchEpiWarps); }
+        for (int i = 0; i < kBatchAccStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kBatchEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (uint32_t i = threadIdx.x; i < QG; i += blockDim.x) {
@@ -240,45 +248,42 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
         if (lane == 0) {
             // instruction descriptor: D = s32 (2 << 4), A = u8 (0 at bit 7), B = s8 (1 at bit 10), both K-major,
             // N >> 3 at bit 17, M >> 4 at bit 24
-            const uint32_t idesc = (2u << 4) | (1u << 10) | ((NMMA >> 3) << 17) | ((uint32_t)(kBatchTileRows >> 4) << 24);
+            const uint32_t idesc = (2u << 4) | (1u << 10) | ((kBatchAccCols >> 3) << 17) | ((uint32_t)(kBatchTileRows >> 4) << 24);
             mbar_wait(&q_full, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t it = 0, tile_iter = 0;
-            uint32_t uses0 = 0, uses1 = 0;
-            for (uint32_t t = p.tile_begin + ci; t < p.tile_end; t += cstride, ++tile_iter) {
+            uint32_t it = 0, acc_it = 0;
+            for (uint32_t t = p.tile_begin + ci; t < p.tile_end; t += cstride) {
                 const uint32_t it0 = it;
-                for (uint32_t nb = 0; nb < NB; ++nb) {
-                    const uint32_t ab = (NB == 2) ? nb : (tile_iter & 1u);       // accumulator buffer
-                    mbar_wait(&acc_empty[ab], ((ab ? uses1 : uses0) & 1u) ^ 1u);  // the epilogue has drained its previous use
+                for (uint32_t sg = 0; sg < NS; ++sg, ++acc_it) {
+                    const uint32_t ab = acc_it % kBatchAccStages, par = (acc_it / kBatchAccStages) & 1u;
+                    mbar_wait(&acc_empty[ab], par ^ 1u);                          // the epilogue has drained its previous use
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t d_tmem = tmem + ab * 256u;
+                    const uint32_t d_tmem = tmem + ab * kBatchAccCols;
                     for (uint32_t kc = 0; kc < KC; ++kc) {
                         const uint32_t itk = it0 + kc;
                         const uint32_t st = itk % kBatchStages, ph = (itk / kBatchStages) & 1u;
-                        if (nb == 0) {
+                        if (sg == 0) {
                             mbar_wait(&a_full[st], ph);
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         }
                         const uint64_t da = umma_desc_sw128(sA + (size_t)st * kBatchTileRows * 128);
-                        const uint64_t db = umma_desc_sw128(sQ + ((size_t)kc * QG + (size_t)nb * NMMA) * 128);
+                        const uint64_t db = umma_desc_sw128(sQ + ((size_t)kc * QG + (size_t)sg * kBatchAccCols) * 128);
 #pragma unroll
                         for (uint32_t ks = 0; ks < 4; ++ks)
                             umma_i8(d_tmem, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, (kc | ks) ? 1u : 0u);
-                        if (nb == NB - 1) umma_commit(&a_empty[st]);              // the stage is free once these MMAs retire
+                        if (sg == NS - 1) umma_commit(&a_empty[st]);              // the stage is free once these MMAs retire
                     }
                     umma_commit(&acc_full[ab]);
-                    if (ab) ++uses1; else ++uses0;
                 }
                 it = it0 + KC;
             }
         }
     } else {
-        // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 (a hardware rule) and a quarter of the columns =====
+        // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 (a hardware rule) and 32 of the 128 columns of every
+        // accumulator stage (slice).  The MMA warp may run up to four stages ahead of the slowest epilogue warp. =====
         const uint32_t quarter = (uint32_t)warp & 3u;
         const uint32_t slice = (uint32_t)(warp - 2) >> 2;            // 0..3
-        const uint32_t cols_per_warp = NMMA / 4;                     // 64 or 32
-        uint32_t tile_iter = 0;
-        uint32_t uses0 = 0, uses1 = 0;
+        uint32_t tile_iter = 0, acc_it = 0;
         const int dterm = -255 * (int)p.dim;
         u64* my_key = st_key[warp - 2];
         uint32_t* my_q = st_q[warp - 2];
@@ -385,35 +390,31 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                 // a handful of float ops per column; the float -> int conversion saturates, so the clamped +-1e30
                 // thresholds (-inf: nothing seen yet, +inf: padding column) become INT_MIN / INT_MAX
 #pragma unroll
-                for (uint32_t it = 0; it < 4; ++it) {
-                    const uint32_t cc = (uint32_t)lane + 32u * it;
-                    if (cc < NB * cols_per_warp) {
-                        const uint32_t nb = cc / cols_per_warp, cw = cc - nb * cols_per_warp;
-                        const uint32_t col = nb * NMMA + slice * cols_per_warp + cw;
+                for (uint32_t sg = 0; sg < (uint32_t)kBatchAccStages; ++sg) {
+                    if (sg < NS) {
+                        const uint32_t col = sg * kBatchAccCols + slice * 32u + (uint32_t)lane;
                         const float2 pc = s_pre[col];
                         const float tt = pc.x * (pc.x >= 0.0f ? norm_lo : norm_hi);
                         const float y = (tt - pc.y) - rt_f;
                         const float m = fabsf(tt) + fabsf(pc.y) + fabsf(rt_f);   // every rounding above is relative to one of these
-                        my_u[nb * 64 + cw] = __float2int_rd(0.25f * (fmaf(m, -4.0e-6f, y) - 8.0f));
+                        my_u[sg * 32u + (uint32_t)lane] = __float2int_rd(0.25f * (fmaf(m, -4.0e-6f, y) - 8.0f));
                     }
                 }
                 __syncwarp();
             }
-            for (uint32_t nb = 0; nb < NB; ++nb) {
-                const uint32_t ab = (NB == 2) ? nb : (tile_iter & 1u);
-                const uint32_t uses = ab ? uses1 : uses0;
-                mbar_wait(&acc_full[ab], uses & 1u);
-                if (ab) ++uses1; else ++uses0;
+            for (uint32_t sg = 0; sg < NS; ++sg, ++acc_it) {
+                const uint32_t ab = acc_it % kBatchAccStages;
+                mbar_wait(&acc_full[ab], (acc_it / kBatchAccStages) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t tbase = tmem + ((quarter * 32u) << 16) + ab * 256u;
-#ifdef PBX_EXP_BATCH_NOEPI
-                if (false)
-#endif
-                for (uint32_t cw0 = 0; cw0 < cols_per_warp; cw0 += 32) {
-                    const uint32_t c0 = slice * cols_per_warp + cw0;
+                do {                                                  // one 32-column block per warp and stage
                     uint32_t r[32];
-                    tmem_ld32(tbase + c0, r);
-                    const uint32_t colbase = nb * NMMA + c0;
+                    tmem_ld32(tmem + ((quarter * 32u) << 16) + ab * kBatchAccCols + slice * 32u, r);
+                    // the scores are in registers: hand the accumulator back to the MMA warp before looking at them
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[ab]);
+                    const uint32_t colbase = sg * kBatchAccCols + slice * 32u;
+                    const int* my_us = my_u + sg * 32u;
                     if constexpr (FLOOD) {
                         // round 0: every score of a real query is a candidate; its slot in the query's buffer is its row
 #pragma unroll
@@ -429,7 +430,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                     bool some = false, some2 = false;
 #pragma unroll
                     for (int i4 = 0; i4 < 8; ++i4) {
-                        const int4 u4 = *reinterpret_cast<const int4*>(my_u + nb * 64 + cw0 + 4 * i4);
+                        const int4 u4 = *reinterpret_cast<const int4*>(my_us + 4 * i4);
                         some |= ((int)r[4 * i4 + 0] >= u4.x);
                         some2 |= ((int)r[4 * i4 + 1] >= u4.y);
                         some |= ((int)r[4 * i4 + 2] >= u4.z);
@@ -439,7 +440,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                     // some lane passed the pre-test in some column: find which (bounds re-read through an opaque pointer,
                     // so that the compiler does not keep the 32 bounds of the fast pass alive across the branch)
                     uint32_t mask = 0;
-                    const int* u_s = my_u + nb * 64 + cw0;
+                    const int* u_s = my_us;
                     asm volatile("" : "+l"(u_s));
 #pragma unroll
                     for (int i4 = 0; i4 < 8; ++i4) {
@@ -450,9 +451,6 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                             if ((int)r[4 * i4 + j] >= us[j]) mask |= 1u << (4 * i4 + j);
                     }
                     if (!row_ok) mask = 0;
-#ifdef PBX_EXP_BATCH_NOSLOW
-                    if (mask != 0x12345u) mask = 0;
-#endif
                     // rare: for every column in which some lane survived the pre-test, those lanes take the exact test
                     uint32_t any = __reduce_or_sync(0xFFFFFFFFu, mask);
                     while (any) {
@@ -484,10 +482,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                         staged += (uint32_t)__popc(hb);
                         if (staged >= 32) flush();
                     }
-                }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[ab]);
+                } while (false);
             }
         }
         flush();
