@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -594,7 +595,12 @@ static int ensure_batch_scratch(pbx_corpus* c, uint32_t nq_pad) {
 static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, uint32_t k, double max_dist, pbx_hit* d_hits,
                                   uint32_t* d_count, cudaStream_t s, uint32_t n) {
     const uint32_t pitch = c->pitch, kc = pitch / 128;
-    const uint32_t qg = pitch <= 256 ? 512u : pitch <= 512 ? 256u : 128u;      // resident queries per CTA: qg * pitch <= 128 KB
+    // Resident queries per CTA: as many as fit 128 KB of shared memory (512, 256 or 128); what is left holds the corpus
+    // ring.  Measured at 10M x 256: 512 queries + 4 ring stages beat 256 + 8 and 128 + 8 (4.8 / 5.1 / 6.0 ms per batch):
+    // the per-tile work of the epilogue warps is amortised over more scores.
+    uint32_t qg = 512;
+    while ((size_t)qg * pitch > 128u * 1024u) qg >>= 1;
+    if (qg < 128) return fail(PBX_E_INTERNAL, "batched path: pitch %u too wide", pitch);
     const uint32_t groups = (nq + qg - 1) / qg, nq_pad = groups * qg;
     const uint32_t nmma = qg < 256 ? qg : 256;
     int rc = ensure_query_scratch(c, nq);
@@ -632,7 +638,10 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
     mp.bhist = c->d_bhist; mp.inv_q = c->d_binvq; mp.thr_live = c->d_thr; mp.keep = keep;
     mp.n = n; mp.dim = c->dim; mp.kc = kc; mp.qg = qg; mp.groups = groups;
     const int grid = std::max<int>((int)groups, (c->sm_count / (int)groups) * (int)groups);
-    const size_t mma_smem = (size_t)qg * pitch + (size_t)kBatchStages * kBatchTileRows * 128 + (size_t)qg * 20 + (size_t)kBatchEpiWarps * 128 * 4 + 1024;
+    const size_t mma_fixed = (size_t)qg * pitch + (size_t)qg * 20 + (size_t)kBatchEpiWarps * 128 * 4 + 1024;
+    const uint32_t stages = (uint32_t)std::min<size_t>(kBatchMaxStages, (212u * 1024u - mma_fixed) / ((size_t)kBatchTileRows * 128));
+    const size_t mma_smem = mma_fixed + (size_t)stages * kBatchTileRows * 128;
+    mp.stages = stages;
     BatchTightenParams tp;
     tp.cand = c->d_bcand; tp.cand_cnt = c->d_bcnt; tp.thr = c->d_thr; tp.keep = keep; tp.nq = nq;
 

@@ -31,7 +31,7 @@ namespace pbx {
 
 constexpr int kBatchEpiWarps = 16;           // four per TMEM lane quarter, each takes a quarter of an accumulator's columns
 constexpr int kBatchThreads = 64 + 32 * kBatchEpiWarps;   // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
-constexpr int kBatchStages = 4;              // corpus K-chunk ring: 4 x 16 KB
+constexpr int kBatchMaxStages = 8;           // corpus K-chunk ring: up to 8 x 16 KB (the host sizes it to the shared memory left)
 constexpr int kBatchTileRows = 128;          // UMMA M
 constexpr int kBatchAccStages = 4;           // TMEM: 4 accumulators of 128 rows x 128 queries (512 columns), a ring between MMA and epilogue
 constexpr uint32_t kBatchAccCols = 128;      // UMMA N
@@ -170,6 +170,7 @@ struct BatchMmaParams {
     uint32_t kc;                // K-chunks of 128 bytes per row (pitch / 128)
     uint32_t qg;                // queries per group (resident per CTA): 128, 256 or 512
     uint32_t groups;            // query groups; gridDim.x is a multiple of it
+    uint32_t stages;            // corpus K-chunk ring depth (16 KB each)
     uint32_t tile_begin, tile_end;   // 128-row tiles of this round
 };
 
@@ -185,7 +186,8 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
     const uint32_t NS = QG / kBatchAccCols;             // accumulator stages per tile (4, 2 or 1): 128 queries each
     uint8_t* sQ = bsm;                                  // [KC][QG][128]
     uint8_t* sA = bsm + (size_t)QG * KC * 128;          // [stages][128][128]
-    int* s_colterm = reinterpret_cast<int*>(sA + kBatchStages * kBatchTileRows * 128);
+    const uint32_t STAGES = p.stages;
+    int* s_colterm = reinterpret_cast<int*>(sA + (size_t)STAGES * kBatchTileRows * 128);
     float* s_thr = reinterpret_cast<float*>(s_colterm + QG);
     float* s_invq = s_thr + QG;
     float2* s_pre = reinterpret_cast<float2*>(s_invq + QG);   // per column {threshold clamped to +-1e30, (float)colterm}: inputs of the pre-test bound
@@ -194,7 +196,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
     // ~1 us round trip of the slot atomic is paid once per 32 candidates instead of once per candidate
     __shared__ u64 st_key[kBatchEpiWarps][64];
     __shared__ uint32_t st_q[kBatchEpiWarps][64];
-    __shared__ __align__(8) uint64_t q_full, a_full[kBatchStages], a_empty[kBatchStages], acc_full[kBatchAccStages], acc_empty[kBatchAccStages];
+    __shared__ __align__(8) uint64_t q_full, a_full[kBatchMaxStages], a_empty[kBatchMaxStages], acc_full[kBatchAccStages], acc_empty[kBatchAccStages];
     __shared__ uint32_t tmem_base;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -207,7 +209,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
     }
     if (threadIdx.x == 0) {
         mbar_init(&q_full, 1);
-        for (int i = 0; i < kBatchStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < kBatchMaxStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < kBatchAccStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kBatchEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -236,7 +238,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
             uint32_t it = 0;
             for (uint32_t t = p.tile_begin + ci; t < p.tile_end; t += cstride) {
                 for (uint32_t kc = 0; kc < KC; ++kc, ++it) {
-                    const uint32_t st = it % kBatchStages, ph = (it / kBatchStages) & 1u;
+                    const uint32_t st = it % STAGES, ph = (it / STAGES) & 1u;
                     mbar_wait(&a_empty[st], ph ^ 1u);
                     mbar_expect_tx(&a_full[st], kBatchTileRows * 128);
                     tma_load_2d(sA + (size_t)st * kBatchTileRows * 128, &p.map_rows, &a_full[st], (int)(kc * 128), (int)(t * kBatchTileRows));
@@ -261,7 +263,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                     const uint32_t d_tmem = tmem + ab * kBatchAccCols;
                     for (uint32_t kc = 0; kc < KC; ++kc) {
                         const uint32_t itk = it0 + kc;
-                        const uint32_t st = itk % kBatchStages, ph = (itk / kBatchStages) & 1u;
+                        const uint32_t st = itk % STAGES, ph = (itk / STAGES) & 1u;
                         if (sg == 0) {
                             mbar_wait(&a_full[st], ph);
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
