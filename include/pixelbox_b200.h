@@ -185,6 +185,21 @@ PBX_API void pbx_exchange_destroy(pbx_exchange* x);
 PBX_API int pbx_cosine_distance_pairs(int device, const uint8_t* a, const uint8_t* b, uint64_t n, uint32_t dim,
                                       float* out_dist, int32_t* out_dot, int32_t* out_norm2_a, int32_t* out_norm2_b);
 
+/* ---- the other two registered scalar functions ---------------------------------
+ * Replace, for a batch of pairs in host memory (a and b are [n][dim] u8):
+ *   `pub fn byte_distance(&Vec<u8>, &Vec<u8>) -> f32`     src/engine.rs:590-592  (UDF registered at :624-638)
+ *       out_dist = sum |a_i - b_i| / (255 * dim), bit for bit; out_l1 (optional) = the integer sum.
+ *   `pub fn hamming_distance(&Vec<u8>, &Vec<u8>) -> f32`  src/engine.rs:594-604  (UDF registered at :640-654)
+ *       upstream adds the per-byte bit counts in a u8: past 255 differing bits the sum wraps (release build; a
+ *       debug build panics).  out_dist reproduces the wrapped value, (bits mod 256) / (8 * dim); out_bits
+ *       (optional) = the true number of differing bits.  Upstream KATs: test_hamming_distance, :693-701.
+ * No query upstream uses either function; they exist for external users of the database, like
+ * pbx_cosine_distance_pairs.  n <= 2^26 pairs per call. */
+PBX_API int pbx_byte_distance_pairs(int device, const uint8_t* a, const uint8_t* b, uint64_t n, uint32_t dim,
+                                    float* out_dist, uint32_t* out_l1);
+PBX_API int pbx_hamming_distance_pairs(int device, const uint8_t* a, const uint8_t* b, uint64_t n, uint32_t dim,
+                                       float* out_dist, uint32_t* out_bits);
+
 /* ---- the ingest quantizer ---------------------------------------------------------------------
  * Replaces: the f32 -> u8 map of mlhash, `128u8.saturating_add_signed((f*128.0).max(-128.0).min(128.0) as i8)`
  * (src/image_hashes/efficientnet.rs:39; README.md:54 example [-1, 1, 0, 0.1] -> [0x00, 0xFF, 0x80, 0x8C]), for a batch

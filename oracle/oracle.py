@@ -52,6 +52,10 @@ def lib() -> ctypes.CDLL:
                                       ctypes.c_double, ctypes.c_int, _i64p, _f32p, _i32p, _i32p, _u32p]
         L.pbx_oracle_all_distances.restype = None
         L.pbx_oracle_all_distances.argtypes = [_u8p, ctypes.c_uint64, ctypes.c_uint32, _u8p, _f32p]
+        L.pbx_oracle_byte_distance.restype = ctypes.c_float
+        L.pbx_oracle_byte_distance.argtypes = [_u8p, _u8p, ctypes.c_size_t]
+        L.pbx_oracle_hamming_distance.restype = ctypes.c_float
+        L.pbx_oracle_hamming_distance.argtypes = [_u8p, _u8p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32)]
         L.pbx_oracle_quantize.restype = ctypes.c_uint8
         L.pbx_oracle_quantize.argtypes = [ctypes.c_float]
         L.pbx_oracle_synth_rows.restype = None
@@ -132,6 +136,22 @@ def all_distances(corpus, query) -> np.ndarray:
     out = np.zeros(n, np.float32)
     lib().pbx_oracle_all_distances(_p(corpus, _u8p), n, d, _p(query, _u8p), _p(out, _f32p))
     return out
+
+
+def byte_distance(a, b) -> np.float32:
+    """src/engine.rs:590-592."""
+    a, b = _u8(a).ravel(), _u8(b).ravel()
+    assert a.size == b.size
+    return np.float32(lib().pbx_oracle_byte_distance(_p(a, _u8p), _p(b, _u8p), a.size))
+
+
+def hamming_distance(a, b):
+    """src/engine.rs:594-604 with the u8 sum wrapping as in a release build; returns (f32 distance, true differing bits)."""
+    a, b = _u8(a).ravel(), _u8(b).ravel()
+    assert a.size == b.size
+    bits = ctypes.c_uint32(0)
+    d = lib().pbx_oracle_hamming_distance(_p(a, _u8p), _p(b, _u8p), a.size, ctypes.byref(bits))
+    return np.float32(d), int(bits.value)
 
 
 def quantize(f) -> np.ndarray:

@@ -242,6 +242,40 @@ void pbx_oracle_all_distances(const uint8_t* corpus, uint64_t n, uint32_t d, con
 }
 
 /* ------------------------------------------------------------------------------------------
+ * The other two registered distances.
+ * byte_distance, src/engine.rs:590-592: f32 fold of |a - b| (every partial sum is an integer below 2^24,
+ *   so the fold is exact), divided by (255f32 * len as f32).
+ * hamming_distance, src/engine.rs:594-604: per byte the number of differing bits as a u8, `.sum::<u8>()`,
+ *   divided by (8f32 * len as f32).  The u8 sum overflows past 255 differing bits: a debug build panics,
+ *   a release build wraps modulo 256; this restatement wraps (the behaviour of the shipped binary) and
+ *   reports the true bit count separately.  Upstream KATs: test_hamming_distance, src/engine.rs:693-701.
+ * ------------------------------------------------------------------------------------------ */
+PBX_ORACLE_API
+float pbx_oracle_byte_distance(const uint8_t* a, const uint8_t* b, size_t len) {
+    float acc = 0.0f;
+    for (size_t i = 0; i < len; ++i) {
+        float d = (float)a[i] - (float)b[i];
+        acc = acc + (d < 0.0f ? -d : d);
+    }
+    return acc / (255.0f * (float)len);
+}
+
+PBX_ORACLE_API
+float pbx_oracle_hamming_distance(const uint8_t* a, const uint8_t* b, size_t len, uint32_t* true_bits) {
+    uint8_t sum = 0;
+    uint32_t all = 0;
+    for (size_t i = 0; i < len; ++i) {
+        uint8_t diff = (uint8_t)(a[i] ^ b[i]);
+        uint8_t bits_set = 0;
+        while (diff != 0) { bits_set = (uint8_t)(bits_set + (diff & 1)); diff >>= 1; }
+        sum = (uint8_t)(sum + bits_set);          /* wrapping, as in a release build */
+        all += bits_set;
+    }
+    if (true_bits) *true_bits = all;
+    return (float)sum / (8.0f * (float)len);
+}
+
+/* ------------------------------------------------------------------------------------------
  * Quantizer, src/image_hashes/efficientnet.rs:39:
  *   128u8.saturating_add_signed((f*128.0f32).max(-128.0).min(128.0) as i8)
  * `as i8` from f32 truncates toward zero and saturates (so +128.0 -> 127); NaN -> 0.

@@ -184,6 +184,35 @@ def cosine_distance_pairs(a, b, device: int = 0):
     return dist, dot, na, nb
 
 
+def _pairs(a, b):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.uint8))
+    b = np.ascontiguousarray(np.asarray(b, dtype=np.uint8))
+    if a.ndim == 1:
+        a, b = a.reshape(1, -1), b.reshape(1, -1)
+    if a.shape != b.shape:
+        raise nat.PbxError(-2, f"pair shapes differ: {a.shape} vs {b.shape}")
+    return a, b
+
+
+def byte_distance_pairs(a, b, device: int = 0):
+    """pbx_byte_distance_pairs: the reference's byte_distance (src/engine.rs:590-592); returns (dist f32, L1 sum u32)."""
+    a, b = _pairs(a, b)
+    n, d = a.shape
+    dist, l1 = np.zeros(n, np.float32), np.zeros(n, np.uint32)
+    nat.check(nat.lib().pbx_byte_distance_pairs(int(device), nat.ptr(a), nat.ptr(b), n, d, nat.ptr(dist), nat.ptr(l1)))
+    return dist, l1
+
+
+def hamming_distance_pairs(a, b, device: int = 0):
+    """pbx_hamming_distance_pairs: the reference's hamming_distance (src/engine.rs:594-604, u8 sum wrapping as in a
+    release build); returns (dist f32, true differing bits u32)."""
+    a, b = _pairs(a, b)
+    n, d = a.shape
+    dist, bits = np.zeros(n, np.float32), np.zeros(n, np.uint32)
+    nat.check(nat.lib().pbx_hamming_distance_pairs(int(device), nat.ptr(a), nat.ptr(b), n, d, nat.ptr(dist), nat.ptr(bits)))
+    return dist, bits
+
+
 def quantize(embeddings, device: int = 0) -> np.ndarray:
     """pbx_quantize: the reference's f32 -> u8 encoder (src/image_hashes/efficientnet.rs:39) on the GPU."""
     f = np.ascontiguousarray(np.asarray(embeddings, dtype=np.float32))

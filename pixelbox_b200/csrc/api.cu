@@ -1142,6 +1142,48 @@ extern "C" int pbx_cosine_distance_pairs(int device, const uint8_t* a, const uin
     return rc;
 }
 
+// byte_distance / hamming_distance for pairs: which = 0 byte, 1 hamming
+static int pair_byte_hamming(int device, const uint8_t* a, const uint8_t* b, uint64_t n, uint32_t dim, int which, float* out_dist,
+                             uint32_t* out_int) {
+    if (dim == 0 || dim > PBX_MAX_DIM) return fail(PBX_E_DIM, "dim %u outside [1, %u]", dim, PBX_MAX_DIM);
+    if (n == 0) return PBX_OK;
+    if (!a || !b || !out_dist) return fail(PBX_E_INVALID, "NULL argument");
+    if (pbx_device_count() == 0) return fail(PBX_E_NO_DEVICE, "no sm_100 device: pixelbox_b200 has no CPU fallback");
+    CU_TRY(cudaSetDevice(device));
+    uint8_t *da = nullptr, *db = nullptr;
+    float* dd = nullptr;
+    uint32_t* di = nullptr;
+    cudaError_t e = cudaMalloc(&da, n * dim);
+    if (e == cudaSuccess) e = cudaMalloc(&db, n * dim);
+    if (e == cudaSuccess) e = cudaMalloc(&dd, n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&di, n * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(da, a, n * dim, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(db, b, n * dim, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        const unsigned blocks = (unsigned)((n * 32 + 255) / 256);
+        if (which == 0) pair_byte_hamming_kernel<<<blocks, 256>>>(da, db, n, dim, dd, di, nullptr, nullptr);
+        else pair_byte_hamming_kernel<<<blocks, 256>>>(da, db, n, dim, nullptr, nullptr, dd, di);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out_dist, dd, n * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && out_int) e = cudaMemcpy(out_int, di, n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    cudaFree(da); cudaFree(db); cudaFree(dd); cudaFree(di);
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? PBX_E_OOM : PBX_E_CUDA, "pair distance failed: %s", cudaGetErrorString(e));
+    return PBX_OK;
+}
+
+extern "C" int pbx_byte_distance_pairs(int device, const uint8_t* a, const uint8_t* b, uint64_t n, uint32_t dim, float* out_dist,
+                                       uint32_t* out_l1) {
+    if (n > (1ull << 26)) return fail(PBX_E_INVALID, "at most 2^26 pairs per call");
+    return pair_byte_hamming(device, a, b, n, dim, 0, out_dist, out_l1);
+}
+
+extern "C" int pbx_hamming_distance_pairs(int device, const uint8_t* a, const uint8_t* b, uint64_t n, uint32_t dim, float* out_dist,
+                                          uint32_t* out_bits) {
+    if (n > (1ull << 26)) return fail(PBX_E_INVALID, "at most 2^26 pairs per call");
+    return pair_byte_hamming(device, a, b, n, dim, 1, out_dist, out_bits);
+}
+
 extern "C" int pbx_quantize(int device, const float* embeddings, uint64_t n, uint8_t* out) {
     if (n == 0) return PBX_OK;
     if (!embeddings || !out) return fail(PBX_E_INVALID, "NULL argument");

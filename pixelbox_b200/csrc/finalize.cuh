@@ -451,4 +451,48 @@ __global__ void pair_distance_kernel(const uint8_t* __restrict__ a, const uint8_
     if (out_nb) out_nb[t] = inb;
 }
 
+// ---- byte_distance (src/engine.rs:590-592) and hamming_distance (:594-604) for explicit pairs, SURVEY.md 8f N4 ------
+// One warp per pair; 4 bytes per lane and step (__vsadu4 = sum of absolute byte differences, __popc of the xor) when
+// dim is a multiple of 4, bytes otherwise.  Both sums are exact integers; the reference's f32 fold of |a - b| is exact
+// too (every partial sum is an integer below 2^24), so one correctly rounded division reproduces it bit for bit.
+// hamming_distance sums per-byte bit counts in a u8 upstream: the sum wraps modulo 256 in a release build, which is
+// what `out_ham` reproduces; `out_bits` is the true count.
+__global__ void __launch_bounds__(256)
+pair_byte_hamming_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint64_t n, uint32_t dim,
+                         float* __restrict__ out_byte, uint32_t* __restrict__ out_l1, float* __restrict__ out_ham,
+                         uint32_t* __restrict__ out_bits) {
+    const uint64_t pair = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    if (pair >= n) return;
+    const uint8_t* pa = a + pair * dim;
+    const uint8_t* pb = b + pair * dim;
+    uint32_t l1 = 0, bits = 0;
+    if ((dim & 3u) == 0 && (((uintptr_t)a | (uintptr_t)b) & 3u) == 0) {
+        const uint32_t* wa = reinterpret_cast<const uint32_t*>(pa);
+        const uint32_t* wb = reinterpret_cast<const uint32_t*>(pb);
+        for (uint32_t i = lane; i < dim / 4; i += 32) {
+            const uint32_t x = wa[i], y = wb[i];
+            l1 += __vsadu4(x, y);
+            bits += (uint32_t)__popc(x ^ y);
+        }
+    } else {
+        for (uint32_t i = lane; i < dim; i += 32) {
+            const int x = pa[i], y = pb[i];
+            l1 += (uint32_t)abs(x - y);
+            bits += (uint32_t)__popc((uint32_t)(x ^ y));
+        }
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        l1 += __shfl_xor_sync(0xFFFFFFFFu, l1, off);
+        bits += __shfl_xor_sync(0xFFFFFFFFu, bits, off);
+    }
+    if (lane == 0) {
+        if (out_byte) out_byte[pair] = __fdiv_rn((float)l1, __fmul_rn(255.0f, (float)dim));
+        if (out_l1) out_l1[pair] = l1;
+        if (out_ham) out_ham[pair] = __fdiv_rn((float)(bits & 0xFFu), __fmul_rn(8.0f, (float)dim));
+        if (out_bits) out_bits[pair] = bits;
+    }
+}
+
 }  // namespace pbx

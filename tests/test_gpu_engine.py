@@ -140,3 +140,30 @@ def test_quantizer_matches_reference_encoder():
     rng = np.random.default_rng(5)
     x = np.concatenate([special, rng.uniform(-1.2, 1.2, 20000).astype(np.float32), np.tanh(rng.normal(0, 1, 20000)).astype(np.float32)])
     assert np.array_equal(quantize(x), oracle.quantize(x))
+
+
+def test_byte_and_hamming_distance_pairs_match_reference():
+    """byte_distance (src/engine.rs:590-592) and hamming_distance (:594-604) on the GPU against the
+    oracle, bit for bit, including upstream's KATs (:693-701), odd dims (byte path) and the wrapping u8 sum."""
+    from oracle import oracle
+    from pixelbox_b200.corpus import byte_distance_pairs, hamming_distance_pairs
+    kat = [([0], [0xFF], 1.0), ([0x0F], [0xFF], 0.5), ([0x0], [0x0], 0.0), ([0b10101010], [0b01010101], 1.0)]
+    for a, b, want in kat:
+        d, bits_ = hamming_distance_pairs(a, b)
+        assert d[0] == np.float32(want)
+    d, _ = hamming_distance_pairs([[0b10101010, 0b01010101], [0xFF, 0x0F]], [[0b01010101, 0b10101010], [0x0F, 0x0F]])
+    assert list(d) == [np.float32(1.0), np.float32(0.25)]
+    rng = np.random.default_rng(11)
+    for dim in (1, 3, 4, 31, 64, 256, 1001, 4096):
+        n = 257
+        a = rng.integers(0, 256, size=(n, dim), dtype=np.uint8)
+        b = rng.integers(0, 256, size=(n, dim), dtype=np.uint8)
+        b[:8] = a[:8]                                       # identical pairs
+        b[8:16] = 255 - a[8:16]                             # every bit differs: wraps when dim * 8 > 255
+        bd, l1 = byte_distance_pairs(a, b)
+        hd, hb = hamming_distance_pairs(a, b)
+        for i in range(0, n, 3 if dim > 256 else 1):
+            assert np.float32(bd[i]).view(np.uint32) == oracle.byte_distance(a[i], b[i]).view(np.uint32), (dim, i)
+            o_h, o_bits = oracle.hamming_distance(a[i], b[i])
+            assert np.float32(hd[i]).view(np.uint32) == o_h.view(np.uint32) and int(hb[i]) == o_bits, (dim, i)
+        assert np.array_equal(l1, np.abs(a.astype(np.int64) - b.astype(np.int64)).sum(axis=1).astype(np.uint32))

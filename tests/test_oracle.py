@@ -159,3 +159,27 @@ def test_synth_generators_agree():
         assert np.array_equal(oracle.synth_rows(seed, r0, n, d), synth.synth_rows(seed, r0, n, d))
     x = synth.synth_rows(42, 0, 4096, 256)
     assert abs(float(x.mean()) - 127.5) < 1.0
+
+
+def test_upstream_hamming_kat_and_byte_distance():
+    """test_hamming_distance, src/engine.rs:693-701, against the restatement; byte_distance (:590-592) against a
+    direct numpy evaluation of the same f32 expression."""
+    kat = [([0], [0xFF], 1.0), ([0x0F], [0xFF], 0.5), ([0x0], [0x0], 0.0), ([0b10101010], [0b01010101], 1.0),
+           ([0b10101010, 0b01010101], [0b01010101, 0b10101010], 1.0), ([0xFF, 0x0F], [0x0F, 0x0F], 0.25)]
+    for a, b, want in kat:
+        got, true_bits = oracle.hamming_distance(a, b)
+        assert got == np.float32(want), (a, b)
+        assert true_bits == int(np.unpackbits(np.bitwise_xor(np.array(a, np.uint8), np.array(b, np.uint8))).sum())
+    # the u8 sum wraps past 255 differing bits (release build): 64 bytes all different -> 512 bits -> 0
+    a, b = np.zeros(64, np.uint8), np.full(64, 0xFF, np.uint8)
+    got, true_bits = oracle.hamming_distance(a, b)
+    assert true_bits == 512 and got == np.float32(0.0)
+    got, true_bits = oracle.hamming_distance(np.zeros(33, np.uint8), np.full(33, 0xFF, np.uint8))
+    assert true_bits == 264 and got == np.float32(8.0) / (np.float32(8.0) * np.float32(33.0))
+    rng = np.random.default_rng(3)
+    for d in (1, 2, 7, 64, 256, 1000, 4096):
+        a, b = rng.integers(0, 256, d, dtype=np.uint8), rng.integers(0, 256, d, dtype=np.uint8)
+        l1 = np.float32(np.abs(a.astype(np.int32) - b.astype(np.int32)).sum())          # exact in f32: < 2^24
+        assert bits(oracle.byte_distance(a, b)) == bits(l1 / (np.float32(255.0) * np.float32(d)))
+    assert oracle.byte_distance([0, 255], [255, 0]) == np.float32(1.0)
+    assert oracle.byte_distance([7, 7], [7, 7]) == np.float32(0.0)
