@@ -102,7 +102,8 @@ struct pbx_corpus {
     float* d_thr = nullptr;
     uint32_t* d_bcnt = nullptr;
     uint32_t* d_boverflow = nullptr;
-    u64* d_bcand = nullptr;           // [batch_pad][kBatchCap]
+    u64* d_bcand = nullptr;           // [batch_pad][batch_cap]
+    uint32_t batch_cap = 0;           // candidate buffer entries per query the scratch is sized for
     uint32_t* d_bhist = nullptr;      // [batch_pad][kBatchHistBins]
     float* d_binvq = nullptr;         // [batch_pad]
     CUtensorMap map_rows, map_q;
@@ -246,7 +247,7 @@ static cudaError_t init_kernel_attributes() {
     if (e == cudaSuccess) e = allow_smem(finalize_kernel<true>, fin_cap);
     if (e == cudaSuccess) e = allow_smem(batch_mma_kernel<false>, 212 * 1024);
     if (e == cudaSuccess) e = allow_smem(batch_mma_kernel<true>, 212 * 1024);
-    if (e == cudaSuccess) e = allow_smem(batch_tighten_kernel, kBatchCap * sizeof(u64));
+    if (e == cudaSuccess) e = allow_smem(batch_tighten_kernel, kBatchCapLarge * sizeof(u64));
     if (e == cudaSuccess) e = allow_smem(finalize_exact_kernel, fin_cap);
     return e;
 }
@@ -565,29 +566,36 @@ static int make_u8_map(CUtensorMap* m, void* base, uint64_t rows, uint32_t pitch
     return PBX_OK;
 }
 
+// Candidate buffer entries per query and the size of the flood round (round 0: every score is kept) for a given keep.
+static uint32_t batch_cap_for(uint32_t keep) { return keep * 8u <= kBatchCap ? kBatchCap : kBatchCapLarge; }
+static uint32_t batch_flood_tiles(uint32_t keep) { return std::max<uint32_t>(16u, (2u * keep + kBatchTileRows - 1) / kBatchTileRows); }
+
 static bool batch_eligible(const pbx_corpus* c, uint32_t nq, uint32_t n, uint32_t k) {
     // per-query candidate buffers hold kBatchCap keys and are cut back to keep = k + slack between rounds: the scheme
     // needs keep well below the capacity, larger k loops over the single-query scan
     const uint32_t keep = default_keep(k, c->slack);
-    return nq >= c->batch_min && c->pitch % 128 == 0 && c->pitch <= 1024 && n >= 16u * kBatchTileRows && keep * 8u <= kBatchCap;
+    return nq >= c->batch_min && c->pitch % 128 == 0 && c->pitch <= 1024 && keep * 8u <= kBatchCapLarge && n >= batch_flood_tiles(keep) * kBatchTileRows;
 }
 
-static int ensure_batch_scratch(pbx_corpus* c, uint32_t nq_pad) {
-    if (nq_pad <= c->batch_pad) return PBX_OK;
+static int ensure_batch_scratch(pbx_corpus* c, uint32_t nq_pad, uint32_t cap) {
+    if (nq_pad <= c->batch_pad && cap <= c->batch_cap) return PBX_OK;
+    nq_pad = std::max(nq_pad, c->batch_pad);
+    cap = std::max(cap, c->batch_cap);
     CU_TRY(cudaDeviceSynchronize());
     cudaFree(c->d_qpad); cudaFree(c->d_colterm); cudaFree(c->d_thr); cudaFree(c->d_bcnt); cudaFree(c->d_boverflow); cudaFree(c->d_bcand);
     cudaFree(c->d_bhist); cudaFree(c->d_binvq); c->d_bhist = nullptr; c->d_binvq = nullptr;
     c->d_qpad = nullptr; c->d_colterm = nullptr; c->d_thr = nullptr; c->d_bcnt = nullptr; c->d_boverflow = nullptr; c->d_bcand = nullptr;
-    c->batch_pad = 0; c->map_q_pad = 0;
+    c->batch_pad = 0; c->map_q_pad = 0; c->batch_cap = 0;
     CU_TRY(cudaMalloc(&c->d_qpad, (size_t)nq_pad * c->pitch));
     CU_TRY(cudaMalloc(&c->d_colterm, (size_t)nq_pad * sizeof(int)));
     CU_TRY(cudaMalloc(&c->d_thr, (size_t)nq_pad * sizeof(float)));
     CU_TRY(cudaMalloc(&c->d_bcnt, (size_t)nq_pad * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&c->d_boverflow, (size_t)nq_pad * sizeof(uint32_t)));
-    CU_TRY(cudaMalloc(&c->d_bcand, (size_t)nq_pad * kBatchCap * sizeof(u64)));
+    CU_TRY(cudaMalloc(&c->d_bcand, (size_t)nq_pad * cap * sizeof(u64)));
     CU_TRY(cudaMalloc(&c->d_bhist, (size_t)nq_pad * kBatchHistBins * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&c->d_binvq, (size_t)nq_pad * sizeof(float)));
     c->batch_pad = nq_pad;
+    c->batch_cap = cap;
     return PBX_OK;
 }
 
@@ -605,7 +613,9 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
     const uint32_t nmma = qg < 256 ? qg : 256;
     int rc = ensure_query_scratch(c, nq);
     if (rc != PBX_OK) return rc;
-    rc = ensure_batch_scratch(c, nq_pad);
+    const uint32_t keep = std::min<uint32_t>(default_keep(k, c->slack), kMaxKeep);
+    const uint32_t cap = batch_cap_for(keep);
+    rc = ensure_batch_scratch(c, nq_pad, cap);
     if (rc != PBX_OK) return rc;
     if (c->map_rows_gen != c->rows_generation) {
         rc = make_u8_map(&c->map_rows, c->d_rows, c->capacity, pitch, kBatchTileRows);
@@ -618,7 +628,6 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
         c->map_q_pad = c->batch_pad; c->map_q_box = nmma;
     }
     const int grid_scan = scan_grid(c);
-    const uint32_t keep = std::min<uint32_t>(default_keep(k, c->slack), kMaxKeep);
     rc = ensure_cand(c, (size_t)std::max<uint32_t>(keep, k) * grid_scan * sizeof(KeyX));      // exact-pass scratch
     if (rc != PBX_OK) return rc;
 
@@ -627,7 +636,8 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
     bp.qpad = c->d_qpad; bp.q16 = c->d_q16; bp.qbytes = c->d_qbytes; bp.qh = c->d_qh;
     bp.colterm = c->d_colterm; bp.thr = c->d_thr; bp.cand_cnt = c->d_bcnt; bp.overflow = c->d_boverflow;
     bp.bhist = c->d_bhist; bp.inv_q = c->d_binvq;
-    bp.flood_rows = std::min<uint32_t>(n, 16u * kBatchTileRows);          // round 0 below
+    const uint32_t flood_tiles = batch_flood_tiles(keep);                   // round 0 below: at least 2 * keep rows
+    bp.flood_rows = std::min<uint32_t>(n, flood_tiles * kBatchTileRows);
     batch_prep_kernel<<<nq_pad, 128, 0, s>>>(bp);
     CU_TRY(cudaGetLastError());
 
@@ -635,7 +645,7 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
     mp.map_rows = c->map_rows; mp.map_q = c->map_q;
     mp.inv_norm = c->d_inv; mp.row_sum = c->d_rsum; mp.colterm = c->d_colterm; mp.thr = c->d_thr;
     mp.cand = c->d_bcand; mp.cand_cnt = c->d_bcnt; mp.overflow = c->d_boverflow;
-    mp.bhist = c->d_bhist; mp.inv_q = c->d_binvq; mp.thr_live = c->d_thr; mp.keep = keep;
+    mp.bhist = c->d_bhist; mp.inv_q = c->d_binvq; mp.thr_live = c->d_thr; mp.keep = keep; mp.cap = cap;
     mp.n = n; mp.dim = c->dim; mp.kc = kc; mp.qg = qg; mp.groups = groups;
     const int grid = std::max<int>((int)groups, (c->sm_count / (int)groups) * (int)groups);
     const size_t mma_fixed = (size_t)qg * pitch + (size_t)qg * 20 + (size_t)kBatchEpiWarps * 128 * 4 + 1024;
@@ -643,27 +653,28 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
     const size_t mma_smem = mma_fixed + (size_t)stages * kBatchTileRows * 128;
     mp.stages = stages;
     BatchTightenParams tp;
-    tp.cand = c->d_bcand; tp.cand_cnt = c->d_bcnt; tp.thr = c->d_thr; tp.keep = keep; tp.nq = nq;
+    tp.cand = c->d_bcand; tp.cand_cnt = c->d_bcnt; tp.thr = c->d_thr; tp.keep = keep; tp.nq = nq; tp.cap = cap;
 
-    // rounds over geometrically growing row ranges: round 0 floods (threshold -inf) 16 tiles = 2048 candidates per
-    // query; afterwards the threshold is the keep-th best of everything seen, so a round over 8x the rows seen adds
-    // about 8 * keep candidates -- the buffers (kBatchCap entries) are cut back to keep between rounds
+    // Rounds over geometrically growing row ranges.  Round 0 has no thresholds: the flood variant keeps every score of
+    // its >= 2 * keep rows (slot = row).  Afterwards a query's threshold is the keep-th best of everything seen, so a
+    // round over g times the rows seen so far adds about g * keep candidates before any tightening; the buffers hold
+    // `cap`, so g = cap / (4 keep) + 1 leaves a wide margin, and they are cut back to keep between rounds.  Inside long
+    // rounds the thresholds also tighten from per-query histograms, which is what keeps the last rounds cheap.
     const uint32_t tiles = (n + kBatchTileRows - 1) / kBatchTileRows;
-    // A round over g times the rows seen so far adds about g * keep candidates per query before any tightening; the
-    // buffers hold kBatchCap, so g = cap / (4 keep) + 1 leaves a wide margin.  Inside long rounds the thresholds also
-    // tighten from per-query histograms, which is what keeps the last rounds cheap.
-    const uint32_t grow = std::max<uint32_t>(2u, kBatchCap / (4u * std::max<uint32_t>(keep, 1u))) + 1u;
-    uint32_t begin = 0, end = std::min<uint32_t>(tiles, 16u);
+    const uint32_t grow = std::max<uint32_t>(2u, cap / (4u * std::max<uint32_t>(keep, 1u))) + 1u;
+    uint32_t begin = 0, end = std::min<uint32_t>(tiles, flood_tiles);
     while (begin < tiles) {
         mp.tile_begin = begin; mp.tile_end = end;
-        // round 0 runs the flood variant: thresholds are -inf, every score is a candidate and its slot is its row
         if (begin == 0) batch_mma_kernel<true><<<grid, kBatchThreads, mma_smem, s>>>(mp);
         else batch_mma_kernel<false><<<grid, kBatchThreads, mma_smem, s>>>(mp);
         CU_TRY(cudaGetLastError());
         begin = end;
-        if (begin < tiles) {
-            batch_tighten_kernel<<<nq, 256, kBatchCap * sizeof(u64), s>>>(tp);
+        // the large buffers do not fit the finalize kernel's shared memory: cut them back after the last round too
+        if (begin < tiles || cap > kBatchCap) {
+            batch_tighten_kernel<<<nq, 256, (size_t)cap * sizeof(u64), s>>>(tp);
             CU_TRY(cudaGetLastError());
+        }
+        if (begin < tiles) {
             const uint64_t next = (uint64_t)end + (uint64_t)end * grow;
             end = (uint32_t)std::min<uint64_t>(tiles, next);
         }
@@ -671,7 +682,7 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
 
     // per-query finalize: cut to keep, bit-exact re-rank, certificate; exact passes are tail-launched by its last CTA
     const uint32_t chunk = kFinalThreads;
-    const uint32_t cap_merge = std::max<uint32_t>(next_pow2(keep + chunk), kBatchCap);
+    const uint32_t cap_merge = std::max<uint32_t>(next_pow2(keep + chunk), kBatchCap);     // >= candidates left per query
     const size_t off_sorted = (size_t)cap_merge * sizeof(u64);
     const size_t off_dots = 2 * off_sorted;
     const size_t off_q = (off_dots + (size_t)keep * 20 + 15) & ~(size_t)15;
@@ -694,7 +705,7 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
     fp.hits = d_hits; fp.count = d_count; fp.status = c->d_status; fp.tile_counter = c->d_tile_counter;
     fp.hist = c->d_hist; fp.cand = nullptr; fp.cand_cnt = nullptr;
     fp.bcand = c->d_bcand; fp.bcnt = c->d_bcnt; fp.boverflow = c->d_boverflow; fp.bticket = c->d_tile_counter + 100;
-    fp.bcap = kBatchCap; fp.nq = nq;
+    fp.bcap = cap; fp.nq = nq;
     // exact-pass template (query 0); the launching CTA offsets the per-query pointers
     ScanParams spx;
     memset(&spx, 0, sizeof(spx));

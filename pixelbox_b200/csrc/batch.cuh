@@ -35,7 +35,8 @@ constexpr int kBatchMaxStages = 8;           // corpus K-chunk ring: up to 8 x 1
 constexpr int kBatchTileRows = 128;          // UMMA M
 constexpr int kBatchAccStages = 4;           // TMEM: 4 accumulators of 128 rows x 128 queries (512 columns), a ring between MMA and epilogue
 constexpr uint32_t kBatchAccCols = 128;      // UMMA N
-constexpr uint32_t kBatchCap = 4096;         // candidate buffer entries per query
+constexpr uint32_t kBatchCap = 4096;         // candidate buffer entries per query (small k)
+constexpr uint32_t kBatchCapLarge = 16384;   // ... for keep > 512 (k = 1000 class)
 constexpr uint32_t kBatchQueryBytes = 128 * 1024;   // resident queries per CTA
 constexpr uint32_t kBatchHistBins = 256;            // per-query histogram of accepted keys over kappa in [-1, 1]
 
@@ -158,13 +159,14 @@ struct BatchMmaParams {
     const int* row_sum;
     const int* colterm;         // [nq_pad]
     const float* thr;           // [nq_pad] thresholds on kappa' for this round
-    u64* cand;                  // [nq_pad][kBatchCap]
+    u64* cand;                  // [nq_pad][cap]
     uint32_t* cand_cnt;         // [nq_pad]
     uint32_t* overflow;         // [nq_pad]
     uint32_t* bhist;            // [nq_pad][kBatchHistBins] accepted keys per query and kappa bin (in-round tightening)
     const float* inv_q;         // [nq_pad] 1 / |c(q)|  (0 for padding queries)
     float* thr_live;            // == thr, written: thresholds tightened while the round runs
     uint32_t keep;
+    uint32_t cap;               // candidate buffer entries per query
     uint32_t n;                 // rows visible to this search
     uint32_t dim;
     uint32_t kc;                // K-chunks of 128 bytes per row (pitch / 128)
@@ -299,7 +301,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                     const uint32_t qi = my_q[e];
                     const u64 key = my_key[e];
                     const uint32_t slot = atomicAdd(p.cand_cnt + qi, 1u);
-                    if (slot < kBatchCap) p.cand[(size_t)qi * kBatchCap + slot] = key;
+                    if (slot < p.cap) p.cand[(size_t)qi * p.cap + slot] = key;
                     else p.overflow[qi] = 1u;
                     // every accepted key is counted once in its query's kappa histogram
                     const float kap = __fmul_rn(key64_kappa(key), p.inv_q[qi]);
@@ -424,7 +426,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                             const uint32_t col = colbase + (uint32_t)i;
                             const int dot_i = 4 * (int)r[i] + rowterm + s_colterm[col];
                             const float kf = __fmul_rn((float)dot_i, inv_r);
-                            if (row_ok && s_invq[col] > 0.0f) p.cand[(size_t)(g * QG + col) * kBatchCap + row] = make_key64(kf, row);
+                            if (row_ok && s_invq[col] > 0.0f) p.cand[(size_t)(g * QG + col) * p.cap + row] = make_key64(kf, row);
                         }
                         continue;
                     }
@@ -501,23 +503,24 @@ struct BatchTightenParams {
     float* thr;
     uint32_t keep;
     uint32_t nq;
+    uint32_t cap;               // candidate buffer entries per query
 };
 
 __global__ void __launch_bounds__(256)
 batch_tighten_kernel(const BatchTightenParams p) {
     extern __shared__ __align__(16) unsigned char tsm[];
-    u64* buf = reinterpret_cast<u64*>(tsm);              // [kBatchCap]
+    u64* buf = reinterpret_cast<u64*>(tsm);              // [cap]
     __shared__ uint32_t s_cnt;
     __shared__ u64 s_tau;
     __shared__ SelectScratch sel;
     const uint32_t q = blockIdx.x;
-    const uint32_t c = min(p.cand_cnt[q], kBatchCap);
+    const uint32_t c = min(p.cand_cnt[q], p.cap);
     if (c <= p.keep) return;                             // nothing to cut: the threshold stays where it is
-    u64* src = p.cand + (size_t)q * kBatchCap;
+    u64* src = p.cand + (size_t)q * p.cap;
     for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) buf[i] = src[i];
     if (threadIdx.x == 0) { s_cnt = c; s_tau = 0; }
     __syncthreads();
-    TopBuf<u64> tb{buf, &s_cnt, &s_tau, kBatchCap, p.keep};
+    TopBuf<u64> tb{buf, &s_cnt, &s_tau, p.cap, p.keep};
     block_select_top(tb, &sel);
     const uint32_t kept = s_cnt;
     for (uint32_t i = threadIdx.x; i < kept; i += blockDim.x) src[i] = buf[i];

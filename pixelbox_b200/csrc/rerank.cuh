@@ -394,7 +394,7 @@ finalize_kernel(const FinalizeParams p) {
     } else {
         // ---- 1 (batched). this query's candidate buffer: kappa' -> kappa, cut to `keep`, order ---------------
         __syncthreads();
-        const uint32_t c = min(p.bcnt[q], p.bcap);
+        const uint32_t c = min(min(p.bcnt[q], p.bcap), p.cap);       // p.cap: what this kernel's shared buffers hold
         const float inv_q = qh_g->inv_q;
         const u64* src = p.bcand + (size_t)q * p.bcap;
         for (uint32_t i = tid; i < c; i += blockDim.x) {

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle
+from pixelbox_b200 import synth
 from pixelbox_b200.corpus import Corpus
 
 pytestmark = pytest.mark.gpu
@@ -59,8 +60,27 @@ def test_batched_with_ties_filters_and_small_k():
     queries = np.concatenate([corpus[[1000, 1001, 5, 77_777]], rng.integers(0, 256, size=(28, d), dtype=np.uint8)])
     with Corpus(d) as c:
         c.load(ids, corpus)
-        for k, md in ((100, 1e3), (10, 1e3), (300, 0.05), (100, 1e7), (1000, 1e3)):
+        for k, md in ((100, 1e3), (10, 1e3), (300, 0.05), (100, 1e7), (1000, 1e3), (2048, 1e3)):
             check(corpus, ids, queries, k, md, c)
         st = c.stats()
-        # k = 1000 is answered by the single-query loop (its candidate set would not fit the per-query buffers)
-        assert st.batched_queries == 4 * len(queries) and st.exact_passes > 0
+        # k = 1000 runs on the tensor cores with the large candidate buffers (16384 entries per query); k = 2048
+        # (keep * 8 > 16384) is answered by the single-query loop
+        assert st.batched_queries == 5 * len(queries) and st.exact_passes > 0
+
+
+def test_batched_k1000_large_buffers_on_a_bigger_corpus():
+    """keep = 1280: flood round of 20 tiles, candidate buffers of 16384 entries, cut back after the last round too."""
+    n, d, nq, k = 600_000, 256, 40, 1000
+    corpus = synth.synth_rows(21, 0, n, d)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    queries = synth.synth_queries(22, nq, d, n, 21)
+    with Corpus(d) as c:
+        c.load(ids, corpus)
+        before = c.stats().batched_queries
+        got = c.search(queries, k)
+        assert c.stats().batched_queries == before + nq, "the tensor-core path did not run"
+        for qi in range(0, nq, 7):
+            o_ids, o_dist, o_dot, o_n2 = oracle.topk(corpus, ids, queries[qi], k, 1e3, threads=oracle.max_threads())
+            assert list(got[qi].ids) == list(o_ids), qi
+            assert np.array_equal(np.asarray(got[qi].dist).view(np.uint32), o_dist.view(np.uint32)), qi
+            assert np.array_equal(got[qi].dot, o_dot) and np.array_equal(got[qi].norm2, o_n2)
