@@ -669,11 +669,10 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
         else batch_mma_kernel<false><<<grid, kBatchThreads, mma_smem, s>>>(mp);
         CU_TRY(cudaGetLastError());
         begin = end;
-        // the large buffers do not fit the finalize kernel's shared memory: cut them back after the last round too
-        if (begin < tiles || cap > kBatchCap) {
-            batch_tighten_kernel<<<nq, 256, (size_t)cap * sizeof(u64), s>>>(tp);
-            CU_TRY(cudaGetLastError());
-        }
+        // also after the last round: the large buffers would not fit the finalize kernel's shared memory, and for the
+        // small ones the cut is cheaper here (256-thread CTAs, several per SM) than in the finalize kernel (one per SM)
+        batch_tighten_kernel<<<nq, 256, (size_t)cap * sizeof(u64), s>>>(tp);
+        CU_TRY(cudaGetLastError());
         if (begin < tiles) {
             const uint64_t next = (uint64_t)end + (uint64_t)end * grow;
             end = (uint32_t)std::min<uint64_t>(tiles, next);
