@@ -1,9 +1,11 @@
 """ShardedCorpus: the `semantic_hashes` table row-sharded over the GPUs of one box.
 
 One process per GPU (torch.distributed); every rank owns one Corpus shard, answers each query
-over its rows and contributes its k best records; ONE all-gather of those records (NCCL over
-NVLink on GPUs) is the only exchange step of the path, followed by a merge under the
-reference's order (dist asc, image_id asc) on every rank.
+over its rows and contributes its k best records; ONE all-gather of those records is the only
+exchange step of the path, followed by a merge under the reference's order (dist asc, image_id
+asc) on every rank.  On GPUs the exchange and the merge are one kernel
+over NVLink peer memory (pbx_exchange_*: CUDA IPC mailboxes, release/acquire flags); NCCL
+all_gather_into_tensor + pbx_merge_hits_device is the fallback, gloo + pbx_merge_hits the CPU test path.
 
 torch is plumbing here (process group, device buffers, streams); the search, the records and
 both merge implementations are the C-ABI library's.
@@ -122,8 +124,9 @@ class ShardedCorpus:
 
     def search_device(self, d_queries: torch.Tensor, nq: int, k: int, max_dist: float = nat.DEFAULT_MAX_DIST):
         """Device-resident sharded search on the current torch stream, no host synchronisation:
-        local scan -> NCCL all-gather of the [nq][k] records -> device merge.  Returns (hits, counts)
-        device tensors (uint8 view of pbx_hit records, int32)."""
+        local search -> exchange of the [nq][k] records + merge (one kernel over peer memory, or NCCL
+        all-gather + merge kernel).  Returns (hits, counts) device tensors (uint8 view of pbx_hit
+        records, int32)."""
         assert self.on_gpu
         b = self._buffers(nq, k)
         stream = torch.cuda.current_stream().cuda_stream
