@@ -238,6 +238,11 @@ static cudaError_t init_kernel_attributes() {
     if (e == cudaSuccess) e = allow_smem(scan_kernel<LL, CC, true>, scan_cap);
     PBX_ALLOW(1, 1) PBX_ALLOW(2, 1) PBX_ALLOW(4, 1) PBX_ALLOW(8, 1) PBX_ALLOW(16, 1) PBX_ALLOW(32, 1) PBX_ALLOW(32, 2) PBX_ALLOW(32, 4)
 #undef PBX_ALLOW
+#define PBX_ALLOW_M(LL, CC, MM)                                                        \
+    if (e == cudaSuccess) e = allow_smem(scan_kernel<LL, CC, false, MM>, scan_cap);    \
+    if (e == cudaSuccess) e = allow_smem(scan_kernel<LL, CC, true, MM>, scan_cap);
+    PBX_EXTRA_SHAPES(PBX_ALLOW_M)
+#undef PBX_ALLOW_M
     if (e == cudaSuccess) e = allow_smem(scan_kernel<16, 1, false, 3>, scan_cap);
     if (e == cudaSuccess) e = allow_smem(scan_kernel<16, 1, false, 4>, scan_cap);
     if (e == cudaSuccess) e = allow_smem(scan_generic_kernel<false>, scan_cap);
@@ -520,6 +525,9 @@ static cudaError_t launch_scan(const pbx_corpus* c, const ScanParams& p, int gri
         case 32: PBX_SCAN_CASE(32, 1)
         case 64: PBX_SCAN_CASE(32, 2)
         case 128: PBX_SCAN_CASE(32, 4)
+#define PBX_SCAN_CASE_M(LL, CC, MM) case (LL) * (CC): return launch_pdl<ScanParams>(scan_kernel<LL, CC, EXACT, MM>, grid, kScanThreads, smem, s, p);
+        PBX_EXTRA_SHAPES(PBX_SCAN_CASE_M)
+#undef PBX_SCAN_CASE_M
         default: {
             size_t sm = smem + (size_t)c->pitch16 * 32;
             return launch_pdl<ScanParams>(scan_generic_kernel<EXACT>, grid, kScanThreads, sm, s, p);
@@ -530,7 +538,11 @@ static cudaError_t launch_scan(const pbx_corpus* c, const ScanParams& p, int gri
 
 static int scan_grid(const pbx_corpus* c) {
     // 3 CTAs per SM (<= 80 registers) measured best for 256-byte rows; larger rows need the registers, smaller ones fit 4
-    uint32_t per_sm = c->ctas_per_sm ? c->ctas_per_sm : ((c->pitch16 == 16) ? 3u : (c->pitch16 > 16) ? 2u : 4u);
+    const bool pow2 = (c->pitch16 & (c->pitch16 - 1)) == 0;
+    uint32_t per_sm = c->ctas_per_sm ? c->ctas_per_sm
+                      : c->pitch16 >= 256          ? 1u      // 32 lanes x 8 chunks: one CTA per SM has the registers
+                      : !pow2                      ? 2u      // the x3 / x5 / x6 shapes are built for two
+                      : (c->pitch16 == 16) ? 3u : (c->pitch16 > 16) ? 2u : 4u;
     int g = c->sm_count * (int)per_sm;
     return std::min<int>(g, (int)kMaxScanGrid);
 }
@@ -597,6 +609,18 @@ static int ensure_batch_scratch(pbx_corpus* c, uint32_t nq_pad, uint32_t cap) {
     c->batch_pad = nq_pad;
     c->batch_cap = cap;
     return PBX_OK;
+}
+
+// Staging layout of the finalize kernel: groups of up to kFinalThreads candidates, `slice16` 16-byte chunks of every
+// row of the group per round (row stride slice16 * 16 + 16 bytes).  Returns false if not even one chunk fits.
+static bool finalize_stage_layout(size_t avail_bytes, uint32_t keep, uint32_t pitch16, uint32_t* group, uint32_t* slice16, size_t* bytes) {
+    uint32_t g = std::min<uint32_t>(keep, (uint32_t)kFinalThreads);
+    if (g == 0) g = 1;
+    while (g > 32 && avail_bytes / g < 32) g /= 2;
+    if (avail_bytes / g < 32) return false;
+    const uint32_t s16 = (uint32_t)std::min<size_t>(pitch16, (avail_bytes / g - 16) / 16);
+    *group = g; *slice16 = s16; *bytes = (size_t)g * ((size_t)s16 * 16 + 16);
+    return s16 >= 1;
 }
 
 // Enqueues the tensor-core search of nq (<= 1024) device-resident queries.  Caller holds c->mu.
@@ -687,17 +711,18 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
     const size_t off_q = (off_dots + (size_t)keep * 20 + 15) & ~(size_t)15;
     const size_t off_stage = (off_q + (size_t)pitch * 6 + 15) & ~(size_t)15;
     const size_t fin_budget = 200 * 1024;
-    const size_t srow = (size_t)pitch + 16;
-    if (off_stage + srow > fin_budget) return fail(PBX_E_INTERNAL, "finalize layout does not fit shared memory (k=%u dim=%u)", k, c->dim);
-    const uint32_t stage_rows = (uint32_t)std::min<size_t>(keep, (fin_budget - off_stage) / srow);
-    const size_t fin_smem = off_stage + (size_t)stage_rows * srow;
+    uint32_t stage_rows = 0, slice16 = 0;
+    size_t stage_bytes = 0;
+    if (off_stage >= fin_budget || !finalize_stage_layout(fin_budget - off_stage, keep, pitch / 16, &stage_rows, &slice16, &stage_bytes))
+        return fail(PBX_E_INTERNAL, "finalize layout does not fit shared memory (k=%u dim=%u)", k, c->dim);
+    const size_t fin_smem = off_stage + stage_bytes;
     const uint32_t cap_scan_x = next_pow2(k + kTileRows);
     const uint32_t cap_merge_x = next_pow2(k + kMergeChunk);
 
     FinalizeParams fp;
     memset(&fp, 0, sizeof(fp));
     fp.grid = (uint32_t)grid_scan; fp.keep = keep; fp.cap = cap_merge; fp.chunk = chunk; fp.k = k; fp.n = n;
-    fp.dim = c->dim; fp.pitch = pitch; fp.stage_rows = stage_rows;
+    fp.dim = c->dim; fp.pitch = pitch; fp.stage_rows = stage_rows; fp.slice16 = slice16;
     fp.off_sorted = (uint32_t)off_sorted; fp.off_ent = 0; fp.off_dots = (uint32_t)off_dots; fp.off_q = (uint32_t)off_q; fp.off_stage = (uint32_t)off_stage;
     fp.rows = c->d_rows; fp.ids = c->d_ids; fp.qbytes = c->d_qbytes; fp.q16 = c->d_q16; fp.qh = c->d_qh;
     fp.max_dist = max_dist; fp.margin = certificate_margin(c->dim);
@@ -766,10 +791,11 @@ static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, 
         const size_t off_q = (off_dots + (size_t)keep * 20 + 15) & ~(size_t)15;
         const size_t off_stage = (off_q + (size_t)c->pitch * 6 + 15) & ~(size_t)15;
         const size_t fin_budget = 200 * 1024;
-        const size_t srow = (size_t)c->pitch + 16;
-        if (off_stage + srow > fin_budget) return fail(PBX_E_INTERNAL, "finalize layout does not fit shared memory (k=%u dim=%u)", k, c->dim);
-        const uint32_t stage_rows = (uint32_t)std::min<size_t>(keep, (fin_budget - off_stage) / srow);
-        const size_t fin_smem = off_stage + (size_t)stage_rows * srow;
+        uint32_t stage_rows = 0, slice16 = 0;
+        size_t stage_bytes = 0;
+        if (off_stage >= fin_budget || !finalize_stage_layout(fin_budget - off_stage, keep, c->pitch16, &stage_rows, &slice16, &stage_bytes))
+            return fail(PBX_E_INTERNAL, "finalize layout does not fit shared memory (k=%u dim=%u)", k, c->dim);
+        const size_t fin_smem = off_stage + stage_bytes;
         const size_t finx_smem = (size_t)cap_merge_x * sizeof(KeyX);
 
         for (uint32_t q = 0; q < nq; ++q) {
@@ -825,6 +851,7 @@ static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, 
             fp.chunk = chunk;
             fp.hist = c->d_hist;
             fp.stage_rows = stage_rows;
+            fp.slice16 = slice16;
             fp.off_sorted = (uint32_t)off_sorted;
             fp.off_ent = 0;
             fp.off_dots = (uint32_t)off_dots;

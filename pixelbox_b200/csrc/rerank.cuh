@@ -56,7 +56,8 @@ struct FinalizeParams {
     uint32_t n;                 // rows searched
     uint32_t dim;
     uint32_t pitch;             // bytes
-    uint32_t stage_rows;        // candidate rows staged in shared memory per batch
+    uint32_t stage_rows;        // candidates per staging group (<= kFinalThreads: one thread per candidate)
+    uint32_t slice16;           // 16-byte chunks of every candidate row staged per round
     uint32_t off_sorted;        // byte offsets into dynamic shared memory
     uint32_t off_ent, off_dots, off_q, off_stage;
     const uint8_t* rows;
@@ -156,6 +157,10 @@ __device__ inline void launch_exact_tail(const ExactLaunch& x) {
     switch (x.scan.pitch16) {
         PBX_X_CASE(1, 1) PBX_X_CASE(2, 1) PBX_X_CASE(4, 1) PBX_X_CASE(8, 1) PBX_X_CASE(16, 1) PBX_X_CASE(32, 1)
         PBX_X_CASE(32, 2) PBX_X_CASE(32, 4)
+#define PBX_X_CASE_M(LL, CC, MM) \
+    case (LL) * (CC): scan_kernel<LL, CC, true, MM><<<x.grid, kScanThreads, x.scan_smem, cudaStreamTailLaunch>>>(x.scan); break;
+        PBX_EXTRA_SHAPES(PBX_X_CASE_M)
+#undef PBX_X_CASE_M
         default:
             scan_generic_kernel<true><<<x.grid, kScanThreads, x.scan_smem + x.scan.pitch16 * 32, cudaStreamTailLaunch>>>(x.scan);
             break;
@@ -279,7 +284,7 @@ finalize_kernel(const FinalizeParams p) {
     float* fdots = sbs + p.keep;
     float* s_qa = reinterpret_cast<float*>(smem_raw + p.off_q);                    // [pitch] decoded query
     int16_t* s_q16 = reinterpret_cast<int16_t*>(smem_raw + p.off_q + 4 * p.pitch); // [pitch] centred query
-    unsigned char* stage = smem_raw + p.off_stage;                                 // [stage_rows][pitch + 16]
+    unsigned char* stage = smem_raw + p.off_stage;                                 // [stage_rows][slice16 * 16 + 16]
 
     __shared__ uint32_t s_cnt, s_pushed, s_maxcnt, s_nonplateau, s_bstar, s_mprime, s_total, s_odlo, s_odhi;
     __shared__ u64 s_tau;
@@ -420,69 +425,80 @@ finalize_kernel(const FinalizeParams p) {
         s_sa = sa;
         qh_g->sa = sa;
     }
-    const uint32_t pitch16 = p.pitch / 16, srow = p.pitch + 16;     // staged row stride: odd number of 16-byte units
+    // Candidate rows are staged in shared memory in COLUMN SLICES: every thread owns one candidate (groups of up to
+    // 1024) and carries its five partial sums in registers from slice to slice, so all candidates advance together
+    // whatever the row length.  (Staging whole rows would serialise the strictly sequential f32 folds of a long row
+    // over a handful of rows at a time: 8 rounds of 45 rows at dim 4096.)
+    const uint32_t pitch16 = p.pitch / 16, slice16 = p.slice16, srow = slice16 * 16 + 16;   // stride: odd number of 16-byte units
     const uint32_t full = p.dim >> 4;
     const int sum_cq = qh_g->sum_cq;
+    constexpr uint32_t kStageBatch = 6;
     for (uint32_t c0 = 0; c0 < nc; c0 += p.stage_rows) {
-        const uint32_t cb = min(p.stage_rows, nc - c0);
-        constexpr uint32_t kStageBatch = 6;
-        // all threads: one 16-byte load per (candidate, chunk), kStageBatch of them in flight per thread before the first
-        // store (a load -> store loop keeps ONE in flight: the candidates are random rows, every load is a DRAM + TLB miss)
-        const uint32_t total16 = cb * pitch16;
-        for (uint32_t e0 = tid; e0 < total16; e0 += kStageBatch * blockDim.x) {
-            uint4 v[kStageBatch];
+        const uint32_t cb = min(p.stage_rows, nc - c0);                // <= blockDim.x
+        float s = 0.0f, d = 0.0f;
+        int acc = 0;
+        unsigned s1 = 0, s2 = 0;
+        for (uint32_t ch0 = 0; ch0 < pitch16; ch0 += slice16) {
+            const uint32_t w16 = min(slice16, pitch16 - ch0);
+            // all threads: one 16-byte load per (candidate, chunk of the slice), kStageBatch of them in flight per thread
+            // before the first store (a load -> store loop keeps ONE in flight: the candidates are random rows, every
+            // load is a DRAM + TLB miss)
+            const uint32_t total16 = cb * w16;
+            for (uint32_t e0 = tid; e0 < total16; e0 += kStageBatch * blockDim.x) {
+                uint4 v[kStageBatch];
 #pragma unroll
-            for (uint32_t u = 0; u < kStageBatch; ++u) {
-                const uint32_t e = e0 + u * blockDim.x;
-                if (e < total16) {
-                    const uint32_t ci = e / pitch16, ch = e - ci * pitch16;
-                    const uint32_t row = key64_row(sorted[c0 + ci]);
-                    v[u] = __ldg(reinterpret_cast<const uint4*>(p.rows + (size_t)row * p.pitch) + ch);
-                }
-            }
-#pragma unroll
-            for (uint32_t u = 0; u < kStageBatch; ++u) {
-                const uint32_t e = e0 + u * blockDim.x;
-                if (e < total16) {
-                    const uint32_t ci = e / pitch16, ch = e - ci * pitch16;
-                    *reinterpret_cast<uint4*>(stage + (size_t)ci * srow + 16 * ch) = v[u];
-                }
-            }
-        }
-        __syncthreads();
-        PBX_FIN_STAMP(5);
-        for (uint32_t ci = tid; ci < cb; ci += blockDim.x) {
-            const unsigned char* r = stage + (size_t)ci * srow;
-            float s = 0.0f, d = 0.0f;
-            int acc = 0;
-            unsigned s1 = 0, s2 = 0;
-            for (uint32_t ch = 0; ch < pitch16; ++ch) {
-                const uint4 v = *reinterpret_cast<const uint4*>(r + 16 * ch);
-                if (ch < full) {
-                    fold16(v, s_qa + 16 * ch, s_lut, s, d);
-                } else {                                            // ragged tail: dim is not a multiple of 16
-                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                    for (uint32_t i = 16 * ch; i < p.dim; ++i) {
-                        const uint32_t o = i - 16 * ch;
-                        const float fb = s_lut[(w[o >> 2] >> (8 * (o & 3))) & 255u];
-                        s = ref_fold(s, fb, fb);
-                        d = ref_fold(d, s_qa[i], fb);
+                for (uint32_t u = 0; u < kStageBatch; ++u) {
+                    const uint32_t e = e0 + u * blockDim.x;
+                    if (e < total16) {
+                        const uint32_t ci = e / w16, ch = e - ci * w16;
+                        const uint32_t row = key64_row(sorted[c0 + ci]);
+                        v[u] = __ldg(reinterpret_cast<const uint4*>(p.rows + (size_t)row * p.pitch) + ch0 + ch);
                     }
                 }
-                const int4 a = *reinterpret_cast<const int4*>(s_q16 + 16 * ch), b = *reinterpret_cast<const int4*>(s_q16 + 16 * ch + 8);
-                const int qq[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-                acc = dot16(v, qq, acc);
-                s1 = dp4a_uu(v.x, 0x01010101u, s1); s1 = dp4a_uu(v.y, 0x01010101u, s1);
-                s1 = dp4a_uu(v.z, 0x01010101u, s1); s1 = dp4a_uu(v.w, 0x01010101u, s1);
-                s2 = dp4a_uu(v.x, v.x, s2); s2 = dp4a_uu(v.y, v.y, s2);
-                s2 = dp4a_uu(v.z, v.z, s2); s2 = dp4a_uu(v.w, v.w, s2);
+#pragma unroll
+                for (uint32_t u = 0; u < kStageBatch; ++u) {
+                    const uint32_t e = e0 + u * blockDim.x;
+                    if (e < total16) {
+                        const uint32_t ci = e / w16, ch = e - ci * w16;
+                        *reinterpret_cast<uint4*>(stage + (size_t)ci * srow + 16 * ch) = v[u];
+                    }
+                }
             }
-            sbs[c0 + ci] = s;
-            fdots[c0 + ci] = d;
-            dots[c0 + ci] = 2 * acc - 255 * sum_cq;
-            norms[c0 + ci] = (int)(4u * s2 - 1020u * s1 + 65025u * p.dim);
+            __syncthreads();
+            PBX_FIN_STAMP(5);
+            if (tid < cb) {
+                const unsigned char* r = stage + (size_t)tid * srow;
+                for (uint32_t cl = 0; cl < w16; ++cl) {
+                    const uint32_t ch = ch0 + cl;                       // chunk index within the row
+                    const uint4 v = *reinterpret_cast<const uint4*>(r + 16 * cl);
+                    if (ch < full) {
+                        fold16(v, s_qa + 16 * ch, s_lut, s, d);
+                    } else {                                            // ragged tail: dim is not a multiple of 16
+                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                        for (uint32_t i = 16 * ch; i < p.dim; ++i) {
+                            const uint32_t o = i - 16 * ch;
+                            const float fb = s_lut[(w[o >> 2] >> (8 * (o & 3))) & 255u];
+                            s = ref_fold(s, fb, fb);
+                            d = ref_fold(d, s_qa[i], fb);
+                        }
+                    }
+                    const int4 qa4 = *reinterpret_cast<const int4*>(s_q16 + 16 * ch), qb4 = *reinterpret_cast<const int4*>(s_q16 + 16 * ch + 8);
+                    const int qq[8] = {qa4.x, qa4.y, qa4.z, qa4.w, qb4.x, qb4.y, qb4.z, qb4.w};
+                    acc = dot16(v, qq, acc);
+                    s1 = dp4a_uu(v.x, 0x01010101u, s1); s1 = dp4a_uu(v.y, 0x01010101u, s1);
+                    s1 = dp4a_uu(v.z, 0x01010101u, s1); s1 = dp4a_uu(v.w, 0x01010101u, s1);
+                    s2 = dp4a_uu(v.x, v.x, s2); s2 = dp4a_uu(v.y, v.y, s2);
+                    s2 = dp4a_uu(v.z, v.z, s2); s2 = dp4a_uu(v.w, v.w, s2);
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
+        if (tid < cb) {
+            sbs[c0 + tid] = s;
+            fdots[c0 + tid] = d;
+            dots[c0 + tid] = 2 * acc - 255 * sum_cq;
+            norms[c0 + tid] = (int)(4u * s2 - 1020u * s1 + 65025u * p.dim);
+        }
     }
     __syncthreads();
     PBX_FIN_STAMP(6);

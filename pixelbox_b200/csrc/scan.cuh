@@ -448,3 +448,10 @@ scan_generic_kernel(const ScanParams p) {
 }
 
 }  // namespace pbx
+
+// Row pitches of 3, 5, 6 or 8 times a power of two (in 16-byte chunks): dims 48 ... 4096 such as 96, 192, 384, 768,
+// 1536 (x3), 80, 160, 320, 640, 1280, 2560 (x5), 3072 (x6), 4096 (x8).  X(lanes per row, chunks per lane, CTAs per SM).
+#define PBX_EXTRA_SHAPES(X)                                                                  \
+    X(1, 3, 2) X(2, 3, 2) X(4, 3, 2) X(8, 3, 2) X(16, 3, 2) X(32, 3, 2)                      \
+    X(1, 5, 2) X(2, 5, 2) X(4, 5, 2) X(8, 5, 2) X(16, 5, 2) X(32, 5, 2)                      \
+    X(32, 6, 2) X(32, 8, 1)
