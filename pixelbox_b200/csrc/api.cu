@@ -616,10 +616,11 @@ static int ensure_batch_scratch(pbx_corpus* c, uint32_t nq_pad, uint32_t cap) {
 static bool finalize_stage_layout(size_t avail_bytes, uint32_t keep, uint32_t pitch16, uint32_t* group, uint32_t* slice16, size_t* bytes) {
     uint32_t g = std::min<uint32_t>(keep, (uint32_t)kFinalThreads);
     if (g == 0) g = 1;
-    while (g > 32 && avail_bytes / g < 32) g /= 2;
-    if (avail_bytes / g < 32) return false;
-    const uint32_t s16 = (uint32_t)std::min<size_t>(pitch16, (avail_bytes / g - 16) / 16);
-    *group = g; *slice16 = s16; *bytes = (size_t)g * ((size_t)s16 * 16 + 16);
+    while (g > 32 && avail_bytes / g < 48) g /= 2;
+    // the row stride is (slice16 + 1) rounded up to an odd number of 16-byte units: reserve 32 bytes beyond the slice
+    if (avail_bytes / g < 48) return false;
+    const uint32_t s16 = (uint32_t)std::min<size_t>(pitch16, (avail_bytes / g - 32) / 16);
+    *group = g; *slice16 = s16; *bytes = (size_t)g * ((size_t)((s16 + 1) | 1u) * 16);
     return s16 >= 1;
 }
 

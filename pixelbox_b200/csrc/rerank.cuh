@@ -418,18 +418,33 @@ finalize_kernel(const FinalizeParams p) {
 
     PBX_FIN_STAMP(4);
     // ---- 2. kernel C ------------------------------------------------------------------------------------
-    // the query's own norm fold (src/engine.rs:580) by one thread of the last warp
-    if (tid == kFinalThreads - 1) {
-        float sa = 0.0f;
-        for (uint32_t i = 0; i < p.dim; ++i) { const float a = s_qa[i]; sa = ref_fold(sa, a, a); }
-        s_sa = sa;
-        qh_g->sa = sa;
+    // The query's own norm fold (src/engine.rs:580): the products in parallel (same rounding), the strictly sequential
+    // additions by one thread of the last warp, eight loads ahead of the 4-cycle add chain.  The squares live in `buf`,
+    // which is dead between the candidate selection and the sort records; nobody else waits for this thread before the
+    // first barrier of the staging loop.
+    {
+        float* sq = reinterpret_cast<float*>(buf);
+        for (uint32_t i = tid; i < p.dim; i += blockDim.x) { const float a = s_qa[i]; sq[i] = __fmul_rn(a, a); }
+        __syncthreads();
+        if (tid == kFinalThreads - 1) {
+            float sa = 0.0f;
+            uint32_t i = 0;
+            for (; i + 8 <= p.dim; i += 8) {
+                const float4 x = *reinterpret_cast<const float4*>(sq + i), y = *reinterpret_cast<const float4*>(sq + i + 4);
+                sa = __fadd_rn(sa, x.x); sa = __fadd_rn(sa, x.y); sa = __fadd_rn(sa, x.z); sa = __fadd_rn(sa, x.w);
+                sa = __fadd_rn(sa, y.x); sa = __fadd_rn(sa, y.y); sa = __fadd_rn(sa, y.z); sa = __fadd_rn(sa, y.w);
+            }
+            for (; i < p.dim; ++i) sa = __fadd_rn(sa, sq[i]);
+            s_sa = sa;
+            qh_g->sa = sa;
+        }
     }
     // Candidate rows are staged in shared memory in COLUMN SLICES: every thread owns one candidate (groups of up to
     // 1024) and carries its five partial sums in registers from slice to slice, so all candidates advance together
     // whatever the row length.  (Staging whole rows would serialise the strictly sequential f32 folds of a long row
     // over a handful of rows at a time: 8 rounds of 45 rows at dim 4096.)
-    const uint32_t pitch16 = p.pitch / 16, slice16 = p.slice16, srow = slice16 * 16 + 16;   // stride: odd number of 16-byte units
+    const uint32_t pitch16 = p.pitch / 16, slice16 = p.slice16;
+    const uint32_t srow = ((slice16 + 1) | 1u) * 16;            // row stride: an odd number of 16-byte units (no bank conflicts)
     const uint32_t full = p.dim >> 4;
     const int sum_cq = qh_g->sum_cq;
     constexpr uint32_t kStageBatch = 6;
