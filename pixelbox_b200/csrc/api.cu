@@ -68,6 +68,8 @@ struct pbx_corpus {
     uint8_t* d_qbytes = nullptr;
     QueryHeader* d_qh = nullptr;
     SearchStatus* d_status = nullptr;
+    unsigned char* d_split = nullptr;  // split finalize hand-over: keys[kMaxKeep] u64 | sbs, fdots, dots, norms [kMaxKeep] 4 B each | meta[4]
+    bool split_finalize = true;        // PBX_NO_SPLIT_FINALIZE=1 keeps the one-kernel finalize for every shape
     pbx_hit* d_hits = nullptr;
     size_t hits_cap = 0;
     // scan scratch
@@ -192,6 +194,7 @@ static int ensure_query_scratch(pbx_corpus* c, uint32_t nq) {
     CU_TRY(cudaMalloc(&c->d_qbytes, (size_t)want * c->pitch));
     CU_TRY(cudaMalloc(&c->d_qh, (size_t)want * sizeof(QueryHeader)));
     CU_TRY(cudaMalloc(&c->d_status, (size_t)want * sizeof(SearchStatus)));
+    if (!c->d_split) CU_TRY(cudaMalloc(&c->d_split, (size_t)kMaxKeep * 24 + 64));
     c->max_nq = want;
     return PBX_OK;
 }
@@ -249,6 +252,7 @@ static cudaError_t init_kernel_attributes() {
     if (e == cudaSuccess) e = allow_smem(scan_generic_kernel<true>, scan_cap);
     if (e == cudaSuccess) e = allow_smem(prep_seed_kernel, PBX_MAX_DIM * 2 + 1024);
     if (e == cudaSuccess) e = allow_smem(finalize_kernel<false>, fin_cap);
+    if (e == cudaSuccess) e = allow_smem(replay_kernel, (size_t)PBX_MAX_DIM * 6 + (size_t)kReplayRows * (kReplaySlice16 + 2) * 16);
     if (e == cudaSuccess) e = allow_smem(finalize_kernel<true>, fin_cap);
     if (e == cudaSuccess) e = allow_smem(batch_mma_kernel<false>, 212 * 1024);
     if (e == cudaSuccess) e = allow_smem(batch_mma_kernel<true>, 212 * 1024);
@@ -290,6 +294,7 @@ extern "C" int pbx_corpus_create(uint32_t dim, uint64_t capacity_hint, int devic
     if (!c) return fail(PBX_E_OOM, "host allocation failed");
     c->device = device;
     c->dim = dim;
+    c->split_finalize = getenv("PBX_NO_SPLIT_FINALIZE") == nullptr;
     c->pitch = (dim + 15u) & ~15u;
     c->pitch16 = c->pitch / 16u;
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -326,7 +331,7 @@ extern "C" void pbx_corpus_destroy(pbx_corpus* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     free_corpus_buffers(c);
-    cudaFree(c->d_queries); cudaFree(c->d_q16); cudaFree(c->d_qbytes); cudaFree(c->d_qh); cudaFree(c->d_status);
+    cudaFree(c->d_queries); cudaFree(c->d_q16); cudaFree(c->d_qbytes); cudaFree(c->d_qh); cudaFree(c->d_status); cudaFree(c->d_split);
     cudaFree(c->d_qpad); cudaFree(c->d_colterm); cudaFree(c->d_thr); cudaFree(c->d_bcnt); cudaFree(c->d_boverflow); cudaFree(c->d_bcand);
     cudaFree(c->d_bhist); cudaFree(c->d_binvq);
     cudaFree(c->d_hits); cudaFree(c->d_cand); cudaFree(c->d_cand_cnt); cudaFree(c->d_tile_counter); cudaFree(c->d_hist);
@@ -890,7 +895,31 @@ static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, 
             fp.x.scan_smem = (uint32_t)((size_t)cap_scan_x * sizeof(KeyX));
             fp.x.fin_smem = (uint32_t)finx_smem;
             fp.x.pad = 0;
-            CU_TRY(launch_pdl<FinalizeParams>(finalize_kernel<false>, 1, kFinalThreads, fin_smem, s, fp));
+            // Long rows or many candidates: one SM would replay keep * dim elements alone (instruction bound, ~0.15 us
+            // per candidate-KB).  Split: candidate selection -> replay on keep / 32 CTAs -> order, filter, certificate.
+            fp.phase = 0;
+            fp.x_keys = reinterpret_cast<u64*>(c->d_split);
+            fp.x_sbs = reinterpret_cast<float*>(c->d_split + (size_t)kMaxKeep * 8);
+            fp.x_fdots = fp.x_sbs + kMaxKeep;
+            fp.x_dots = reinterpret_cast<int*>(fp.x_fdots + kMaxKeep);
+            fp.x_norms = fp.x_dots + kMaxKeep;
+            fp.x_meta = reinterpret_cast<uint32_t*>(fp.x_norms + kMaxKeep);
+            if (c->split_finalize && (size_t)keep * c->pitch >= 256u * 1024u) {
+                fp.phase = 1;
+                CU_TRY(launch_pdl<FinalizeParams>(finalize_kernel<false>, 1, kFinalThreads, fin_smem, s, fp));
+                ReplayParams rp;
+                rp.keys = fp.x_keys; rp.meta = fp.x_meta; rp.rows = c->d_rows; rp.qbytes = sp.qbytes; rp.q16 = sp.q16; rp.qh = sp.qh;
+                rp.dim = c->dim; rp.pitch = c->pitch;
+                rp.sbs = fp.x_sbs; rp.fdots = fp.x_fdots; rp.dots = fp.x_dots; rp.norms = fp.x_norms;
+                const size_t rsm = (size_t)c->pitch * 6 + (size_t)kReplayRows * (kReplaySlice16 + 2) * 16;
+                replay_kernel<<<(keep + kReplayRows - 1) / kReplayRows, kReplayThreads, rsm, s>>>(rp);
+                CU_TRY(cudaGetLastError());
+                fp.phase = 2;
+                finalize_kernel<false><<<1, kFinalThreads, fin_smem, s>>>(fp);
+                CU_TRY(cudaGetLastError());
+            } else {
+                CU_TRY(launch_pdl<FinalizeParams>(finalize_kernel<false>, 1, kFinalThreads, fin_smem, s, fp));
+            }
 #ifndef PBX_USE_CDP
             // without device-side launch both kernels are enqueued always and return at once unless need_exact was raised
             CU_TRY(launch_scan<true>(c, spx, grid, (size_t)cap_scan_x * sizeof(KeyX), s));

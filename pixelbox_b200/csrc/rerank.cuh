@@ -58,6 +58,16 @@ struct FinalizeParams {
     uint32_t pitch;             // bytes
     uint32_t stage_rows;        // candidates per staging group (<= kFinalThreads: one thread per candidate)
     uint32_t slice16;           // 16-byte chunks of every candidate row staged per round
+    // Split mode for large keep * pitch: phase 1 stops after the candidate selection and leaves the keys in x_keys /
+    // x_meta, replay_kernel (many CTAs) replays the candidates into x_sbs / x_fdots / x_dots / x_norms, phase 2 picks
+    // both up and orders, filters, writes the hits and the certificate.  phase 0: everything in this kernel.
+    uint32_t phase;
+    u64* x_keys;                // [keep]
+    uint32_t* x_meta;           // {nc, kappa_k bits, kappa_last bits}
+    float* x_sbs;               // [keep]
+    float* x_fdots;             // [keep]
+    int* x_dots;                // [keep]
+    int* x_norms;               // [keep]
     uint32_t off_sorted;        // byte offsets into dynamic shared memory
     uint32_t off_ent, off_dots, off_q, off_stage;
     const uint8_t* rows;
@@ -147,6 +157,113 @@ __device__ __forceinline__ void fold16(const uint4& v, const float* qa, const fl
             s = ref_fold(s, fb, fb);
             d = ref_fold(d, av[b], fb);
         }
+    }
+}
+
+// One 16-byte chunk (index ch within the row) of a candidate against the query: the two f32 folds of the reference in
+// element order, and the exact integer sums beside them.
+__device__ __forceinline__ void replay_chunk(const uint4& v, uint32_t ch, uint32_t full, uint32_t dim, const float* s_qa,
+                                             const int16_t* s_q16, const float* s_lut, float& s, float& d, int& acc, unsigned& s1,
+                                             unsigned& s2) {
+    if (ch < full) {
+        fold16(v, s_qa + 16 * ch, s_lut, s, d);
+    } else {                                            // ragged tail: dim is not a multiple of 16
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        for (uint32_t i = 16 * ch; i < dim; ++i) {
+            const uint32_t o = i - 16 * ch;
+            const float fb = s_lut[(w[o >> 2] >> (8 * (o & 3))) & 255u];
+            s = ref_fold(s, fb, fb);
+            d = ref_fold(d, s_qa[i], fb);
+        }
+    }
+    const int4 qa4 = *reinterpret_cast<const int4*>(s_q16 + 16 * ch), qb4 = *reinterpret_cast<const int4*>(s_q16 + 16 * ch + 8);
+    const int qq[8] = {qa4.x, qa4.y, qa4.z, qa4.w, qb4.x, qb4.y, qb4.z, qb4.w};
+    acc = dot16(v, qq, acc);
+    s1 = dp4a_uu(v.x, 0x01010101u, s1); s1 = dp4a_uu(v.y, 0x01010101u, s1);
+    s1 = dp4a_uu(v.z, 0x01010101u, s1); s1 = dp4a_uu(v.w, 0x01010101u, s1);
+    s2 = dp4a_uu(v.x, v.x, s2); s2 = dp4a_uu(v.y, v.y, s2);
+    s2 = dp4a_uu(v.z, v.z, s2); s2 = dp4a_uu(v.w, v.w, s2);
+}
+
+// ---- the replay of the candidates on many SMs (split finalize) ----------------------------------------------------------
+// One CTA per 32 candidates: 256 threads stage slices of the 32 rows, the lanes of warp 0 each fold one candidate.  The
+// folds are strictly sequential per candidate, so what this buys is all candidates at once at one SM's latency each,
+// instead of one SM's instruction throughput for keep * dim elements.
+constexpr uint32_t kReplayRows = 32, kReplayThreads = 256, kReplaySlice16 = 31;
+struct ReplayParams {
+    const u64* keys;
+    const uint32_t* meta;
+    const uint8_t* rows;
+    const uint8_t* qbytes;
+    const int16_t* q16;
+    const QueryHeader* qh;
+    uint32_t dim, pitch;
+    float* sbs;
+    float* fdots;
+    int* dots;
+    int* norms;
+};
+
+__global__ void __launch_bounds__(kReplayThreads)
+replay_kernel(const ReplayParams p) {
+    extern __shared__ __align__(16) unsigned char rsm[];
+    float* s_qa = reinterpret_cast<float*>(rsm);                                       // [pitch]
+    int16_t* s_q16 = reinterpret_cast<int16_t*>(rsm + 4 * (size_t)p.pitch);            // [pitch]
+    unsigned char* stage = rsm + 6 * (size_t)p.pitch;                                   // [32][33 * 16]
+    __shared__ float s_lut[256];
+    __shared__ uint32_t s_rows[kReplayRows];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t nc = p.meta[0];
+    const uint32_t c0 = blockIdx.x * kReplayRows;
+    if (c0 >= nc) return;
+    const uint32_t cb = min(kReplayRows, nc - c0);
+    s_lut[tid] = ref_decode(tid);
+    if (tid < cb) s_rows[tid] = key64_row(p.keys[c0 + tid]);
+    for (uint32_t i = tid; i < p.pitch / 8; i += blockDim.x)
+        reinterpret_cast<uint4*>(s_q16)[i] = __ldg(reinterpret_cast<const uint4*>(p.q16) + i);
+    __syncthreads();
+    for (uint32_t i = tid; i < p.pitch; i += blockDim.x) s_qa[i] = s_lut[p.qbytes[i]];
+    __syncthreads();
+    const uint32_t pitch16 = p.pitch / 16, full = p.dim >> 4;
+    constexpr uint32_t srow = (kReplaySlice16 + 2) * 16;        // 33 x 16 bytes: an odd number of 16-byte units
+    float s = 0.0f, d = 0.0f;
+    int acc = 0;
+    unsigned s1 = 0, s2 = 0;
+    for (uint32_t ch0 = 0; ch0 < pitch16; ch0 += kReplaySlice16) {
+        const uint32_t w16 = min(kReplaySlice16, pitch16 - ch0);
+        const uint32_t total16 = cb * w16;
+        for (uint32_t e0 = tid; e0 < total16; e0 += 4 * blockDim.x) {
+            uint4 v[4];
+#pragma unroll
+            for (uint32_t u = 0; u < 4; ++u) {
+                const uint32_t e = e0 + u * blockDim.x;
+                if (e < total16) {
+                    const uint32_t ci = e / w16, ch = e - ci * w16;
+                    v[u] = __ldg(reinterpret_cast<const uint4*>(p.rows + (size_t)s_rows[ci] * p.pitch) + ch0 + ch);
+                }
+            }
+#pragma unroll
+            for (uint32_t u = 0; u < 4; ++u) {
+                const uint32_t e = e0 + u * blockDim.x;
+                if (e < total16) {
+                    const uint32_t ci = e / w16, ch = e - ci * w16;
+                    *reinterpret_cast<uint4*>(stage + (size_t)ci * srow + 16 * ch) = v[u];
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < cb) {
+            const unsigned char* r = stage + (size_t)tid * srow;
+            for (uint32_t cl = 0; cl < w16; ++cl)
+                replay_chunk(*reinterpret_cast<const uint4*>(r + 16 * cl), ch0 + cl, full, p.dim, s_qa, s_q16, s_lut, s, d, acc, s1, s2);
+        }
+        __syncthreads();
+    }
+    if (tid < cb) {
+        p.sbs[c0 + tid] = s;
+        p.fdots[c0 + tid] = d;
+        p.dots[c0 + tid] = 2 * acc - 255 * p.qh->sum_cq;
+        p.norms[c0 + tid] = (int)(4u * s2 - 1020u * s1 + 65025u * p.dim);
     }
 }
 
@@ -313,7 +430,13 @@ finalize_kernel(const FinalizeParams p) {
     __syncthreads();
     for (uint32_t i = tid; i < p.pitch; i += blockDim.x) s_qa[i] = s_lut[qbytes_g[i]];
     uint32_t nc;
-    if constexpr (!BATCH) {
+    if (!BATCH && p.phase == 2) {
+        // split mode, second half: the candidate keys come back from the first half
+        nc = p.x_meta[0];
+        for (uint32_t i = tid; i < nc; i += blockDim.x) sorted[i] = p.x_keys[i];
+        if (tid == 0) { s_kappa_k = __uint_as_float(p.x_meta[1]); s_kappa_last = __uint_as_float(p.x_meta[2]); }
+        __syncthreads();
+    } else if constexpr (!BATCH) {
         for (uint32_t b = tid; b < p.grid; b += blockDim.x) {
             uint32_t c = p.cand_cnt[b];
             s_listcnt[b] = c;
@@ -417,6 +540,12 @@ finalize_kernel(const FinalizeParams p) {
     }
 
     PBX_FIN_STAMP(4);
+    if (!BATCH && p.phase == 1) {
+        // split mode, first half: hand the candidate keys to replay_kernel and to the second half
+        for (uint32_t i = tid; i < nc; i += blockDim.x) p.x_keys[i] = sorted[i];
+        if (tid == 0) { p.x_meta[0] = nc; p.x_meta[1] = __float_as_uint(s_kappa_k); p.x_meta[2] = __float_as_uint(s_kappa_last); }
+        return;
+    }
     // ---- 2. kernel C ------------------------------------------------------------------------------------
     // The query's own norm fold (src/engine.rs:580): the products in parallel (same rounding), the strictly sequential
     // additions by one thread of the last warp, eight loads ahead of the 4-cycle add chain.  The squares live in `buf`,
@@ -448,6 +577,11 @@ finalize_kernel(const FinalizeParams p) {
     const uint32_t full = p.dim >> 4;
     const int sum_cq = qh_g->sum_cq;
     constexpr uint32_t kStageBatch = 6;
+    if (!BATCH && p.phase == 2) {
+        for (uint32_t i = tid; i < nc; i += blockDim.x) {
+            sbs[i] = p.x_sbs[i]; fdots[i] = p.x_fdots[i]; dots[i] = p.x_dots[i]; norms[i] = p.x_norms[i];
+        }
+    } else
     for (uint32_t c0 = 0; c0 < nc; c0 += p.stage_rows) {
         const uint32_t cb = min(p.stage_rows, nc - c0);                // <= blockDim.x
         float s = 0.0f, d = 0.0f;
@@ -483,28 +617,8 @@ finalize_kernel(const FinalizeParams p) {
             PBX_FIN_STAMP(5);
             if (tid < cb) {
                 const unsigned char* r = stage + (size_t)tid * srow;
-                for (uint32_t cl = 0; cl < w16; ++cl) {
-                    const uint32_t ch = ch0 + cl;                       // chunk index within the row
-                    const uint4 v = *reinterpret_cast<const uint4*>(r + 16 * cl);
-                    if (ch < full) {
-                        fold16(v, s_qa + 16 * ch, s_lut, s, d);
-                    } else {                                            // ragged tail: dim is not a multiple of 16
-                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                        for (uint32_t i = 16 * ch; i < p.dim; ++i) {
-                            const uint32_t o = i - 16 * ch;
-                            const float fb = s_lut[(w[o >> 2] >> (8 * (o & 3))) & 255u];
-                            s = ref_fold(s, fb, fb);
-                            d = ref_fold(d, s_qa[i], fb);
-                        }
-                    }
-                    const int4 qa4 = *reinterpret_cast<const int4*>(s_q16 + 16 * ch), qb4 = *reinterpret_cast<const int4*>(s_q16 + 16 * ch + 8);
-                    const int qq[8] = {qa4.x, qa4.y, qa4.z, qa4.w, qb4.x, qb4.y, qb4.z, qb4.w};
-                    acc = dot16(v, qq, acc);
-                    s1 = dp4a_uu(v.x, 0x01010101u, s1); s1 = dp4a_uu(v.y, 0x01010101u, s1);
-                    s1 = dp4a_uu(v.z, 0x01010101u, s1); s1 = dp4a_uu(v.w, 0x01010101u, s1);
-                    s2 = dp4a_uu(v.x, v.x, s2); s2 = dp4a_uu(v.y, v.y, s2);
-                    s2 = dp4a_uu(v.z, v.z, s2); s2 = dp4a_uu(v.w, v.w, s2);
-                }
+                for (uint32_t cl = 0; cl < w16; ++cl)
+                    replay_chunk(*reinterpret_cast<const uint4*>(r + 16 * cl), ch0 + cl, full, p.dim, s_qa, s_q16, s_lut, s, d, acc, s1, s2);
             }
             __syncthreads();
         }
