@@ -70,6 +70,7 @@ struct pbx_corpus {
     SearchStatus* d_status = nullptr;
     unsigned char* d_split = nullptr;  // split finalize hand-over: keys[kMaxKeep] u64 | sbs, fdots, dots, norms [kMaxKeep] 4 B each | meta[4]
     bool split_finalize = true;        // PBX_NO_SPLIT_FINALIZE=1 keeps the one-kernel finalize for every shape
+    size_t split_min_bytes = 256u * 1024u;   // keep * pitch from which the finalize is split (PBX_SPLIT_MIN_BYTES overrides)
     pbx_hit* d_hits = nullptr;
     size_t hits_cap = 0;
     // scan scratch
@@ -295,6 +296,7 @@ extern "C" int pbx_corpus_create(uint32_t dim, uint64_t capacity_hint, int devic
     c->device = device;
     c->dim = dim;
     c->split_finalize = getenv("PBX_NO_SPLIT_FINALIZE") == nullptr;
+    if (const char* e = getenv("PBX_SPLIT_MIN_BYTES")) c->split_min_bytes = (size_t)atoll(e);
     c->pitch = (dim + 15u) & ~15u;
     c->pitch16 = c->pitch / 16u;
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -904,7 +906,7 @@ static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, 
             fp.x_dots = reinterpret_cast<int*>(fp.x_fdots + kMaxKeep);
             fp.x_norms = fp.x_dots + kMaxKeep;
             fp.x_meta = reinterpret_cast<uint32_t*>(fp.x_norms + kMaxKeep);
-            if (c->split_finalize && (size_t)keep * c->pitch >= 256u * 1024u) {
+            if (c->split_finalize && (size_t)keep * c->pitch >= c->split_min_bytes) {
                 fp.phase = 1;
                 CU_TRY(launch_pdl<FinalizeParams>(finalize_kernel<false>, 1, kFinalThreads, fin_smem, s, fp));
                 ReplayParams rp;
