@@ -682,6 +682,10 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
     const int grid = std::max<int>((int)groups, (c->sm_count / (int)groups) * (int)groups);
     const size_t mma_fixed = (size_t)qg * pitch + (size_t)qg * 20 + (size_t)kBatchEpiWarps * 128 * 4 + 1024;
     const uint32_t stages = (uint32_t)std::min<size_t>(kBatchMaxStages, (212u * 1024u - mma_fixed) / ((size_t)kBatchTileRows * 128));
+    // With more than one accumulator stage per tile (qg > 128) a corpus K-chunk stays in the ring until the LAST stage has
+    // used it, so the ring must hold a whole tile (kc chunks) or the producer and the MMA warp would wait for each other.
+    if (stages < 2 || (qg > kBatchAccCols && stages < kc))
+        return fail(PBX_E_INTERNAL, "batched path: ring of %u stages cannot hold a %u-chunk tile (pitch %u, %u queries per CTA)", stages, kc, pitch, qg);
     const size_t mma_smem = mma_fixed + (size_t)stages * kBatchTileRows * 128;
     mp.stages = stages;
     BatchTightenParams tp;

@@ -30,7 +30,8 @@ def check(corpus, ids, queries, k, md, c, oracle_every=1):
     return got
 
 
-@pytest.mark.parametrize("d,n,nq", [(256, 60_000, 40), (256, 150_001, 700), (128, 50_000, 64), (512, 40_000, 300), (1024, 30_000, 130)])
+@pytest.mark.parametrize("d,n,nq", [(256, 60_000, 40), (256, 150_001, 700), (128, 50_000, 64), (512, 40_000, 300), (1024, 30_000, 130),
+                                    (384, 40_000, 300), (640, 30_000, 130), (768, 30_000, 70), (896, 20_000, 33)])
 def test_batched_equals_oracle_and_single_path(d, n, nq):
     rng = np.random.default_rng(d + nq)
     corpus = rng.integers(0, 256, size=(n, d), dtype=np.uint8)
