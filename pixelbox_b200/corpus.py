@@ -5,6 +5,7 @@ Thin host wrapper over the C ABI (include/pixelbox_b200.h); all compute is in th
 from __future__ import annotations
 
 import ctypes
+import threading
 from typing import List, NamedTuple, Optional, Sequence, Tuple
 
 import numpy as np
@@ -37,6 +38,8 @@ class Corpus:
         self.dim = int(dim)
         self.device = int(device)
         nat.check(nat.lib().pbx_corpus_create(self.dim, int(capacity_hint), self.device, ctypes.byref(self._h)))
+        self._tls = threading.local()                   # per-thread output buffers of search()
+        self._pbx_search = nat.lib().pbx_search
 
     # -- lifecycle ---------------------------------------------------------------------------
     def close(self) -> None:
@@ -91,18 +94,38 @@ class Corpus:
 
     # -- search ------------------------------------------------------------------------------
     def search(self, queries, k: int = nat.DEFAULT_K, max_dist: float = nat.DEFAULT_MAX_DIST) -> List[SearchResult]:
-        """pbx_search: host buffers in, host buffers out; one SearchResult per query."""
-        q = _as_u8_2d(queries, self.dim, "search")
+        """pbx_search: host buffers in, host buffers out; one SearchResult per query.
+
+        This is the call the latency of a single interactive query goes through, so the wrapper keeps its own cost
+        down: output arrays and their raw pointers are cached per thread and (nq, k), the query pointer is taken from
+        the array interface (ndarray.ctypes costs ~1 us per use)."""
+        if type(queries) is np.ndarray and queries.dtype == np.uint8 and queries.flags.c_contiguous and (
+                (queries.ndim == 2 and queries.shape[1] == self.dim) or (queries.ndim == 1 and queries.size == self.dim)):
+            q = queries if queries.ndim == 2 else queries.reshape(1, self.dim)
+        else:
+            q = _as_u8_2d(queries, self.dim, "search")
         nq = q.shape[0]
-        ids = np.zeros((nq, k), np.int64)
-        dist = np.zeros((nq, k), np.float32)
-        dot = np.zeros((nq, k), np.int32)
-        n2 = np.zeros((nq, k), np.int32)
-        cnt = np.zeros(nq, np.uint32)
-        nat.check(nat.lib().pbx_search(self._h, nat.ptr(q), nq, int(k), float(max_dist), nat.ptr(ids), nat.ptr(dist),
-                                       nat.ptr(dot), nat.ptr(n2), nat.ptr(cnt)))
-        return [SearchResult(ids[i, :cnt[i]].copy(), dist[i, :cnt[i]].copy(), dot[i, :cnt[i]].copy(), n2[i, :cnt[i]].copy())
-                for i in range(nq)]
+        k = int(k)
+        cache = self._tls.__dict__
+        out = cache.get((nq, k))
+        if out is None:
+            if len(cache) > 64:
+                cache.clear()
+            ids = np.zeros((nq, k), np.int64)
+            dist = np.zeros((nq, k), np.float32)
+            dot = np.zeros((nq, k), np.int32)
+            n2 = np.zeros((nq, k), np.int32)
+            cnt = np.zeros(nq, np.uint32)
+            out = cache[(nq, k)] = (ids, dist, dot, n2, cnt, nat.ptr(ids), nat.ptr(dist), nat.ptr(dot), nat.ptr(n2), nat.ptr(cnt))
+        ids, dist, dot, n2, cnt, p_ids, p_dist, p_dot, p_n2, p_cnt = out
+        rc = self._pbx_search(self._h, q.__array_interface__["data"][0], nq, k, float(max_dist), p_ids, p_dist, p_dot, p_n2, p_cnt)
+        if rc:
+            nat.check(rc)
+        if nq == 1:
+            c = int(cnt[0])
+            return [SearchResult(ids[0, :c].copy(), dist[0, :c].copy(), dot[0, :c].copy(), n2[0, :c].copy())]
+        counts = cnt.tolist()
+        return [SearchResult(ids[i, :c].copy(), dist[i, :c].copy(), dot[i, :c].copy(), n2[i, :c].copy()) for i, c in enumerate(counts)]
 
     def search_hits(self, queries, k: int = nat.DEFAULT_K, max_dist: float = nat.DEFAULT_MAX_DIST) -> Tuple[np.ndarray, np.ndarray]:
         """pbx_search_hits: ([nq][k] pbx_hit records, [nq] counts) -- the per-shard half of a sharded search."""
