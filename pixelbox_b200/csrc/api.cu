@@ -247,6 +247,9 @@ static cudaError_t init_kernel_attributes() {
     if (e == cudaSuccess) e = allow_smem(scan_kernel<LL, CC, true, MM>, scan_cap);
     PBX_EXTRA_SHAPES(PBX_ALLOW_M)
 #undef PBX_ALLOW_M
+#define PBX_ALLOW_R(LL, CC, MM) if (e == cudaSuccess) e = allow_smem(scan_kernel<LL, CC, false, MM, true>, scan_cap);
+    PBX_RAGGED_SHAPES(PBX_ALLOW_R)
+#undef PBX_ALLOW_R
     if (e == cudaSuccess) e = allow_smem(scan_kernel<16, 1, false, 3>, scan_cap);
     if (e == cudaSuccess) e = allow_smem(scan_kernel<16, 1, false, 4>, scan_cap);
     if (e == cudaSuccess) e = allow_smem(scan_generic_kernel<false>, scan_cap);
@@ -536,11 +539,27 @@ static cudaError_t launch_scan(const pbx_corpus* c, const ScanParams& p, int gri
         PBX_EXTRA_SHAPES(PBX_SCAN_CASE_M)
 #undef PBX_SCAN_CASE_M
         default: {
-            size_t sm = smem + (size_t)c->pitch16 * 32;
+            if constexpr (!EXACT) {
+                // any other row length: the smallest lane layout that holds it, with the row stride at run time
+#define PBX_SCAN_CASE_R(LL, CC, MM) \
+    if (c->pitch16 <= (LL) * (CC)) return launch_pdl<ScanParams>(scan_kernel<LL, CC, false, MM, true>, grid, kScanThreads, smem, s, p);
+                PBX_RAGGED_SHAPES(PBX_SCAN_CASE_R)
+#undef PBX_SCAN_CASE_R
+            }
+            size_t sm = smem + (size_t)c->pitch16 * 32;               // the exact pass of those shapes: one lane per row
             return launch_pdl<ScanParams>(scan_generic_kernel<EXACT>, grid, kScanThreads, sm, s, p);
         }
     }
 #undef PBX_SCAN_CASE
+}
+
+// true for the row pitches with a compile-time lane layout (1, 3, 5, 6, 8 times a power of two, see scan.cuh)
+static bool fast_shape(uint32_t pitch16) {
+    if ((pitch16 & (pitch16 - 1)) == 0 && pitch16 <= 256) return true;
+#define PBX_IS_SHAPE(LL, CC, MM) if (pitch16 == (LL) * (CC)) return true;
+    PBX_EXTRA_SHAPES(PBX_IS_SHAPE)
+#undef PBX_IS_SHAPE
+    return false;
 }
 
 static int scan_grid(const pbx_corpus* c) {
@@ -548,7 +567,9 @@ static int scan_grid(const pbx_corpus* c) {
     const bool pow2 = (c->pitch16 & (c->pitch16 - 1)) == 0;
     uint32_t per_sm = c->ctas_per_sm ? c->ctas_per_sm
                       : c->pitch16 >= 256          ? 1u      // 32 lanes x 8 chunks: one CTA per SM has the registers
-                      : !pow2                      ? 2u      // the x3 / x5 / x6 shapes are built for two
+                      : (c->pitch16 > 128 && !fast_shape(c->pitch16)) ? 1u      // ragged rows in the 32 x 8 layout
+                      : (c->pitch16 < 8 && !pow2)  ? 4u      // ragged rows in the 8 x 1 layout
+                      : !pow2                      ? 2u      // the x3 / x5 / x6 shapes and the other ragged layouts
                       : (c->pitch16 == 16) ? 3u : (c->pitch16 > 16) ? 2u : 4u;
     int g = c->sm_count * (int)per_sm;
     return std::min<int>(g, (int)kMaxScanGrid);

@@ -178,13 +178,16 @@ struct ScanShared {
     SelectScratch sel;
 };
 
-// Fast shapes: pitch16 == L * C, L lanes per row, C chunks per lane.
-template <int L, int C, bool EXACT, int MINB = ((L * C >= 16) ? 2 : 4)>
+// Fast shapes: pitch16 == L * C, L lanes per row, C chunks per lane.  RAGGED: the same lane layout for any
+// pitch16 <= L * C (row stride taken from the parameters, lane slots beyond the row neither load nor count), so
+// that every row length streams with coalesced 16-byte loads; only the idle slots are lost.
+template <int L, int C, bool EXACT, int MINB = ((L * C >= 16) ? 2 : 4), bool RAGGED = false>
 __global__ void __launch_bounds__(kScanThreads, MINB)
 scan_kernel(const ScanParams p) {
     using K = typename std::conditional<EXACT, KeyX, u64>::type;
     constexpr int G = 32 / L;                 // rows handled by one warp-wide load
     constexpr int P16 = L * C;                // row pitch in chunks (compile time for fast shapes)
+    const uint32_t PR = RAGGED ? p.pitch16 : (uint32_t)P16;       // actual row stride in chunks
     extern __shared__ __align__(16) unsigned char smem_raw[];
     K* buf = reinterpret_cast<K*>(smem_raw);
     __shared__ ScanShared<K, EXACT> sh;
@@ -203,10 +206,15 @@ scan_kernel(const ScanParams p) {
 
     // centred query chunks of this lane: chunk index j + c*L, 16 values = 8 packed registers each
     int q[C][8];
+    bool has_chunk[C];
+    uint32_t coff[C];                           // RAGGED: chunk offset of slot c within the row
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        const int4* src = reinterpret_cast<const int4*>(p.q16 + (size_t)(j + c * L) * 16);
+        has_chunk[c] = !RAGGED || (uint32_t)(j + c * L) < PR;
+        coff[c] = has_chunk[c] ? (uint32_t)(j + c * L) : PR - 1u;
+        const int4* src = reinterpret_cast<const int4*>(p.q16 + (size_t)(has_chunk[c] ? (j + c * L) : 0) * 16);
         int4 a = __ldg(src), b = __ldg(src + 1);
+        if (!has_chunk[c]) { a = make_int4(0, 0, 0, 0); b = a; }
         q[c][0] = a.x; q[c][1] = a.y; q[c][2] = a.z; q[c][3] = a.w;
         q[c][4] = b.x; q[c][5] = b.y; q[c][6] = b.z; q[c][7] = b.w;
     }
@@ -285,14 +293,16 @@ scan_kernel(const ScanParams p) {
 #else
                 const float inv_r = __ldg(p.inv_norm + my_row);      // capacity is padded to whole tiles
 #endif
-                const uint4* base = p.rows + (size_t)row0 * P16 + (size_t)g * P16 + j;
+                const uint4* base = p.rows + (size_t)row0 * PR + (size_t)g * PR + (RAGGED ? 0 : j);
                 int acc[L];
 #pragma unroll
                 for (int r = 0; r < L; ++r) {
                     int a = 0;
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
-                        uint4 v = ldg_stream(base + (r * G) * P16 + c * L);
+                        // RAGGED: a lane slot beyond the row re-reads the row's last chunk against a zero query chunk:
+                        // no branch, so the loads of an iteration stay batched
+                        uint4 v = ldg_stream(base + (size_t)(r * G) * PR + (RAGGED ? coff[c] : (uint32_t)(c * L)));
                         a = dot16(v, q[c], a);
                     }
                     acc[r] = a;
@@ -316,7 +326,7 @@ scan_kernel(const ScanParams p) {
                     bool pass = false;
                     KeyX key = KeyOps<KeyX>::lowest();
                     if (my_row < p.n && kappa >= theta) {
-                        const ReplayOut ro = replay_row<false>(reinterpret_cast<const uint8_t*>(p.rows) + (size_t)my_row * (P16 * 16),
+                        const ReplayOut ro = replay_row<false>(reinterpret_cast<const uint8_t*>(p.rows) + (size_t)my_row * ((size_t)PR * 16),
                                                                p.qbytes, p.q16, p.dim, qh.sum_cq, sh.lut);
                         float dist = ref_distance(qh.sa, ro.sb, ro.dot);
                         if ((double)dist < p.max_dist) {
@@ -455,3 +465,6 @@ scan_generic_kernel(const ScanParams p) {
     X(1, 3, 2) X(2, 3, 2) X(4, 3, 2) X(8, 3, 2) X(16, 3, 2) X(32, 3, 2)                      \
     X(1, 5, 2) X(2, 5, 2) X(4, 5, 2) X(8, 5, 2) X(16, 5, 2) X(32, 5, 2)                      \
     X(32, 6, 2) X(32, 8, 1)
+
+// Every other pitch: the smallest of these (lanes, chunks, CTAs per SM) layouts that holds the row, run RAGGED.
+#define PBX_RAGGED_SHAPES(X) X(8, 1, 4) X(16, 1, 2) X(32, 1, 2) X(32, 2, 2) X(32, 4, 2) X(32, 8, 1)

@@ -93,11 +93,11 @@ def test_golden_topk_fixture():
                     assert np.array_equal(got[qi].norm2, z[key + "/norm2"]), key
 
 
-@pytest.mark.parametrize("d", [1, 3, 8, 13, 16, 24, 32, 48, 64, 80, 96, 100, 128, 160, 192, 256, 272, 320, 384, 512, 640, 768, 1000, 1024,
-                               1280, 1536, 2048, 2560, 3072, 4096])
+@pytest.mark.parametrize("d", [1, 3, 8, 13, 16, 24, 32, 48, 64, 80, 96, 100, 128, 160, 192, 200, 256, 272, 320, 384, 512, 640, 768, 1000,
+                               1024, 1280, 1536, 1792, 2048, 2100, 2560, 3072, 4000, 4096])
 def test_random_corpus_every_row_shape(d):
-    """Every kernel shape: fast (pitch = 1, 3, 5, 6 or 8 times a power of two chunks: 16..4096 bytes) and generic
-    (everything else, e.g. 112, 272), with ragged n."""
+    """Every kernel shape: compile-time layouts (pitch = 1, 3, 5, 6 or 8 times a power of two chunks: 16..4096 bytes)
+    and the ragged layouts for everything else (e.g. pitches 112, 208, 272, 1008, 1792, 2112, 4000), with ragged n."""
     rng = np.random.default_rng(1000 + d)
     for n in (1, 33, 1500, 4097):
         corpus = rng.integers(0, 256, size=(n, d), dtype=np.uint8)
@@ -107,7 +107,7 @@ def test_random_corpus_every_row_shape(d):
         check_against_oracle(corpus, ids, queries, ks=(7, 100), mds=(1e3, 0.9))
 
 
-@pytest.mark.parametrize("d", [8, 64, 256, 384, 1280])
+@pytest.mark.parametrize("d", [8, 64, 100, 256, 384, 1000, 1280])
 def test_heavy_ties_need_the_exact_pass(d):
     """More identical rows than candidates: order must be by image_id, ids deliberately unsorted
     with respect to row order (SQLite scans by rowid, we scan by load order)."""
