@@ -167,12 +167,15 @@ def run_reference(args):
     return 0
 
 
+TRAFFIC_CSV = "r1i_scan_kernel_ncu_full_summary.csv"      # ncu --set full of the scan kernel, last build of round 1
+
+
 def ncu_traffic(rows: int, dim: int):
     """dram__bytes_read.sum + dram__bytes_write.sum of the scan kernel per launch, from the committed ncu --set full
     capture of this workload (profiles/); None for any other workload."""
     if rows != 10_000_000 or dim != 256:
         return None
-    path = os.path.join(ROOT, "profiles", "r1c_scan_kernel_ncu_full_summary.csv")
+    path = os.path.join(ROOT, "profiles", TRAFFIC_CSV)
     try:
         import csv
         with open(path) as f:
@@ -374,7 +377,7 @@ def run_ours(args):
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "kernel": "scan_kernel<16,1,false,3>" if dim == 256 else "scan_kernel", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(rows, dim),
-                         "traffic_source": "profiles/r1c_scan_kernel_ncu_full_summary.csv (ncu --set full, bytes per launch)",
+                         "traffic_source": f"profiles/{TRAFFIC_CSV} (ncu --set full, bytes per launch)",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": rows * dim, "launch_ms": scan_ms,
                          "share_of_step": scan_ms / ms_step},
             "clocks": clocks,
