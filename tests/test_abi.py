@@ -120,3 +120,22 @@ def test_merge_hits_argument_errors():
     assert L.pbx_merge_hits(None, nat.ptr(c), 1, 1, 4, nat.ptr(o), nat.ptr(oc)) == -1
     assert L.pbx_merge_hits(nat.ptr(g), nat.ptr(c), 1, 1, 0, nat.ptr(o), nat.ptr(oc)) == -1
     assert L.pbx_merge_hits(nat.ptr(g), nat.ptr(c), 1, 1, 4, nat.ptr(o), nat.ptr(oc)) == 0 and oc[0] == 0
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under pixelbox_b200/ (Python or CUDA) may import, link or read it,
+    and the shared library must not depend on libpbx_oracle."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "pixelbox_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), encoding="utf-8", errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f"{f} imports the oracle"
+                assert "pbx_oracle" not in text, f"{f} refers to the oracle library"
+    so = os.path.join(pkg, "lib", "libpixelbox_b200.so")
+    needed = subprocess.run(["readelf", "-d", so], capture_output=True, text=True).stdout
+    assert "pbx_oracle" not in needed
