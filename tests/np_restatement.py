@@ -35,3 +35,24 @@ def cosine_distance(hash_a, hash_b):
     if np.isnan(cosine_similarity):
         m = F(1e-6)
     return (F(1.0) / m) - F(1.0)             # engine.rs:587
+
+
+def byte_distance(hash_a, hash_b):
+    # fold(0f32, |init, (&a, &b)| init + (a as f32 - b as f32).abs()) / (255f32 * len as f32)      engine.rs:590-592
+    init = F(0.0)
+    for a, b in zip(hash_a, hash_b):
+        init = init + abs(F(int(a)) - F(int(b)))
+    return init / (F(255.0) * F(len(hash_a)))
+
+
+def hamming_distance(hash_a, hash_b):
+    # per byte: bits of a ^ b counted into a u8; .sum::<u8>() (wrapping in a release build) / (8f32 * len as f32)   :594-604
+    total = 0
+    for a, b in zip(hash_a, hash_b):
+        diff = int(a) ^ int(b)
+        bits_set = 0
+        while diff != 0:
+            bits_set += diff & 1
+            diff >>= 1
+        total = (total + bits_set) & 0xFF
+    return F(total) / (F(8.0) * F(len(hash_a)))

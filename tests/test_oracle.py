@@ -183,3 +183,8 @@ def test_upstream_hamming_kat_and_byte_distance():
         assert bits(oracle.byte_distance(a, b)) == bits(l1 / (np.float32(255.0) * np.float32(d)))
     assert oracle.byte_distance([0, 255], [255, 0]) == np.float32(1.0)
     assert oracle.byte_distance([7, 7], [7, 7]) == np.float32(0.0)
+    # the independent numpy restatement agrees with the C one, bit for bit
+    for d in (1, 5, 32, 33, 100, 257):
+        a, b = rng.integers(0, 256, d, dtype=np.uint8), rng.integers(0, 256, d, dtype=np.uint8)
+        assert bits(oracle.byte_distance(a, b)) == bits(npr.byte_distance(a, b))
+        assert bits(oracle.hamming_distance(a, b)[0]) == bits(npr.hamming_distance(a, b))
