@@ -45,8 +45,15 @@ extern "C" {
 
 #define PBX_MAX_DIM 4096u
 #define PBX_MAX_K 2048u
-#define PBX_MAX_ROWS 0xFFFFFFF0ull
+#define PBX_MAX_ROWS 0xFFFFF000ull   /* capacity rounding and the +1023 terms of the kernels stay inside 32 bits */
 #define PBX_MAX_SHARDS 64u
+
+/* Per-query error markers in the count output of the device-resident calls (pbx_search_device,
+ * pbx_exchange_allgather_merge); valid counts are <= k <= PBX_MAX_K.  The host-buffer calls never return them: they
+ * repair the query (exact pass re-run from the host) or fail with PBX_E_INTERNAL. */
+#define PBX_COUNT_EXCHANGE_TIMEOUT 0xFFFFFFFFu    /* a peer did not post its records within ~10 s               */
+#define PBX_COUNT_EXACT_LAUNCH_FAILED 0xFFFFFFFEu /* the device-side launch of the exact pass was refused: the  */
+                                                  /* hits of this query are the uncertified fast-pass ones      */
 
 /* DEFAULT_MAX_QUERY_DISTANCE and the literal LIMIT of the reference (src/engine.rs:23, :381). */
 #define PBX_DEFAULT_MAX_DIST 1e3

@@ -51,6 +51,7 @@ struct pbx_corpus {
     uint8_t* d_rows = nullptr;
     float* d_inv = nullptr;
     int* d_rsum = nullptr;            // sum of the raw bytes of each row (batched tensor-core path)
+    float4* d_bmeta = nullptr;        // per 32-row block {norm_lo, norm_hi, rowterm_max}: the batched epilogue's bound
     int64_t* d_ids = nullptr;
 
     cudaStream_t stream = nullptr;    // default search stream
@@ -97,6 +98,7 @@ struct pbx_corpus {
     float last_search_ms = 0.f;
     uint64_t last_bytes = 0;
     int last_grid = 0;
+    uint32_t last_n = 0;              // rows the last enqueued search saw
     uint64_t rows_generation = 0;     // bumped whenever the row buffers are re-allocated
     // batched (tensor-core) path
     uint32_t batch_pad = 0;           // padded queries the batch scratch is sized for
@@ -109,9 +111,12 @@ struct pbx_corpus {
     uint32_t batch_cap = 0;           // candidate buffer entries per query the scratch is sized for
     uint32_t* d_bhist = nullptr;      // [batch_pad][kBatchHistBins]
     float* d_binvq = nullptr;         // [batch_pad]
+    float* d_seedlb = nullptr;        // [kBatchSeedTiles * 8][batch_pad] block bounds of the seed pass
     CUtensorMap map_rows, map_q;
     uint64_t map_rows_gen = ~0ull;
-    uint32_t map_q_pad = 0, map_q_box = 0;
+    uint32_t map_q_pad = 0, map_q_box = 0, map_rows_box = 0;
+    uint32_t batch_cg = 2;            // CTAs per cluster of the batched kernel: 2 = cta_group::2 pairs; PBX_BATCH_CG=1: single CTAs
+
     uint32_t batch_min = 16;          // batches at least this large use the tensor-core path
     uint64_t batched_queries = 0;
     bool scan_timed = false;          // ev_s0/ev_s1 were recorded by the last enqueue
@@ -131,8 +136,8 @@ static float certificate_margin(uint32_t dim) {
 }
 
 static int free_corpus_buffers(pbx_corpus* c) {
-    cudaFree(c->d_rows); cudaFree(c->d_inv); cudaFree(c->d_ids); cudaFree(c->d_rsum);
-    c->d_rows = nullptr; c->d_inv = nullptr; c->d_ids = nullptr; c->d_rsum = nullptr;
+    cudaFree(c->d_rows); cudaFree(c->d_inv); cudaFree(c->d_ids); cudaFree(c->d_rsum); cudaFree(c->d_bmeta);
+    c->d_rows = nullptr; c->d_inv = nullptr; c->d_ids = nullptr; c->d_rsum = nullptr; c->d_bmeta = nullptr;
     c->capacity = 0;
     return PBX_OK;
 }
@@ -143,41 +148,53 @@ static int reserve_rows(pbx_corpus* c, uint64_t rows) {
     if (rows > PBX_MAX_ROWS) return fail(PBX_E_CAPACITY, "shard would hold %llu rows (max %llu)", (unsigned long long)rows, (unsigned long long)PBX_MAX_ROWS);
     uint64_t want = std::max<uint64_t>(rows, c->capacity + c->capacity / 2);
     want = (want + kTileRows - 1) / kTileRows * kTileRows;
-    uint8_t* nr = nullptr; float* ni = nullptr; int64_t* nid = nullptr; int* ns = nullptr;
-    cudaError_t e = cudaMalloc(&nr, want * c->pitch);
-    if (e == cudaSuccess) e = cudaMalloc(&ni, want * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&nid, want * sizeof(int64_t));
-    if (e == cudaSuccess) e = cudaMalloc(&ns, want * sizeof(int));
-    if (e != cudaSuccess && want > rows) {          // retry without growth head-room
-        cudaFree(nr); cudaFree(ni); cudaFree(nid); cudaFree(ns); nr = nullptr; ni = nullptr; nid = nullptr; ns = nullptr;
+    uint8_t* nr = nullptr; float* ni = nullptr; int64_t* nid = nullptr; int* ns = nullptr; float4* nb = nullptr;
+    auto alloc_all = [&](uint64_t rows_) {
+        cudaError_t e_ = cudaMalloc(&nr, rows_ * c->pitch);
+        if (e_ == cudaSuccess) e_ = cudaMalloc(&ni, rows_ * sizeof(float));
+        if (e_ == cudaSuccess) e_ = cudaMalloc(&nid, rows_ * sizeof(int64_t));
+        if (e_ == cudaSuccess) e_ = cudaMalloc(&ns, rows_ * sizeof(int));
+        if (e_ == cudaSuccess) e_ = cudaMalloc(&nb, rows_ / 32 * sizeof(float4));
+        return e_;
+    };
+    auto free_all = [&]() {
+        cudaFree(nr); cudaFree(ni); cudaFree(nid); cudaFree(ns); cudaFree(nb);
+        nr = nullptr; ni = nullptr; nid = nullptr; ns = nullptr; nb = nullptr;
         cudaGetLastError();
+    };
+    cudaError_t e = alloc_all(want);
+    if (e != cudaSuccess && want > rows) {          // retry without growth head-room
+        free_all();
         want = (rows + kTileRows - 1) / kTileRows * kTileRows;
-        e = cudaMalloc(&nr, want * c->pitch);
-        if (e == cudaSuccess) e = cudaMalloc(&ni, want * sizeof(float));
-        if (e == cudaSuccess) e = cudaMalloc(&nid, want * sizeof(int64_t));
-        if (e == cudaSuccess) e = cudaMalloc(&ns, want * sizeof(int));
+        e = alloc_all(want);
     }
     if (e != cudaSuccess) {
-        cudaFree(nr); cudaFree(ni); cudaFree(nid); cudaFree(ns);
-        cudaGetLastError();
+        free_all();
         return fail(PBX_E_OOM, "cannot allocate %llu rows x %u bytes on device %d: %s", (unsigned long long)want, c->pitch, c->device, cudaGetErrorString(e));
     }
     const uint64_t n = c->n.load();
-    CU_TRY(cudaDeviceSynchronize());                // nothing may still read the old buffers
-    if (n) {
-        CU_TRY(cudaMemcpyAsync(nr, c->d_rows, n * c->pitch, cudaMemcpyDeviceToDevice, c->stream));
-        CU_TRY(cudaMemcpyAsync(ni, c->d_inv, n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
-        CU_TRY(cudaMemcpyAsync(nid, c->d_ids, n * sizeof(int64_t), cudaMemcpyDeviceToDevice, c->stream));
-        CU_TRY(cudaMemcpyAsync(ns, c->d_rsum, n * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    e = cudaDeviceSynchronize();                    // nothing may still read the old buffers
+    if (e == cudaSuccess && n) {
+        e = cudaMemcpyAsync(nr, c->d_rows, n * c->pitch, cudaMemcpyDeviceToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ni, c->d_inv, n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(nid, c->d_ids, n * sizeof(int64_t), cudaMemcpyDeviceToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ns, c->d_rsum, n * sizeof(int), cudaMemcpyDeviceToDevice, c->stream);
     }
+    // block metadata: zero everywhere (a valid, merely loose bound), then the blocks of the committed rows again
+    if (e == cudaSuccess) e = cudaMemsetAsync(nb, 0, want / 32 * sizeof(float4), c->stream);
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(nb, c->d_bmeta, (n + 31) / 32 * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream);
     // rows beyond the committed prefix are read (and ignored) by whole-tile loads: keep them defined
-    CU_TRY(cudaMemsetAsync(nr + n * c->pitch, 0, (want - n) * c->pitch, c->stream));
-    CU_TRY(cudaMemsetAsync(ni + n, 0, (want - n) * sizeof(float), c->stream));
-    CU_TRY(cudaMemsetAsync(nid + n, 0, (want - n) * sizeof(int64_t), c->stream));
-    CU_TRY(cudaMemsetAsync(ns + n, 0, (want - n) * sizeof(int), c->stream));
-    CU_TRY(cudaStreamSynchronize(c->stream));
-    cudaFree(c->d_rows); cudaFree(c->d_inv); cudaFree(c->d_ids); cudaFree(c->d_rsum);
-    c->d_rows = nr; c->d_inv = ni; c->d_ids = nid; c->d_rsum = ns;
+    if (e == cudaSuccess) e = cudaMemsetAsync(nr + n * c->pitch, 0, (want - n) * c->pitch, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ni + n, 0, (want - n) * sizeof(float), c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(nid + n, 0, (want - n) * sizeof(int64_t), c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ns + n, 0, (want - n) * sizeof(int), c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {                         // the old buffers stay in place, the new ones go
+        free_all();
+        return fail(PBX_E_CUDA, "moving %llu rows to the grown shard failed: %s", (unsigned long long)n, cudaGetErrorString(e));
+    }
+    cudaFree(c->d_rows); cudaFree(c->d_inv); cudaFree(c->d_ids); cudaFree(c->d_rsum); cudaFree(c->d_bmeta);
+    c->d_rows = nr; c->d_inv = ni; c->d_ids = nid; c->d_rsum = ns; c->d_bmeta = nb;
     c->rows_generation++;                           // device pointers moved: tensor maps must be rebuilt
     c->capacity = want;
     return PBX_OK;
@@ -233,6 +250,8 @@ template <typename Kern>
 static cudaError_t allow_smem(Kern kern, size_t bytes) {
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
+constexpr uint32_t kBatchSeedTiles = 256;            // sample tiles of the batched path's seed pass
+constexpr size_t kBatchSmemLimit = 232448 - 1024;   // 227 KB per CTA minus the kernel's static shared memory
 static cudaError_t init_kernel_attributes() {
     const size_t scan_cap = 8192 * sizeof(KeyX) + PBX_MAX_DIM * 2 + 1024;       // largest cap (keep 4096 + tile) + generic query stage
     const size_t fin_cap = 200 * 1024;
@@ -258,8 +277,12 @@ static cudaError_t init_kernel_attributes() {
     if (e == cudaSuccess) e = allow_smem(finalize_kernel<false>, fin_cap);
     if (e == cudaSuccess) e = allow_smem(replay_kernel, (size_t)PBX_MAX_DIM * 6 + (size_t)kReplayRows * (kReplaySlice16 + 2) * 16);
     if (e == cudaSuccess) e = allow_smem(finalize_kernel<true>, fin_cap);
-    if (e == cudaSuccess) e = allow_smem(batch_mma_kernel<false>, 212 * 1024);
-    if (e == cudaSuccess) e = allow_smem(batch_mma_kernel<true>, 212 * 1024);
+    if (e == cudaSuccess) e = allow_smem(batch_mma_kernel<1, false>, kBatchSmemLimit);
+    if (e == cudaSuccess) e = allow_smem(batch_mma_kernel<1, true>, kBatchSmemLimit);
+    if (e == cudaSuccess) e = allow_smem(batch_mma_kernel<2, false>, kBatchSmemLimit);
+    if (e == cudaSuccess) e = allow_smem(batch_mma_kernel<2, true>, kBatchSmemLimit);
+    if (e == cudaSuccess) e = allow_smem(batch_finalize_kernel, (size_t)PBX_MAX_DIM * 3);
+    if (e == cudaSuccess) e = allow_smem(batch_seed_select_kernel, (size_t)kBatchSeedTiles * 8u * sizeof(u64));
     if (e == cudaSuccess) e = allow_smem(batch_tighten_kernel, kBatchCapLarge * sizeof(u64));
     if (e == cudaSuccess) e = allow_smem(finalize_exact_kernel, fin_cap);
     return e;
@@ -300,6 +323,7 @@ extern "C" int pbx_corpus_create(uint32_t dim, uint64_t capacity_hint, int devic
     c->dim = dim;
     c->split_finalize = getenv("PBX_NO_SPLIT_FINALIZE") == nullptr;
     if (const char* e = getenv("PBX_SPLIT_MIN_BYTES")) c->split_min_bytes = (size_t)atoll(e);
+    if (const char* e = getenv("PBX_BATCH_CG")) c->batch_cg = atoi(e) == 1 ? 1u : 2u;       // experiments / fallback
     c->pitch = (dim + 15u) & ~15u;
     c->pitch16 = c->pitch / 16u;
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -311,6 +335,13 @@ extern "C" int pbx_corpus_create(uint32_t dim, uint64_t capacity_hint, int devic
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_s0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_s1);
     if (e == cudaSuccess) e = init_kernel_attributes();
+    // Device-side (tail) launches of the exact pass: up to 2 per query of a 1024-query batch are queued by ONE finalize
+    // grid.  The default pool holds 2048 pending launches; leave room for back-to-back batches.
+    if (e == cudaSuccess) {
+        size_t cur = 0;
+        if (cudaDeviceGetLimit(&cur, cudaLimitDevRuntimePendingLaunchCount) == cudaSuccess && cur < 8192)
+            e = cudaDeviceSetLimit(cudaLimitDevRuntimePendingLaunchCount, 8192);
+    }
     if (e == cudaSuccess) e = cudaMalloc(&c->d_cand_cnt, kMaxScanGrid * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_tile_counter, 512);      // [0] chunk counter, [32] global bin, +256 B exact-pass count
     if (e == cudaSuccess) e = cudaMemset(c->d_tile_counter, 0, 512);
@@ -338,7 +369,7 @@ extern "C" void pbx_corpus_destroy(pbx_corpus* c) {
     free_corpus_buffers(c);
     cudaFree(c->d_queries); cudaFree(c->d_q16); cudaFree(c->d_qbytes); cudaFree(c->d_qh); cudaFree(c->d_status); cudaFree(c->d_split);
     cudaFree(c->d_qpad); cudaFree(c->d_colterm); cudaFree(c->d_thr); cudaFree(c->d_bcnt); cudaFree(c->d_boverflow); cudaFree(c->d_bcand);
-    cudaFree(c->d_bhist); cudaFree(c->d_binvq);
+    cudaFree(c->d_bhist); cudaFree(c->d_binvq); cudaFree(c->d_seedlb);
     cudaFree(c->d_hits); cudaFree(c->d_cand); cudaFree(c->d_cand_cnt); cudaFree(c->d_tile_counter); cudaFree(c->d_hist);
     cudaFreeHost(c->h_queries); cudaFreeHost(c->h_hits); cudaFreeHost(c->h_stage);
     if (c->ev_chain) cudaEventDestroy(c->ev_chain);
@@ -412,6 +443,13 @@ static int upload_rows(pbx_corpus* c, uint64_t at, const int64_t* ids, const uin
         slot ^= 1;
         off += m;
     }
+    if (rc == PBX_OK && n) {
+        // per-32-row block metadata of every block that holds one of the new rows (the first one may be shared with
+        // committed rows: its bound can only widen, which a concurrent search tolerates)
+        const uint64_t b0 = at / 32, b1 = (at + n + 31) / 32;
+        block_meta_kernel<<<(unsigned)((b1 - b0 + 7) / 8), 256, 0, c->copy_stream>>>(c->d_inv, c->d_rsum, c->dim, b0, b1 - b0, at + n, c->d_bmeta);
+        if (cudaGetLastError() != cudaSuccess) rc = fail(PBX_E_CUDA, "block metadata launch failed");
+    }
     cudaError_t e = cudaStreamSynchronize(c->copy_stream);
     if (rc == PBX_OK && e != cudaSuccess) rc = fail(PBX_E_CUDA, "row upload failed: %s", cudaGetErrorString(e));
     cudaEventDestroy(done[0]);
@@ -419,11 +457,8 @@ static int upload_rows(pbx_corpus* c, uint64_t at, const int64_t* ids, const uin
     return rc;
 }
 
-extern "C" int pbx_corpus_append(pbx_corpus* c, const int64_t* image_ids, const uint8_t* hashes, uint64_t n) {
-    if (!c) return fail(PBX_E_INVALID, "corpus is NULL");
-    if (n == 0) return PBX_OK;
-    if (!image_ids || !hashes) return fail(PBX_E_INVALID, "NULL ids or hashes with n > 0");
-    std::lock_guard<std::mutex> alk(c->append_mu);
+// Caller holds append_mu.
+static int append_locked(pbx_corpus* c, const int64_t* image_ids, const uint8_t* hashes, uint64_t n) {
     CU_TRY(cudaSetDevice(c->device));
     const uint64_t at = c->n.load();
     if (at + n > c->capacity) {
@@ -438,17 +473,25 @@ extern "C" int pbx_corpus_append(pbx_corpus* c, const int64_t* image_ids, const 
     return PBX_OK;
 }
 
+extern "C" int pbx_corpus_append(pbx_corpus* c, const int64_t* image_ids, const uint8_t* hashes, uint64_t n) {
+    if (!c) return fail(PBX_E_INVALID, "corpus is NULL");
+    if (n == 0) return PBX_OK;
+    if (!image_ids || !hashes) return fail(PBX_E_INVALID, "NULL ids or hashes with n > 0");
+    std::lock_guard<std::mutex> alk(c->append_mu);
+    return append_locked(c, image_ids, hashes, n);
+}
+
 extern "C" int pbx_corpus_load(pbx_corpus* c, const int64_t* image_ids, const uint8_t* hashes, uint64_t n) {
     if (!c) return fail(PBX_E_INVALID, "corpus is NULL");
     if (n && (!image_ids || !hashes)) return fail(PBX_E_INVALID, "NULL ids or hashes with n > 0");
+    std::lock_guard<std::mutex> alk(c->append_mu);  // held across the reset and the upload: no append can land in between
     {
-        std::lock_guard<std::mutex> alk(c->append_mu);
         std::lock_guard<std::mutex> lk(c->mu);
         CU_TRY(cudaSetDevice(c->device));
         CU_TRY(cudaDeviceSynchronize());
         c->n.store(0);
     }
-    return pbx_corpus_append(c, image_ids, hashes, n);
+    return n ? append_locked(c, image_ids, hashes, n) : PBX_OK;
 }
 
 extern "C" int pbx_corpus_fill_synthetic(pbx_corpus* c, uint64_t n, uint64_t seed, uint64_t first_row) {
@@ -467,6 +510,8 @@ extern "C" int pbx_corpus_fill_synthetic(pbx_corpus* c, uint64_t n, uint64_t see
         synth_fill_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_rows, c->pitch, c->dim, off, m, seed, first_row + off, c->d_ids);
         const unsigned blocks = (unsigned)((m + 7) / 8);
         row_meta_kernel<<<blocks, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_rows), c->pitch16, c->dim, off, m, c->d_inv, c->d_rsum);
+        const uint64_t b0 = off / 32, b1 = (off + m + 31) / 32;
+        block_meta_kernel<<<(unsigned)((b1 - b0 + 7) / 8), 256, 0, c->stream>>>(c->d_inv, c->d_rsum, c->dim, b0, b1 - b0, off + m, c->d_bmeta);
     }
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaStreamSynchronize(c->stream));
@@ -477,7 +522,8 @@ extern "C" int pbx_corpus_fill_synthetic(pbx_corpus* c, uint64_t n, uint64_t see
 extern "C" int pbx_corpus_read_rows(const pbx_corpus* cc, uint64_t first, uint64_t n, int64_t* image_ids, uint8_t* hashes) {
     pbx_corpus* c = const_cast<pbx_corpus*>(cc);
     if (!c) return fail(PBX_E_INVALID, "corpus is NULL");
-    if (first + n > c->n.load()) return fail(PBX_E_INVALID, "rows [%llu, %llu) outside the corpus", (unsigned long long)first, (unsigned long long)(first + n));
+    const uint64_t size_now = c->n.load();
+    if (n > size_now || first > size_now - n) return fail(PBX_E_INVALID, "rows [%llu, %llu) outside the corpus", (unsigned long long)first, (unsigned long long)(first + n));
     if (n == 0) return PBX_OK;
     std::lock_guard<std::mutex> lk(c->mu);
     CU_TRY(cudaSetDevice(c->device));
@@ -592,29 +638,87 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-// [rows][pitch] u8 matrix, boxes of {128 bytes, box_rows rows}, 128-byte swizzle (the UMMA K-major operand layout)
-static int make_u8_map(CUtensorMap* m, void* base, uint64_t rows, uint32_t pitch, uint32_t box_rows) {
+// [rows][pitch] u8 matrix, boxes of {w bytes, box_rows rows}, w-byte swizzle (the UMMA K-major operand layout)
+static int make_u8_map(CUtensorMap* m, void* base, uint64_t rows, uint32_t pitch, uint32_t w, uint32_t box_rows) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return fail(PBX_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)pitch};
-    cuuint32_t box[2] = {128, box_rows};
+    cuuint32_t box[2] = {w, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUtensorMapSwizzle sw = w == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (w == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(PBX_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return PBX_OK;
 }
 
-// Candidate buffer entries per query and the size of the flood round (round 0: every score is kept) for a given keep.
+// Shape of one batched launch (batch.cuh): K-chunk width, CTA grouping, resident queries, ring depth.
+struct BatchPlan {
+    uint32_t cg;        // CTAs per cluster: 2 = cta_group::2 pairs (default), 1 = single CTAs (PBX_BATCH_CG=1)
+    uint32_t tn;        // corpus rows per tile (UMMA N)
+    uint32_t w, kc;     // K-chunk bytes, chunks per row
+    uint32_t qg;        // resident queries per CTA
+    uint32_t groups;    // query groups of cg * qg queries
+    uint32_t nq_pad;
+    uint32_t stages;
+    size_t smem;
+    int grid;
+};
+
+static bool batch_plan(const pbx_corpus* c, uint32_t nq, BatchPlan* out) {
+    BatchPlan bp;
+    const uint32_t pitch = c->pitch;
+    if (pitch % 32 != 0 || pitch > 1024) return false;
+    bp.cg = c->batch_cg;
+    bp.tn = bp.cg == 2 ? 256u : 128u;                // pairs: 256-row tiles, 128 rows per CTA; single CTAs: 128-row tiles
+    bp.w = pitch % 128 == 0 ? 128u : (pitch % 64 == 0 ? 64u : 32u);
+    bp.kc = pitch / bp.w;
+    const uint32_t stage_bytes = (bp.tn / bp.cg) * bp.w;
+    // resident queries per CTA: what the batch needs, at most 512 and at most 128 KB; fewer if the corpus ring would not
+    // fit (with more than one 128-query block per CTA a tile must stay resident until the last block has used it)
+    uint32_t want = ((nq + bp.cg - 1) / bp.cg + 127u) / 128u * 128u;
+    uint32_t qg = std::min<uint32_t>(std::min<uint32_t>(want, kBatchMaxQG), std::max<uint32_t>(128u, (128u * 1024u / pitch) / 128u * 128u));
+    for (;; qg -= 128) {
+        const size_t fixed = 1024 + (size_t)qg * pitch + batch_smem_fixed(qg, bp.tn);
+        if (fixed < kBatchSmemLimit) {
+            const uint32_t stages = (uint32_t)std::min<size_t>(kBatchMaxStages, (kBatchSmemLimit - fixed) / stage_bytes);
+            const uint32_t need = qg > 128 ? bp.kc + 1 : 2u;
+            if (stages >= need) {
+                bp.qg = qg; bp.stages = stages; bp.smem = fixed + (size_t)stages * stage_bytes;
+                break;
+            }
+        }
+        if (qg == 128) return false;
+    }
+    bp.groups = (nq + bp.cg * bp.qg - 1) / (bp.cg * bp.qg);
+    bp.nq_pad = bp.groups * bp.cg * bp.qg;
+    const uint32_t clusters = std::max<uint32_t>(bp.groups, ((uint32_t)c->sm_count / bp.cg) / bp.groups * bp.groups);
+    bp.grid = (int)(clusters * bp.cg);
+    *out = bp;
+    return true;
+}
+
+// Candidate buffer entries per query.
 static uint32_t batch_cap_for(uint32_t keep) { return keep * 8u <= kBatchCap ? kBatchCap : kBatchCapLarge; }
-static uint32_t batch_flood_tiles(uint32_t keep) { return std::max<uint32_t>(16u, (2u * keep + kBatchTileRows - 1) / kBatchTileRows); }
+
+// The seed pass samples up to kBatchSeedTiles complete tiles, evenly strided over the shard: one bound per (query,
+// 32-row block), at least `keep` of them per query or there is no starting threshold.
+static void batch_seed_geometry(uint32_t n, uint32_t tn, uint32_t* n_tiles, uint32_t* step) {
+    const uint32_t full = n / tn;
+    *n_tiles = std::min<uint32_t>(full, kBatchSeedTiles);
+    *step = *n_tiles ? full / *n_tiles : 1u;
+}
 
 static bool batch_eligible(const pbx_corpus* c, uint32_t nq, uint32_t n, uint32_t k) {
-    // per-query candidate buffers hold kBatchCap keys and are cut back to keep = k + slack between rounds: the scheme
+    // per-query candidate buffers hold kBatchCap keys and are cut back to keep = k + slack at the end: the scheme
     // needs keep well below the capacity, larger k loops over the single-query scan
     const uint32_t keep = default_keep(k, c->slack);
-    return nq >= c->batch_min && c->pitch % 128 == 0 && c->pitch <= 1024 && keep * 8u <= kBatchCapLarge && n >= batch_flood_tiles(keep) * kBatchTileRows;
+    BatchPlan bp;
+    if (nq < c->batch_min || keep * 8u > kBatchCapLarge || !batch_plan(c, std::min<uint32_t>(nq, 1024u), &bp)) return false;
+    uint32_t seed_tiles, seed_step;
+    batch_seed_geometry(n, bp.tn, &seed_tiles, &seed_step);
+    return seed_tiles * (bp.tn / 32u) >= keep + keep / 2u;
 }
 
 static int ensure_batch_scratch(pbx_corpus* c, uint32_t nq_pad, uint32_t cap) {
@@ -634,6 +738,8 @@ static int ensure_batch_scratch(pbx_corpus* c, uint32_t nq_pad, uint32_t cap) {
     CU_TRY(cudaMalloc(&c->d_bcand, (size_t)nq_pad * cap * sizeof(u64)));
     CU_TRY(cudaMalloc(&c->d_bhist, (size_t)nq_pad * kBatchHistBins * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&c->d_binvq, (size_t)nq_pad * sizeof(float)));
+    cudaFree(c->d_seedlb); c->d_seedlb = nullptr;
+    CU_TRY(cudaMalloc(&c->d_seedlb, (size_t)kBatchSeedTiles * 8u * nq_pad * sizeof(float)));
     c->batch_pad = nq_pad;
     c->batch_cap = cap;
     return PBX_OK;
@@ -652,135 +758,164 @@ static bool finalize_stage_layout(size_t avail_bytes, uint32_t keep, uint32_t pi
     return s16 >= 1;
 }
 
+// The exact (tie-resolving) pass of one query as a pair of launches: the scan that replays every row with
+// kappa >= theta, and the merge of its per-CTA lists.  Launched from the device by the finalize kernels when a
+// certificate fails; from the host only to repair a refused device-side launch.
+struct ExactSetup {
+    ScanParams scan;
+    FinalizeExactParams fin;
+    size_t scan_smem, fin_smem;
+    int grid;
+};
+
+static ExactSetup exact_setup(const pbx_corpus* c, uint32_t q, uint32_t k, double max_dist, uint32_t n, pbx_hit* d_hits, uint32_t* d_count) {
+    ExactSetup x;
+    memset(&x, 0, sizeof(x));
+    x.grid = scan_grid(c);
+    const uint32_t cap_scan_x = next_pow2(k + kTileRows);
+    const uint32_t cap_merge_x = next_pow2(k + kMergeChunk);
+    ScanParams& sp = x.scan;
+    sp.rows = reinterpret_cast<const uint4*>(c->d_rows); sp.inv_norm = c->d_inv; sp.ids = c->d_ids; sp.n = n;
+    sp.pitch16 = c->pitch16; sp.dim = c->dim;
+    sp.q16 = c->d_q16 + (size_t)q * c->pitch; sp.qbytes = c->d_qbytes + (size_t)q * c->pitch; sp.qh = c->d_qh + q;
+    sp.keep = k; sp.cap = cap_scan_x; sp.cand = c->d_cand; sp.cand_cnt = c->d_cand_cnt; sp.tile_counter = c->d_tile_counter;
+    sp.hist = c->d_hist; sp.status = c->d_status + q; sp.max_dist = max_dist;
+    FinalizeExactParams& xp = x.fin;
+    xp.cand = reinterpret_cast<const KeyX*>(c->d_cand); xp.cand_cnt = c->d_cand_cnt; xp.grid = (uint32_t)x.grid; xp.k = k;
+    xp.cap = cap_merge_x; xp.dim = c->dim; xp.pitch = c->pitch; xp.rows = c->d_rows; xp.qbytes = sp.qbytes;
+    xp.hits = d_hits + (size_t)q * k; xp.count = d_count + q; xp.status = c->d_status + q; xp.tile_counter = c->d_tile_counter;
+    xp.exact_passes = c->d_exact_passes;
+    x.scan_smem = (size_t)cap_scan_x * sizeof(KeyX);
+    x.fin_smem = (size_t)cap_merge_x * sizeof(KeyX);
+    return x;
+}
+
+static ExactLaunch exact_launch(const ExactSetup& x) {
+    ExactLaunch l;
+    l.scan = x.scan; l.fin = x.fin; l.grid = (uint32_t)x.grid; l.scan_smem = (uint32_t)x.scan_smem; l.fin_smem = (uint32_t)x.fin_smem; l.pad = 0;
+    return l;
+}
+
+template <int CG, bool SEED>
+static cudaError_t launch_batch_mma(const BatchPlan& bp, const BatchMmaParams& mp, cudaStream_t s) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)bp.grid);
+    cfg.blockDim = dim3(kBatchThreads);
+    cfg.dynamicSmemBytes = bp.smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, batch_mma_kernel<CG, SEED>, mp);
+}
+
 // Enqueues the tensor-core search of nq (<= 1024) device-resident queries.  Caller holds c->mu.
 static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, uint32_t k, double max_dist, pbx_hit* d_hits,
                                   uint32_t* d_count, cudaStream_t s, uint32_t n) {
-    const uint32_t pitch = c->pitch, kc = pitch / 128;
-    // Resident queries per CTA: as many as fit 128 KB of shared memory (512, 256 or 128); what is left holds the corpus
-    // ring.  Measured at 10M x 256: 512 queries + 4 ring stages beat 256 + 8 and 128 + 8 (4.8 / 5.1 / 6.0 ms per batch):
-    // the per-tile work of the epilogue warps is amortised over more scores.
-    uint32_t qg = 512;
-    while ((size_t)qg * pitch > 128u * 1024u) qg >>= 1;
-    if (qg < 128) return fail(PBX_E_INTERNAL, "batched path: pitch %u too wide", pitch);
-    const uint32_t groups = (nq + qg - 1) / qg, nq_pad = groups * qg;
-    const uint32_t nmma = qg < 256 ? qg : 256;
+    const uint32_t pitch = c->pitch;
+    BatchPlan bp;
+    if (!batch_plan(c, nq, &bp)) return fail(PBX_E_INTERNAL, "batched path: no launch shape for pitch %u", pitch);
     int rc = ensure_query_scratch(c, nq);
     if (rc != PBX_OK) return rc;
     const uint32_t keep = std::min<uint32_t>(default_keep(k, c->slack), kMaxKeep);
     const uint32_t cap = batch_cap_for(keep);
-    rc = ensure_batch_scratch(c, nq_pad, cap);
+    rc = ensure_batch_scratch(c, bp.nq_pad, cap);
     if (rc != PBX_OK) return rc;
-    if (c->map_rows_gen != c->rows_generation) {
-        rc = make_u8_map(&c->map_rows, c->d_rows, c->capacity, pitch, kBatchTileRows);
+    const uint32_t box_rows = bp.tn / bp.cg, qbox = (bp.qg % 256u) ? 128u : 256u;
+    if (c->map_rows_gen != c->rows_generation || c->map_rows_box != box_rows) {
+        rc = make_u8_map(&c->map_rows, c->d_rows, c->capacity, pitch, bp.w, box_rows);
         if (rc != PBX_OK) return rc;
-        c->map_rows_gen = c->rows_generation;
+        c->map_rows_gen = c->rows_generation; c->map_rows_box = box_rows;
     }
-    if (c->map_q_pad != c->batch_pad || c->map_q_box != nmma) {
-        rc = make_u8_map(&c->map_q, c->d_qpad, c->batch_pad, pitch, nmma);
+    if (c->map_q_pad != c->batch_pad || c->map_q_box != qbox) {
+        rc = make_u8_map(&c->map_q, c->d_qpad, c->batch_pad, pitch, bp.w, qbox);
         if (rc != PBX_OK) return rc;
-        c->map_q_pad = c->batch_pad; c->map_q_box = nmma;
+        c->map_q_pad = c->batch_pad; c->map_q_box = qbox;
     }
     const int grid_scan = scan_grid(c);
     rc = ensure_cand(c, (size_t)std::max<uint32_t>(keep, k) * grid_scan * sizeof(KeyX));      // exact-pass scratch
     if (rc != PBX_OK) return rc;
 
-    BatchPrepParams bp;
-    bp.queries = d_queries; bp.nq = nq; bp.dim = c->dim; bp.pitch = pitch;
-    bp.qpad = c->d_qpad; bp.q16 = c->d_q16; bp.qbytes = c->d_qbytes; bp.qh = c->d_qh;
-    bp.colterm = c->d_colterm; bp.thr = c->d_thr; bp.cand_cnt = c->d_bcnt; bp.overflow = c->d_boverflow;
-    bp.bhist = c->d_bhist; bp.inv_q = c->d_binvq;
-    const uint32_t flood_tiles = batch_flood_tiles(keep);                   // round 0 below: at least 2 * keep rows
-    bp.flood_rows = std::min<uint32_t>(n, flood_tiles * kBatchTileRows);
-    batch_prep_kernel<<<nq_pad, 128, 0, s>>>(bp);
+    BatchPrepParams pp;
+    pp.queries = d_queries; pp.nq = nq; pp.dim = c->dim; pp.pitch = pitch;
+    pp.qpad = c->d_qpad; pp.q16 = c->d_q16; pp.qbytes = c->d_qbytes; pp.qh = c->d_qh;
+    pp.colterm = c->d_colterm; pp.thr = c->d_thr; pp.cand_cnt = c->d_bcnt; pp.overflow = c->d_boverflow;
+    pp.bhist = c->d_bhist; pp.inv_q = c->d_binvq;
+    batch_prep_kernel<<<bp.nq_pad, 128, (size_t)c->dim * sizeof(float), s>>>(pp);
     CU_TRY(cudaGetLastError());
 
     BatchMmaParams mp;
     mp.map_rows = c->map_rows; mp.map_q = c->map_q;
-    mp.inv_norm = c->d_inv; mp.row_sum = c->d_rsum; mp.colterm = c->d_colterm; mp.thr = c->d_thr;
+    mp.inv_norm = c->d_inv; mp.row_sum = c->d_rsum; mp.blk_meta = c->d_bmeta; mp.colterm = c->d_colterm; mp.thr = c->d_thr;
     mp.cand = c->d_bcand; mp.cand_cnt = c->d_bcnt; mp.overflow = c->d_boverflow;
     mp.bhist = c->d_bhist; mp.inv_q = c->d_binvq; mp.thr_live = c->d_thr; mp.keep = keep; mp.cap = cap;
-    mp.n = n; mp.dim = c->dim; mp.kc = kc; mp.qg = qg; mp.groups = groups;
-    const int grid = std::max<int>((int)groups, (c->sm_count / (int)groups) * (int)groups);
-    const size_t mma_fixed = (size_t)qg * pitch + (size_t)qg * 20 + (size_t)kBatchEpiWarps * 128 * 4 + 1024;
-    const uint32_t stages = (uint32_t)std::min<size_t>(kBatchMaxStages, (212u * 1024u - mma_fixed) / ((size_t)kBatchTileRows * 128));
-    // With more than one accumulator stage per tile (qg > 128) a corpus K-chunk stays in the ring until the LAST stage has
-    // used it, so the ring must hold a whole tile (kc chunks) or the producer and the MMA warp would wait for each other.
-    if (stages < 2 || (qg > kBatchAccCols && stages < kc))
-        return fail(PBX_E_INTERNAL, "batched path: ring of %u stages cannot hold a %u-chunk tile (pitch %u, %u queries per CTA)", stages, kc, pitch, qg);
-    const size_t mma_smem = mma_fixed + (size_t)stages * kBatchTileRows * 128;
-    mp.stages = stages;
+    mp.n = n; mp.dim = c->dim; mp.w = bp.w; mp.kc = bp.kc; mp.qg = bp.qg; mp.groups = bp.groups; mp.stages = bp.stages; mp.tn = bp.tn;
+    mp.seed_lb = c->d_seedlb; mp.nq_pad = bp.nq_pad;
     BatchTightenParams tp;
     tp.cand = c->d_bcand; tp.cand_cnt = c->d_bcnt; tp.thr = c->d_thr; tp.keep = keep; tp.nq = nq; tp.cap = cap;
 
-    // Rounds over geometrically growing row ranges.  Round 0 has no thresholds: the flood variant keeps every score of
-    // its >= 2 * keep rows (slot = row).  Afterwards a query's threshold is the keep-th best of everything seen, so a
-    // round over g times the rows seen so far adds about g * keep candidates before any tightening; the buffers hold
-    // `cap`, so g = cap / (4 keep) + 1 leaves a wide margin, and they are cut back to keep between rounds.  Inside long
-    // rounds the thresholds also tighten from per-query histograms, which is what keeps the last rounds cheap.
-    const uint32_t tiles = (n + kBatchTileRows - 1) / kBatchTileRows;
-    const uint32_t grow = std::max<uint32_t>(2u, cap / (4u * std::max<uint32_t>(keep, 1u))) + 1u;
-    uint32_t begin = 0, end = std::min<uint32_t>(tiles, flood_tiles);
-    while (begin < tiles) {
-        mp.tile_begin = begin; mp.tile_end = end;
-        if (begin == 0) batch_mma_kernel<true><<<grid, kBatchThreads, mma_smem, s>>>(mp);
-        else batch_mma_kernel<false><<<grid, kBatchThreads, mma_smem, s>>>(mp);
-        CU_TRY(cudaGetLastError());
-        begin = end;
-        // also after the last round: the large buffers would not fit the finalize kernel's shared memory, and for the
-        // small ones the cut is cheaper here (256-thread CTAs, several per SM) than in the finalize kernel (one per SM)
-        batch_tighten_kernel<<<nq, 256, (size_t)cap * sizeof(u64), s>>>(tp);
-        CU_TRY(cudaGetLastError());
-        if (begin < tiles) {
-            const uint64_t next = (uint64_t)end + (uint64_t)end * grow;
-            end = (uint32_t)std::min<uint64_t>(tiles, next);
-        }
-    }
-
-    // per-query finalize: cut to keep, bit-exact re-rank, certificate; exact passes are tail-launched by its last CTA
-    const uint32_t chunk = kFinalThreads;
-    const uint32_t cap_merge = std::max<uint32_t>(next_pow2(keep + chunk), kBatchCap);     // >= candidates left per query
-    const size_t off_sorted = (size_t)cap_merge * sizeof(u64);
-    const size_t off_dots = 2 * off_sorted;
-    const size_t off_q = (off_dots + (size_t)keep * 20 + 15) & ~(size_t)15;
-    const size_t off_stage = (off_q + (size_t)pitch * 6 + 15) & ~(size_t)15;
-    const size_t fin_budget = 200 * 1024;
-    uint32_t stage_rows = 0, slice16 = 0;
-    size_t stage_bytes = 0;
-    if (off_stage >= fin_budget || !finalize_stage_layout(fin_budget - off_stage, keep, pitch / 16, &stage_rows, &slice16, &stage_bytes))
-        return fail(PBX_E_INTERNAL, "finalize layout does not fit shared memory (k=%u dim=%u)", k, c->dim);
-    const size_t fin_smem = off_stage + stage_bytes;
-    const uint32_t cap_scan_x = next_pow2(k + kTileRows);
-    const uint32_t cap_merge_x = next_pow2(k + kMergeChunk);
-
-    FinalizeParams fp;
-    memset(&fp, 0, sizeof(fp));
-    fp.grid = (uint32_t)grid_scan; fp.keep = keep; fp.cap = cap_merge; fp.chunk = chunk; fp.k = k; fp.n = n;
-    fp.dim = c->dim; fp.pitch = pitch; fp.stage_rows = stage_rows; fp.slice16 = slice16;
-    fp.off_sorted = (uint32_t)off_sorted; fp.off_ent = 0; fp.off_dots = (uint32_t)off_dots; fp.off_q = (uint32_t)off_q; fp.off_stage = (uint32_t)off_stage;
-    fp.rows = c->d_rows; fp.ids = c->d_ids; fp.qbytes = c->d_qbytes; fp.q16 = c->d_q16; fp.qh = c->d_qh;
-    fp.max_dist = max_dist; fp.margin = certificate_margin(c->dim);
-    fp.hits = d_hits; fp.count = d_count; fp.status = c->d_status; fp.tile_counter = c->d_tile_counter;
-    fp.hist = c->d_hist; fp.cand = nullptr; fp.cand_cnt = nullptr;
-    fp.bcand = c->d_bcand; fp.bcnt = c->d_bcnt; fp.boverflow = c->d_boverflow; fp.bticket = c->d_tile_counter + 100;
-    fp.bcap = cap; fp.nq = nq;
-    // exact-pass template (query 0); the launching CTA offsets the per-query pointers
-    ScanParams spx;
-    memset(&spx, 0, sizeof(spx));
-    spx.rows = reinterpret_cast<const uint4*>(c->d_rows); spx.inv_norm = c->d_inv; spx.ids = c->d_ids; spx.n = n;
-    spx.pitch16 = c->pitch16; spx.dim = c->dim; spx.q16 = c->d_q16; spx.qbytes = c->d_qbytes; spx.qh = c->d_qh;
-    spx.keep = k; spx.cap = cap_scan_x; spx.cand = c->d_cand; spx.cand_cnt = c->d_cand_cnt; spx.tile_counter = c->d_tile_counter;
-    spx.hist = c->d_hist; spx.status = c->d_status; spx.max_dist = max_dist;
-    FinalizeExactParams xp;
-    memset(&xp, 0, sizeof(xp));
-    xp.cand = reinterpret_cast<const KeyX*>(c->d_cand); xp.cand_cnt = c->d_cand_cnt; xp.grid = (uint32_t)grid_scan; xp.k = k;
-    xp.cap = cap_merge_x; xp.dim = c->dim; xp.pitch = pitch; xp.rows = c->d_rows; xp.qbytes = c->d_qbytes;
-    xp.hits = d_hits; xp.count = d_count; xp.status = c->d_status; xp.tile_counter = c->d_tile_counter; xp.exact_passes = c->d_exact_passes;
-    fp.x.scan = spx; fp.x.fin = xp; fp.x.grid = (uint32_t)grid_scan;
-    fp.x.scan_smem = (uint32_t)((size_t)cap_scan_x * sizeof(KeyX)); fp.x.fin_smem = (uint32_t)((size_t)cap_merge_x * sizeof(KeyX)); fp.x.pad = 0;
-    finalize_kernel<true><<<nq, kFinalThreads, fin_smem, s>>>(fp);
+    // 1. seed pass over a strided sample of complete tiles: one bound per (query, 32-row block), nothing is pushed
+    uint32_t seed_tiles, seed_step;
+    batch_seed_geometry(n, bp.tn, &seed_tiles, &seed_step);
+    mp.n_tiles = seed_tiles; mp.tile_step = seed_step;
+    CU_TRY((bp.cg == 2 ? launch_batch_mma<2, true>(bp, mp, s) : launch_batch_mma<1, true>(bp, mp, s)));
+    // 2. starting threshold of every query = its keep-th largest bound
+    BatchSeedSelectParams sp;
+    sp.seed_lb = c->d_seedlb; sp.n_blocks = seed_tiles * (bp.tn / 32u); sp.nq_pad = bp.nq_pad; sp.keep = keep; sp.thr = c->d_thr;
+    batch_seed_select_kernel<<<nq, 256, (size_t)sp.n_blocks * sizeof(u64), s>>>(sp);
     CU_TRY(cudaGetLastError());
+    // 3. the main pass over every tile; thresholds keep tightening from the per-query histograms of accepted keys
+    mp.n_tiles = (n + bp.tn - 1) / bp.tn; mp.tile_step = 1;
+    CU_TRY((bp.cg == 2 ? launch_batch_mma<2, false>(bp, mp, s) : launch_batch_mma<1, false>(bp, mp, s)));
+    // 4. cut every buffer back to keep: the finalize kernels take at most `keep` candidates per query
+    batch_tighten_kernel<<<nq, 256, (size_t)cap * sizeof(u64), s>>>(tp);
+    CU_TRY(cudaGetLastError());
+
+    // per-query finalize: bit-exact re-rank, certificate; exact passes are tail-launched by its last CTA
+    const ExactSetup xs = exact_setup(c, 0, k, max_dist, n, d_hits, d_count);       // template of query 0
+    if (keep <= kBfThreads) {
+        BatchFinalizeParams fp;
+        memset(&fp, 0, sizeof(fp));
+        fp.x = exact_launch(xs);
+        fp.bcand = c->d_bcand; fp.bcnt = c->d_bcnt; fp.boverflow = c->d_boverflow; fp.bticket = c->d_tile_counter + 100;
+        fp.bcap = cap; fp.nq = nq; fp.keep = keep; fp.k = k; fp.n = n; fp.dim = c->dim; fp.pitch = pitch;
+        fp.rows = c->d_rows; fp.ids = c->d_ids; fp.qbytes = c->d_qbytes; fp.q16 = c->d_q16; fp.qh = c->d_qh;
+        fp.max_dist = max_dist; fp.margin = certificate_margin(c->dim);
+        fp.hits = d_hits; fp.count = d_count; fp.status = c->d_status;
+        batch_finalize_kernel<<<nq, kBfThreads, (size_t)pitch * 3, s>>>(fp);
+        CU_TRY(cudaGetLastError());
+    } else {
+        const uint32_t chunk = kFinalThreads;
+        const uint32_t cap_merge = std::max<uint32_t>(next_pow2(keep + chunk), kBatchCap);     // >= candidates left per query
+        const size_t off_sorted = (size_t)cap_merge * sizeof(u64);
+        const size_t off_dots = 2 * off_sorted;
+        const size_t off_q = (off_dots + (size_t)keep * 20 + 15) & ~(size_t)15;
+        const size_t off_stage = (off_q + (size_t)pitch * 6 + 15) & ~(size_t)15;
+        const size_t fin_budget = 200 * 1024;
+        uint32_t stage_rows = 0, slice16 = 0;
+        size_t stage_bytes = 0;
+        if (off_stage >= fin_budget || !finalize_stage_layout(fin_budget - off_stage, keep, pitch / 16, &stage_rows, &slice16, &stage_bytes))
+            return fail(PBX_E_INTERNAL, "finalize layout does not fit shared memory (k=%u dim=%u)", k, c->dim);
+        const size_t fin_smem = off_stage + stage_bytes;
+        FinalizeParams fp;
+        memset(&fp, 0, sizeof(fp));
+        fp.grid = (uint32_t)grid_scan; fp.keep = keep; fp.cap = cap_merge; fp.chunk = chunk; fp.k = k; fp.n = n;
+        fp.dim = c->dim; fp.pitch = pitch; fp.stage_rows = stage_rows; fp.slice16 = slice16;
+        fp.off_sorted = (uint32_t)off_sorted; fp.off_ent = 0; fp.off_dots = (uint32_t)off_dots; fp.off_q = (uint32_t)off_q; fp.off_stage = (uint32_t)off_stage;
+        fp.rows = c->d_rows; fp.ids = c->d_ids; fp.qbytes = c->d_qbytes; fp.q16 = c->d_q16; fp.qh = c->d_qh;
+        fp.max_dist = max_dist; fp.margin = certificate_margin(c->dim);
+        fp.hits = d_hits; fp.count = d_count; fp.status = c->d_status; fp.tile_counter = c->d_tile_counter;
+        fp.hist = c->d_hist; fp.cand = nullptr; fp.cand_cnt = nullptr;
+        fp.bcand = c->d_bcand; fp.bcnt = c->d_bcnt; fp.boverflow = c->d_boverflow; fp.bticket = c->d_tile_counter + 100;
+        fp.bcap = cap; fp.nq = nq;
+        fp.x = exact_launch(xs);
+        finalize_kernel<true><<<nq, kFinalThreads, fin_smem, s>>>(fp);
+        CU_TRY(cudaGetLastError());
+    }
     c->batched_queries += nq;
-    c->last_grid = grid;
+    c->last_grid = bp.grid;
     return PBX_OK;
 }
 
@@ -788,6 +923,7 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
 static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, uint32_t k, double max_dist, pbx_hit* d_hits,
                           uint32_t* d_count, cudaStream_t s, bool timed) {
     const uint32_t n = (uint32_t)c->n.load();
+    c->last_n = n;
     c->scan_timed = false;
     if (c->chain_valid) CU_TRY(cudaStreamWaitEvent(s, c->ev_chain, 0));
     if (timed) CU_TRY(cudaEventRecord(c->ev_t0, s));
@@ -809,11 +945,9 @@ static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, 
         const uint32_t cap_scan = next_pow2(keep + 2 * kTileRows);
         const int seed_grid = c->sm_count;
         const bool seeded = (uint64_t)n >= (uint64_t)seed_grid * kSeedThreads * 8;       // small shards: not worth a launch
-        const uint32_t cap_scan_x = next_pow2(k + kTileRows);
         // merge round size: one element per thread, more only when a round must span a complete rank (2 * grid)
         const uint32_t chunk = std::min<uint32_t>(4u, std::max<uint32_t>(1u, (2u * (uint32_t)grid + kFinalThreads - 1) / kFinalThreads)) * kFinalThreads;
         const uint32_t cap_merge = next_pow2(keep + chunk);
-        const uint32_t cap_merge_x = next_pow2(k + kMergeChunk);
         rc = ensure_cand(c, (size_t)std::max<uint32_t>(keep, k) * grid * sizeof(KeyX));
         if (rc != PBX_OK) return rc;
         const float margin = certificate_margin(c->dim);
@@ -829,7 +963,6 @@ static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, 
         if (off_stage >= fin_budget || !finalize_stage_layout(fin_budget - off_stage, keep, c->pitch16, &stage_rows, &slice16, &stage_bytes))
             return fail(PBX_E_INTERNAL, "finalize layout does not fit shared memory (k=%u dim=%u)", k, c->dim);
         const size_t fin_smem = off_stage + stage_bytes;
-        const size_t finx_smem = (size_t)cap_merge_x * sizeof(KeyX);
 
         for (uint32_t q = 0; q < nq; ++q) {
             ScanParams sp;
@@ -898,30 +1031,11 @@ static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, 
             fp.status = c->d_status + q;
             fp.tile_counter = c->d_tile_counter;
             // exact pass parameters: k entries per CTA, (dist, image_id) keys
-            ScanParams spx = sp;
-            spx.keep = k;
-            spx.cap = cap_scan_x;
-            FinalizeExactParams xp;
-            xp.cand = reinterpret_cast<const KeyX*>(c->d_cand);
-            xp.cand_cnt = c->d_cand_cnt;
-            xp.grid = (uint32_t)grid;
-            xp.k = k;
-            xp.cap = cap_merge_x;
-            xp.dim = c->dim;
-            xp.pitch = c->pitch;
-            xp.rows = c->d_rows;
-            xp.qbytes = sp.qbytes;
-            xp.hits = fp.hits;
-            xp.count = fp.count;
-            xp.status = c->d_status + q;
-            xp.tile_counter = c->d_tile_counter;
-            xp.exact_passes = c->d_exact_passes;
-            fp.x.scan = spx;
-            fp.x.fin = xp;
-            fp.x.grid = (uint32_t)grid;
-            fp.x.scan_smem = (uint32_t)((size_t)cap_scan_x * sizeof(KeyX));
-            fp.x.fin_smem = (uint32_t)finx_smem;
-            fp.x.pad = 0;
+            const ExactSetup xs = exact_setup(c, q, k, max_dist, n, d_hits, d_count);
+            const ScanParams& spx = xs.scan;
+            const FinalizeExactParams& xp = xs.fin;
+            (void)spx; (void)xp;
+            fp.x = exact_launch(xs);
             // Long rows or many candidates: one SM would replay keep * dim elements alone (instruction bound, ~0.15 us
             // per candidate-KB).  Split: candidate selection -> replay on keep / 32 CTAs -> order, filter, certificate.
             fp.phase = 0;
@@ -949,8 +1063,8 @@ static int enqueue_search(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, 
             }
 #ifndef PBX_USE_CDP
             // without device-side launch both kernels are enqueued always and return at once unless need_exact was raised
-            CU_TRY(launch_scan<true>(c, spx, grid, (size_t)cap_scan_x * sizeof(KeyX), s));
-            finalize_exact_kernel<<<1, kFinalThreads, finx_smem, s>>>(xp);
+            CU_TRY(launch_scan<true>(c, spx, grid, xs.scan_smem, s));
+            finalize_exact_kernel<<<1, kFinalThreads, xs.fin_smem, s>>>(xp);
             CU_TRY(cudaGetLastError());
 #endif
         }
@@ -1016,6 +1130,26 @@ extern "C" int pbx_search_hits(pbx_corpus* c, const uint8_t* queries, uint32_t n
         if (rc != PBX_OK) return rc;
         CU_TRY(cudaMemcpyAsync(c->h_hits, c->d_hits, (size_t)b * k * sizeof(pbx_hit) + (size_t)b * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         CU_TRY(cudaStreamSynchronize(c->stream));
+        // A refused device-side launch of the exact pass leaves the uncertified fast-pass hits and a marker in the count:
+        // run that query's exact pass from the host (its status still says need_exact, theta is in place) and fetch again.
+        {
+            uint32_t failed = 0;
+            const uint32_t n_now = (uint32_t)c->n.load();
+            for (uint32_t q = 0; q < b; ++q) {
+                if (h_cnt[q] != PBX_COUNT_EXACT_LAUNCH_FAILED) continue;
+                const ExactSetup xs = exact_setup(c, q, k, max_dist, std::min<uint32_t>(n_now, c->last_n), c->d_hits, d_cnt);
+                CU_TRY(launch_scan<true>(c, xs.scan, xs.grid, xs.scan_smem, c->stream));
+                finalize_exact_kernel<<<1, kFinalThreads, xs.fin_smem, c->stream>>>(xs.fin);
+                CU_TRY(cudaGetLastError());
+                ++failed;
+            }
+            if (failed) {
+                CU_TRY(cudaMemcpyAsync(c->h_hits, c->d_hits, (size_t)b * k * sizeof(pbx_hit) + (size_t)b * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+                CU_TRY(cudaStreamSynchronize(c->stream));
+                for (uint32_t q = 0; q < b; ++q)
+                    if (h_cnt[q] > k) return fail(PBX_E_INTERNAL, "exact pass of query %u could not be completed", q0 + q);
+            }
+        }
         if (c->profiling) {
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1) == cudaSuccess) total_ms += ms;
@@ -1138,7 +1272,12 @@ extern "C" int pbx_exchange_create(int device, uint32_t rank, uint32_t world, ui
     cudaError_t e = cudaMalloc(&x->base, x->bytes);
     if (e == cudaSuccess) e = cudaMemset(x->base, 0, x->bytes);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) { delete x; return fail(e == cudaErrorMemoryAllocation ? PBX_E_OOM : PBX_E_CUDA, "exchange allocation failed: %s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) {
+        cudaFree(x->base);
+        cudaGetLastError();
+        delete x;
+        return fail(e == cudaErrorMemoryAllocation ? PBX_E_OOM : PBX_E_CUDA, "exchange allocation failed: %s", cudaGetErrorString(e));
+    }
     *out = x;
     return PBX_OK;
 }
@@ -1186,12 +1325,12 @@ extern "C" int pbx_exchange_allgather_merge(pbx_exchange* x, const pbx_hit* d_lo
     }
     p.local = d_local; p.out = d_out; p.out_count = d_out_count;
     p.rank = x->rank; p.world = x->world; p.nq = nq; p.k = k;
-    x->seq += 1;
-    p.seq = x->seq; p.slot = x->seq & 1u;
+    p.seq = x->seq + 1; p.slot = p.seq & 1u;
     p.slot_records = x->slot_records; p.slot_flags = x->slot_flags;
     p.stage_bytes = merge_smem_bytes(x->world, k);
     exchange_merge_kernel<<<nq, kMergeThreads, p.stage_bytes, static_cast<cudaStream_t>(cuda_stream)>>>(p);
     CU_TRY(cudaGetLastError());
+    x->seq = p.seq;                                 // only a launched call consumes a sequence number (the ranks stay in step)
     return PBX_OK;
 }
 

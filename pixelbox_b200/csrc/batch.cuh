@@ -1,27 +1,34 @@
 // batch.cuh -- kernel B: the batched-query path.  A batch of queries against the corpus is a dense
-// u8 x s8 -> s32 contraction  S[r, q] = sum_i r_i (q_i - 128),  run on the 5th-generation tensor cores
+// s8 x u8 -> s32 contraction  S[q, r] = sum_i (q_i - 128) r_i,  run on the 5th-generation tensor cores
 // (tcgen05.mma.kind::i8, accumulators in TMEM), with the top-k selection fused into the epilogue so the
-// N x Q score matrix (10^10 entries for 10M x 1024) never exists in memory.
+// Q x N score matrix (10^10 entries for 1024 x 10M) never exists in memory.
 //
-//   operands       :  A = corpus bytes r (u8), B = query bytes centred on 128, q' = q - 128 = q ^ 0x80 (s8);  S = sum r q'
+//   operands       :  A = query bytes centred on 128, q' = q - 128 = q ^ 0x80 (s8), M = 128 queries per CTA and MMA;
+//                     B = corpus bytes r (u8), N = 256 corpus rows per tile;  S = sum q' r
 //   exact integers:  dot_i = sum c(q)c(r) = 4 S + (2 sum r - 255 d) + (-510 sum q')   (c(v) = 2v - 255)
-//                    the per-row term varies little across rows (it is 2 sum r, not 510 sum r), so the epilogue
-//                    can pre-test the RAW accumulator against a per-column integer bound: one compare per score
 //   ranking key   :  kappa' = fl(fl(dot_i) * inv_norm_r)      (the per-query factor 1/|c(q)| is applied later)
 //
-// One CTA = one query group (QG <= 512 queries resident in shared memory, loaded once by TMA) x a strided set of
-// 128-row corpus tiles.  Warp 0 streams corpus tiles with TMA (128-byte swizzle, 16 KB K-chunks, 4-stage
-// mbarrier ring); one thread of warp 1 issues the MMAs (M = 128 rows, N = 128 queries, K = 32 bytes per
-// instruction) into a ring of four TMEM accumulators; warps 2..17 are the epilogue: each owns 32 TMEM lanes (rows)
-// and 32 columns of every accumulator, reads them with one tcgen05.ld.32x32b.x32, hands the accumulator straight
-// back to the MMA warp, and tests every score with ONE integer compare against a per-(warp, column) bound that is
-// rebuilt per tile from the query's current threshold and the norm / row-term range of the warp's 32 rows.  Only
-// columns in which some lane passes take the exact test (int -> float, one multiply, one compare); the few that
-// beat the threshold are staged in shared memory and pushed 32 at a time into the query's candidate buffer.
-// Round 0 (2048 rows) has no threshold yet: a flood variant writes every score to slot = row, no atomics.  Later
-// rounds cover geometrically growing row ranges; between rounds batch_tighten_kernel cuts the buffers back to
-// `keep`, inside a round the thresholds tighten from per-query histograms of the accepted keys.  The final
-// candidates go through the same bit-exact re-rank and certificate as the single-query path (finalize_kernel<true>).
+// Why queries are the M operand: an accumulator lane is then ONE query and its 32-bit columns are corpus rows, so an
+// epilogue thread (one TMEM lane) holds 32 scores of the same query.  All of them share that query's threshold, and the
+// 32 rows' norms / row terms enter only through their range (precomputed per 32-row block at load time): the whole
+// selection test is  max(32 scores) >= one bound,  16 three-input integer max instructions per 32 scores instead of a
+// compare per score.  (The first version had corpus rows on the lanes: a different bound per register, 5.4 issued
+// instructions per score where the tensor pipe leaves room for 4.)
+//
+// Why N = 256: measured on this part (tools/umma_i8_peak.cu), a 128 x 128 x 32 i8 MMA takes 83 cycles instead of 64
+// (6307 MACs/clk/SM), 128 x 192 and 128 x 256 run at the full 8192.  Why cta_group::2: with 256-row tiles one SM cannot
+// hold both a whole batch of queries and two corpus tiles; a CTA pair splits the tile (128 rows each, fetched by the
+// hardware from both shared memories) and holds 2 x 512 queries, so the corpus is streamed once per batch of 1024.
+//
+// Warp roles per CTA: warp 0 streams corpus K-chunks with TMA into an mbarrier ring; one thread of warp 1 (leader CTA
+// only) issues the MMAs into a ring of TMEM accumulators (2 x 256 columns); warps 2..17 are the epilogue: warp w owns
+// TMEM lanes 32 (w % 4) .. +31 (queries) and a quarter of the columns (rows) of every accumulator.  Survivors of the
+// bound take the exact float test; the few that beat the threshold are staged per warp and pushed to the per-query
+// candidate buffers.  Starting thresholds come from a seed pass of the same kernel over a strided sample of tiles (one
+// bound per query and 32-row block, nothing pushed; batch_seed_select_kernel takes each query's keep-th largest); inside
+// the main pass the thresholds tighten from per-query histograms of the accepted keys; batch_tighten_kernel cuts the
+// buffers back to `keep` at the end.  The final candidates go through the same bit-exact re-rank and certificate as the
+// single-query path (batch_finalize_kernel).
 #pragma once
 #include <cuda.h>
 #include <cstdio>
@@ -31,62 +38,102 @@ namespace pbx {
 
 constexpr int kBatchEpiWarps = 16;           // four per TMEM lane quarter, each takes a quarter of an accumulator's columns
 constexpr int kBatchThreads = 64 + 32 * kBatchEpiWarps;   // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
-constexpr int kBatchMaxStages = 8;           // corpus K-chunk ring: up to 8 x 16 KB (the host sizes it to the shared memory left)
-constexpr int kBatchTileRows = 128;          // UMMA M
-constexpr int kBatchAccStages = 4;           // TMEM: 4 accumulators of 128 rows x 128 queries (512 columns), a ring between MMA and epilogue
-constexpr uint32_t kBatchAccCols = 128;      // UMMA N
+constexpr int kBatchMaxStages = 8;           // corpus K-chunk ring depth (the host sizes it to the shared memory left)
+constexpr uint32_t kBatchMaxQG = 512;        // resident queries per CTA
 constexpr uint32_t kBatchCap = 4096;         // candidate buffer entries per query (small k)
 constexpr uint32_t kBatchCapLarge = 16384;   // ... for keep > 512 (k = 1000 class)
-constexpr uint32_t kBatchQueryBytes = 128 * 1024;   // resident queries per CTA
-constexpr uint32_t kBatchHistBins = 256;            // per-query histogram of accepted keys over kappa in [-1, 1]
+constexpr uint32_t kBatchHistBins = 256;     // per-query histogram of accepted keys over kappa in [-1, 1]
+constexpr uint32_t kBatchStage = 32;         // staged candidates per epilogue warp
 
 // ---- PTX helpers -------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {        // shared::cluster address of `addr` in CTA `rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+// Arrive (+ expect_tx) on a barrier given by a shared::cluster address: the CTA's own barrier or its pair leader's.
+// Default semantics (release at CTA scope) on purpose: a cluster-scope release compiles to MEMBAR.ALL.GPU, i.e. every
+// arrive would wait for the thread's outstanding global stores and atomics (measured: 2.6 us per accumulator stage
+// instead of 0.5).  What these arrives order is TMEM / shared-memory reuse, which the tcgen05 fences and the
+// completed loads already guarantee.
+__device__ __forceinline__ void mbar_expect_tx_at(uint32_t bar_addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive_at(uint32_t bar_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_addr) : "memory");
 }
-// try_wait with a suspend-time hint: the waiting thread sleeps in hardware between polls instead of spinning on the
-// issue port.  (Measured against a tight spin and against try_wait + nanosleep(32): within 2.5 % of each other.)
+// Spin on try_wait (which itself suspends the thread for a short, hardware-chosen time).  No suspend-time hint: with a
+// long hint the waiter is parked in NANOSLEEP.SYNCS and, for barriers completed from the other CTA of a pair (multicast
+// commits, remote arrives), was observed to wake up microseconds late -- 4.7 us per accumulator stage instead of 0.5.
+// Always on a barrier of the executing CTA.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "PBX_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
         "@p bra PBX_DONE;\n\t"
         "bra PBX_WAIT;\n\t"
-        "PBX_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+        "PBX_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+template <int CG>
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint32_t bar_addr, int x, int y) {
+    if constexpr (CG == 1)
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                     ::"r"(smem_u32(dst)), "l"(map), "r"(bar_addr), "r"(x), "r"(y) : "memory");
+    else        // the completion may be signalled on the pair leader's barrier
+        asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                     ::"r"(smem_u32(dst)), "l"(map), "r"(bar_addr), "r"(x), "r"(y) : "memory");
 }
-// K-major operand, 128-byte swizzle: start address >> 4, LBO unused (1), SBO = 1024 B (8 rows x 128 B), version 1
-__device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem_ptr) {
+// plain (non-tensor) bulk copy global -> this CTA's shared memory, completing on one of its own barriers
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// K-major operand with a W-byte swizzle (W = 128, 64, 32: one K-chunk of W bytes per row, 8-row groups of 8 W bytes):
+// start address >> 4, LBO unused (1), SBO = 8 W bytes, descriptor version 1, layout type 2 / 4 / 6.
+__device__ __forceinline__ uint64_t umma_desc_k(const void* smem_ptr, uint32_t w) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_u32(smem_ptr) & 0x3FFFF) >> 4);
     d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)((8u * w) >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)(w == 128 ? 2u : (w == 64 ? 4u : 6u)) << 61;
     return d;
 }
+template <int CG>
 __device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+    if constexpr (CG == 1)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
+// Arrives on the barrier once every MMA issued so far by this thread has retired; cta_group::2: on the barrier at the
+// same shared-memory offset in both CTAs of the pair.
+template <int CG>
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    if constexpr (CG == 1)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    else
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -96,14 +143,80 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
           "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld64_issue(uint32_t taddr, uint32_t (&r)[64]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]),
+          "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]),
+          "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]),
+          "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(taddr));
+}
+// The registers are operands of the wait, so that no use of them can be scheduled ahead of it.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                   "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                   "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                   "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait64(uint32_t (&r)[64]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                   "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                   "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                   "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]), "+r"(r[32]), "+r"(r[33]), "+r"(r[34]), "+r"(r[35]), "+r"(r[36]),
+                   "+r"(r[37]), "+r"(r[38]), "+r"(r[39]), "+r"(r[40]), "+r"(r[41]), "+r"(r[42]), "+r"(r[43]), "+r"(r[44]), "+r"(r[45]),
+                   "+r"(r[46]), "+r"(r[47]), "+r"(r[48]), "+r"(r[49]), "+r"(r[50]), "+r"(r[51]), "+r"(r[52]), "+r"(r[53]), "+r"(r[54]),
+                   "+r"(r[55]), "+r"(r[56]), "+r"(r[57]), "+r"(r[58]), "+r"(r[59]), "+r"(r[60]), "+r"(r[61]), "+r"(r[62]), "+r"(r[63])
+                 :: "memory");
+}
+__device__ __forceinline__ int max3(int a, int b, int c) { return max(max(a, b), c); }      // VIMNMX3 on sm_100
+
+// ---- per-32-row block metadata (load time): what the epilogue's one-compare test needs from the rows --------------------
+// blk[b] = { norm_lo, norm_hi, rowterm_max, rowterm_min (as int bits) } over rows [32 b, 32 b + 32) below n_rows:
+// norm = 1 / inv_norm (f32 division, the same expression everywhere), rowterm = 2 sum r - 255 dim.
+__global__ void block_meta_kernel(const float* __restrict__ inv_norm, const int* __restrict__ row_sum, uint32_t dim,
+                                  uint64_t first_block, uint64_t n_blocks, uint64_t n_rows, float4* __restrict__ blk) {
+    const uint64_t b = first_block + (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= first_block + n_blocks) return;
+    const uint64_t row = b * 32 + (uint64_t)lane;
+    const bool ok = row < n_rows;
+    float inv_lo = ok ? inv_norm[row] : __int_as_float(0x7f800000), inv_hi = ok ? inv_norm[row] : 0.0f;
+    int rt_max = ok ? 2 * row_sum[row] - 255 * (int)dim : INT_MIN;
+    int rt_min = ok ? 2 * row_sum[row] - 255 * (int)dim : INT_MAX;
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        inv_lo = fminf(inv_lo, __shfl_xor_sync(0xFFFFFFFFu, inv_lo, off));
+        inv_hi = fmaxf(inv_hi, __shfl_xor_sync(0xFFFFFFFFu, inv_hi, off));
+        rt_max = max(rt_max, __shfl_xor_sync(0xFFFFFFFFu, rt_max, off));
+        rt_min = min(rt_min, __shfl_xor_sync(0xFFFFFFFFu, rt_min, off));
+    }
+    if (lane == 0) {
+        float4 m;
+        m.x = inv_hi > 0.0f ? __fdiv_rn(1.0f, inv_hi) : 0.0f;          // smallest norm of the block
+        m.y = inv_hi > 0.0f ? __fdiv_rn(1.0f, inv_lo) : 0.0f;          // largest
+        m.z = __int_as_float(rt_max);
+        m.w = __int_as_float(rt_min);
+        blk[b] = m;
+    }
 }
 
 // ---- per-batch query preparation: one CTA per (padded) query ---------------------------------------------
 struct BatchPrepParams {
     const uint8_t* queries;     // [nq][dim]
     uint32_t nq, dim, pitch;
-    uint8_t* qpad;              // [nq_pad][pitch] raw bytes, zero padded (rows beyond nq are zero): the MMA's B operand
+    uint8_t* qpad;              // [nq_pad][pitch] query bytes ^ 0x80, zero padded (rows beyond nq are zero): the MMA's A operand
     int16_t* q16;               // [nq][pitch] centred (re-rank)
     uint8_t* qbytes;            // [nq][pitch]
     QueryHeader* qh;            // [nq]
@@ -113,10 +226,11 @@ struct BatchPrepParams {
     uint32_t* overflow;         // [nq_pad]
     uint32_t* bhist;            // [nq_pad][kBatchHistBins], zeroed here
     float* inv_q;               // [nq_pad]
-    uint32_t flood_rows;        // rows of round 0: every real query starts with exactly these candidates (slot = row)
 };
 
-__global__ void batch_prep_kernel(const BatchPrepParams p) {
+__global__ void __launch_bounds__(128)
+batch_prep_kernel(const BatchPrepParams p) {
+    extern __shared__ __align__(16) float prep_sq[];       // [dim] squares of the decoded query (for the reference's norm fold)
     const uint32_t q = blockIdx.x;
     const bool real = q < p.nq;
     int s = 0, n2 = 0, raw = 0;
@@ -126,6 +240,7 @@ __global__ void batch_prep_kernel(const BatchPrepParams p) {
         if (real && i < p.dim) { v = p.queries[(size_t)q * p.dim + i]; c = centre(v); }
         p.qpad[(size_t)q * p.pitch + i] = (real && i < p.dim) ? (uint8_t)(v ^ 0x80u) : (uint8_t)0;   // q - 128 as s8
         if (real) { p.q16[(size_t)q * p.pitch + i] = (int16_t)c; p.qbytes[(size_t)q * p.pitch + i] = (uint8_t)v; }
+        if (real && i < p.dim) { const float a = ref_decode(v); prep_sq[i] = __fmul_rn(a, a); }
         s += c; n2 += c * c; raw += (int)v;
     }
     __shared__ int ss[32], sn[32], sr[32];
@@ -138,13 +253,16 @@ __global__ void batch_prep_kernel(const BatchPrepParams p) {
         int S = 0, N = 0, R = 0;
         for (uint32_t w = 0; w < (blockDim.x + 31) / 32; ++w) { S += ss[w]; N += sn[w]; R += sr[w]; }
         if (real) {
+            // the query's own norm fold (src/engine.rs:580): strictly sequential f32 additions of the rounded squares
+            float sa = 0.0f;
+            for (uint32_t i = 0; i < p.dim; ++i) sa = __fadd_rn(sa, prep_sq[i]);
             QueryHeader h;
-            h.sum_cq = S; h.norm2_q = N; h.inv_q = (float)(1.0 / sqrt((double)N)); h.sa = 0.0f;
+            h.sum_cq = S; h.norm2_q = N; h.inv_q = (float)(1.0 / sqrt((double)N)); h.sa = sa;
             p.qh[q] = h;
         }
         p.colterm[q] = -510 * (R - 128 * (int)p.dim);          // -510 * sum (q_i - 128)   (R = 0 for padding queries)
         p.thr[q] = real ? -__int_as_float(0x7f800000) : __int_as_float(0x7f800000);
-        p.cand_cnt[q] = real ? p.flood_rows : 0u;
+        p.cand_cnt[q] = 0u;
         p.overflow[q] = 0;
         p.inv_q[q] = real ? (float)(1.0 / sqrt((double)N)) : 0.0f;
     }
@@ -153,347 +271,473 @@ __global__ void batch_prep_kernel(const BatchPrepParams p) {
 
 // ---- the contraction + selection kernel ---------------------------------------------------------------------
 struct BatchMmaParams {
-    CUtensorMap map_rows;       // corpus [capacity][pitch] u8, box {128 B, 128 rows}, 128-byte swizzle
-    CUtensorMap map_q;          // padded queries [nq_pad][pitch] u8, box {128 B, min(256, QG) rows}
+    CUtensorMap map_rows;       // corpus [capacity][pitch] u8, box {w bytes, tn / CG rows}, w-byte swizzle
+    CUtensorMap map_q;          // padded queries [nq_pad][pitch] u8, box {w bytes, 256 or 128 rows (must divide qg)}
     const float* inv_norm;
     const int* row_sum;
+    const float4* blk_meta;     // [capacity / 32]
     const int* colterm;         // [nq_pad]
-    const float* thr;           // [nq_pad] thresholds on kappa' for this round
+    const float* thr;           // [nq_pad] starting thresholds on kappa' (MAIN)
     u64* cand;                  // [nq_pad][cap]
     uint32_t* cand_cnt;         // [nq_pad]
     uint32_t* overflow;         // [nq_pad]
-    uint32_t* bhist;            // [nq_pad][kBatchHistBins] accepted keys per query and kappa bin (in-round tightening)
+    uint32_t* bhist;            // [nq_pad][kBatchHistBins] accepted keys per query and kappa bin (in-pass tightening)
     const float* inv_q;         // [nq_pad] 1 / |c(q)|  (0 for padding queries)
-    float* thr_live;            // == thr, written: thresholds tightened while the round runs
+    float* thr_live;            // == thr, written: thresholds tightened while the pass runs
+    float* seed_lb;             // SEED: [sample blocks][nq_pad] lower bounds of the best kappa' of each 32-row block
+    uint32_t nq_pad;
     uint32_t keep;
     uint32_t cap;               // candidate buffer entries per query
     uint32_t n;                 // rows visible to this search
     uint32_t dim;
-    uint32_t kc;                // K-chunks of 128 bytes per row (pitch / 128)
-    uint32_t qg;                // queries per group (resident per CTA): 128, 256 or 512
-    uint32_t groups;            // query groups; gridDim.x is a multiple of it
-    uint32_t stages;            // corpus K-chunk ring depth (16 KB each)
-    uint32_t tile_begin, tile_end;   // 128-row tiles of this round
+    uint32_t w;                 // K-chunk width in bytes = swizzle span: 128, 64 or 32
+    uint32_t kc;                // K-chunks per row (pitch / w)
+    uint32_t qg;                // queries resident per CTA: 128, 256, 384 or 512
+    uint32_t groups;            // query groups of CG * qg queries; the grid holds a multiple of `groups` clusters
+    uint32_t stages;            // corpus K-chunk ring depth
+    uint32_t tn;                // corpus rows per tile = UMMA N (128 or 256)
+    uint32_t n_tiles;           // tiles of this launch: tile index = tile_step * i, i < n_tiles
+    uint32_t tile_step;         // 1: every tile (MAIN); > 1: a strided sample (SEED)
 };
 
-template <bool FLOOD>
+constexpr uint32_t kBatchMetaSlots = 4;      // ring of per-tile metadata (inv_norm, row_sum, block metadata of the tile's rows)
+constexpr uint32_t kBatchScrWords = 36;      // survivor scratch slot: 32 scores + {bound, threshold, colterm, query}
+
+// Dynamic shared memory of batch_mma_kernel after the 1024-byte alignment fix-up; the host sizes the ring with it.
+__host__ __device__ inline size_t batch_smem_fixed(uint32_t qg, uint32_t tn) {
+    return (size_t)qg * 12                                            // s_colterm, s_thr, s_invq
+           + (size_t)kBatchMetaSlots * (tn * 8 + tn / 2)              // metadata ring: inv_norm, row_sum, 16 B per 32 rows
+           + (size_t)kBatchEpiWarps * 2 * kBatchScrWords * 4          // survivor scratch
+           + (size_t)kBatchEpiWarps * kBatchStage * 12;               // staged candidates (key + query)
+}
+
+// SEED = true : thresholds do not exist yet.  Over a strided sample of tiles every (query, 32-row block) pair yields a
+//               lower bound of the best kappa' in the block, from the block's maximal raw score and the block metadata;
+//               batch_seed_select_kernel turns the `keep`-th largest bound of a query into its starting threshold (valid:
+//               `keep` distinct rows are at least that good).  Same cost per score as the main pass, nothing is pushed.
+// SEED = false: the main pass over all tiles with the selection described at the top of this file.
+template <int CG, bool SEED>
 __global__ void __launch_bounds__(kBatchThreads, 1)
 batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
     extern __shared__ __align__(16) uint8_t bsm_raw[];     // NOT declared 1024-aligned: the compiler would fold the fix-up below away
-    // the 128-byte swizzle of TMA and UMMA is a function of the shared-memory address: tiles must sit on 1024-byte
-    // boundaries, and dynamic shared memory only starts after the static variables (the host adds 1 KB of slack)
+    // the swizzle of TMA and UMMA is a function of the shared-memory address: tiles must sit on 1024-byte boundaries,
+    // and dynamic shared memory only starts after the static variables (the host adds 1 KB of slack)
     uint8_t* bsm = bsm_raw + ((1024u - (smem_u32(bsm_raw) & 1023u)) & 1023u);
-    const uint32_t QG = p.qg, KC = p.kc;
-    const uint32_t NMMA = QG < 256 ? QG : 256;          // rows of one TMA box of the query operand
-    const uint32_t NS = QG / kBatchAccCols;             // accumulator stages per tile (4, 2 or 1): 128 queries each
-    uint8_t* sQ = bsm;                                  // [KC][QG][128]
-    uint8_t* sA = bsm + (size_t)QG * KC * 128;          // [stages][128][128]
+    const uint32_t QG = p.qg, KC = p.kc, W = p.w, TN = p.tn;
+    const uint32_t MB = QG / 128u;                      // 128-query blocks = accumulator stages per tile
+    const uint32_t NB = TN / CG;                        // corpus rows of a tile in THIS CTA's shared memory
+    const uint32_t AS = 512u / TN;                      // TMEM accumulator ring: 2 x 256 or 4 x 128 columns
+    const uint32_t CPS = TN / 128u;                     // 32-column blocks per epilogue warp and accumulator
     const uint32_t STAGES = p.stages;
-    int* s_colterm = reinterpret_cast<int*>(sA + (size_t)STAGES * kBatchTileRows * 128);
+    const uint32_t stage_bytes = NB * W;
+    uint8_t* sQ = bsm;                                  // [KC][QG][W]
+    uint8_t* sA = bsm + (size_t)QG * KC * W;            // [STAGES][NB][W]
+    float* s_minv = reinterpret_cast<float*>(sA + (size_t)STAGES * stage_bytes);   // [kBatchMetaSlots][TN] inv_norm of the tile's rows
+    int* s_mrs = reinterpret_cast<int*>(s_minv + kBatchMetaSlots * TN);            // [kBatchMetaSlots][TN] row_sum
+    float4* s_mblk = reinterpret_cast<float4*>(s_mrs + kBatchMetaSlots * TN);      // [kBatchMetaSlots][TN / 32] block metadata
+    int* s_scr = reinterpret_cast<int*>(s_mblk + kBatchMetaSlots * (TN / 32u));    // [epilogue warp][2][kBatchScrWords] survivor scratch
+    u64* st_key = reinterpret_cast<u64*>(s_scr + kBatchEpiWarps * 2 * kBatchScrWords);   // [epilogue warp][kBatchStage]
+    uint32_t* st_q = reinterpret_cast<uint32_t*>(st_key + kBatchEpiWarps * kBatchStage);
+    int* s_colterm = reinterpret_cast<int*>(st_q + kBatchEpiWarps * kBatchStage);
     float* s_thr = reinterpret_cast<float*>(s_colterm + QG);
     float* s_invq = s_thr + QG;
-    float2* s_pre = reinterpret_cast<float2*>(s_invq + QG);   // per column {threshold clamped to +-1e30, (float)colterm}: inputs of the pre-test bound
-    int* s_uw = reinterpret_cast<int*>(s_pre + QG);     // [epilogue warp][2 * 64] integer pre-test bounds, rebuilt per tile
-    // per-epilogue-warp staging of accepted candidates: pushes to global memory go out 32 at a time, so the
-    // ~1 us round trip of the slot atomic is paid once per 32 candidates instead of once per candidate
-    __shared__ u64 st_key[kBatchEpiWarps][64];
-    __shared__ uint32_t st_q[kBatchEpiWarps][64];
-    __shared__ __align__(8) uint64_t q_full, a_full[kBatchMaxStages], a_empty[kBatchMaxStages], acc_full[kBatchAccStages], acc_empty[kBatchAccStages];
+    __shared__ uint32_t st_cnt[kBatchEpiWarps];
+    __shared__ __align__(8) uint64_t q_full, a_full[kBatchMaxStages], a_empty[kBatchMaxStages], acc_full[4], acc_empty[4];
+    __shared__ __align__(8) uint64_t m_full[kBatchMetaSlots], m_empty[kBatchMetaSlots];
     __shared__ uint32_t tmem_base;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t g = blockIdx.x % p.groups;
-    const uint32_t ci = blockIdx.x / p.groups, cstride = gridDim.x / p.groups;
+    const uint32_t rank = CG == 1 ? 0u : cluster_ctarank();
+    const uint32_t cluster_id = blockIdx.x / CG;
+    const uint32_t g = cluster_id % p.groups;                                   // query group of this cluster
+    const uint32_t ci = cluster_id / p.groups, cstride = (gridDim.x / CG) / p.groups;
+    const uint32_t qbase = (g * CG + rank) * QG;                                // first query of this CTA
 
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512u));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if constexpr (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512u));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512u));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        }
     }
     if (threadIdx.x == 0) {
-        mbar_init(&q_full, 1);
-        for (int i = 0; i < kBatchMaxStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < kBatchAccStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kBatchEpiWarps); }
+        // barriers that collect from both CTAs of a pair live in the leader and count CG arrivals
+        mbar_init(&q_full, CG);
+        for (int i = 0; i < kBatchMaxStages; ++i) { mbar_init(&a_full[i], CG); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], CG * kBatchEpiWarps); }
+        for (uint32_t i = 0; i < kBatchMetaSlots; ++i) { mbar_init(&m_full[i], 1); mbar_init(&m_empty[i], kBatchEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (uint32_t i = threadIdx.x; i < QG; i += blockDim.x) {
-        s_colterm[i] = p.colterm[g * QG + i];
-        s_thr[i] = p.thr[g * QG + i];
-        s_invq[i] = p.inv_q[g * QG + i];
-        s_pre[i] = make_float2(fminf(fmaxf(s_thr[i], -1.0e30f), 1.0e30f), (float)s_colterm[i]);
+        s_colterm[i] = p.colterm[qbase + i];
+        s_thr[i] = p.thr[qbase + i];
+        s_invq[i] = p.inv_q[qbase + i];
     }
+    if (threadIdx.x < kBatchEpiWarps) st_cnt[threadIdx.x] = 0;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();          // the peer's barriers are initialised before anything signals them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base;
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer: this CTA's queries (once), its NB rows of every tile, and the tile's row metadata =====
         if (lane == 0) {
-#ifdef PBX_DEBUG_BATCH
-            if (blockIdx.x == 0) printf("bsm_raw %x bsm %x sQ %x sA %x q_full %x map_q %p map_rows %p QG %u KC %u NMMA %u\n", smem_u32(bsm_raw), smem_u32(bsm),
-                                        smem_u32(sQ), smem_u32(sA), smem_u32(&q_full), (const void*)&p.map_q, (const void*)&p.map_rows, QG, KC, NMMA);
-#endif
-            mbar_expect_tx(&q_full, QG * KC * 128);
+            const uint32_t qbox = (QG % 256u) ? 128u : 256u;       // rows per TMA box of the query operand: divides QG
+            const uint32_t qfull_l = CG == 1 ? smem_u32(&q_full) : mapa_u32(smem_u32(&q_full), 0);
+            mbar_expect_tx_at(qfull_l, QG * KC * W);
             for (uint32_t kc = 0; kc < KC; ++kc)
-                for (uint32_t h = 0; h < QG; h += NMMA)
-                    tma_load_2d(sQ + ((size_t)kc * QG + h) * 128, &p.map_q, &q_full, (int)(kc * 128), (int)(g * QG + h));
-            uint32_t it = 0;
-            for (uint32_t t = p.tile_begin + ci; t < p.tile_end; t += cstride) {
+                for (uint32_t h = 0; h < QG; h += qbox)
+                    tma_load_2d<CG>(sQ + ((size_t)kc * QG + h) * W, &p.map_q, qfull_l, (int)(kc * W), (int)(qbase + h));
+            uint32_t it = 0, ti = 0;
+            for (uint32_t i = ci; i < p.n_tiles; i += cstride, ++ti) {
+                const uint32_t t = i * p.tile_step;
+                {
+                    // inv_norm / row_sum / block metadata of the tile's TN rows (every CTA of a pair sees all of them):
+                    // plain bulk copies into a small ring the epilogue reads in place
+                    const uint32_t ms = ti % kBatchMetaSlots;
+                    mbar_wait(&m_empty[ms], ((ti / kBatchMetaSlots) & 1u) ^ 1u);
+                    mbar_expect_tx_at(smem_u32(&m_full[ms]), TN * 8u + (TN / 32u) * 16u);
+                    bulk_load(s_minv + ms * TN, p.inv_norm + (size_t)t * TN, TN * 4u, &m_full[ms]);
+                    bulk_load(s_mrs + ms * TN, p.row_sum + (size_t)t * TN, TN * 4u, &m_full[ms]);
+                    bulk_load(s_mblk + ms * (TN / 32u), p.blk_meta + ((size_t)t * TN >> 5), (TN / 32u) * 16u, &m_full[ms]);
+                }
                 for (uint32_t kc = 0; kc < KC; ++kc, ++it) {
                     const uint32_t st = it % STAGES, ph = (it / STAGES) & 1u;
                     mbar_wait(&a_empty[st], ph ^ 1u);
-                    mbar_expect_tx(&a_full[st], kBatchTileRows * 128);
-                    tma_load_2d(sA + (size_t)st * kBatchTileRows * 128, &p.map_rows, &a_full[st], (int)(kc * 128), (int)(t * kBatchTileRows));
+                    const uint32_t full_l = CG == 1 ? smem_u32(&a_full[st]) : mapa_u32(smem_u32(&a_full[st]), 0);
+                    mbar_expect_tx_at(full_l, stage_bytes);
+                    tma_load_2d<CG>(sA + (size_t)st * stage_bytes, &p.map_rows, full_l, (int)(kc * W), (int)(t * TN + rank * NB));
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            // instruction descriptor: D = s32 (2 << 4), A = u8 (0 at bit 7), B = s8 (1 at bit 10), both K-major,
+        // ===== MMA issuer (one thread; of the pair leader with cta_group::2) =====
+        if (lane == 0 && rank == 0) {
+            // instruction descriptor: D = s32 (2 << 4), A = s8 (1 at bit 7), B = u8 (0 at bit 10), both K-major,
             // N >> 3 at bit 17, M >> 4 at bit 24
-            const uint32_t idesc = (2u << 4) | (1u << 10) | ((kBatchAccCols >> 3) << 17) | ((uint32_t)(kBatchTileRows >> 4) << 24);
+            const uint32_t idesc = (2u << 4) | (1u << 7) | ((TN >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
+            const uint32_t ksteps = W / 32u;
             mbar_wait(&q_full, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t it = 0, acc_it = 0;
-            for (uint32_t t = p.tile_begin + ci; t < p.tile_end; t += cstride) {
-                const uint32_t it0 = it;
-                for (uint32_t sg = 0; sg < NS; ++sg, ++acc_it) {
-                    const uint32_t ab = acc_it % kBatchAccStages, par = (acc_it / kBatchAccStages) & 1u;
-                    mbar_wait(&acc_empty[ab], par ^ 1u);                          // the epilogue has drained its previous use
+            uint32_t it0 = 0, acc_it = 0;
+            for (uint32_t i = ci; i < p.n_tiles; i += cstride) {
+                for (uint32_t mb = 0; mb < MB; ++mb, ++acc_it) {
+                    const uint32_t ab = acc_it % AS, par = (acc_it / AS) & 1u;
+                    mbar_wait(&acc_empty[ab], par ^ 1u);                          // the epilogues have drained its previous use
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t d_tmem = tmem + ab * kBatchAccCols;
+                    const uint32_t d_tmem = tmem + ab * TN;
                     for (uint32_t kc = 0; kc < KC; ++kc) {
                         const uint32_t itk = it0 + kc;
                         const uint32_t st = itk % STAGES, ph = (itk / STAGES) & 1u;
-                        if (sg == 0) {
+                        if (mb == 0) {
                             mbar_wait(&a_full[st], ph);
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         }
-                        const uint64_t da = umma_desc_sw128(sA + (size_t)st * kBatchTileRows * 128);
-                        const uint64_t db = umma_desc_sw128(sQ + ((size_t)kc * QG + (size_t)sg * kBatchAccCols) * 128);
-#pragma unroll
-                        for (uint32_t ks = 0; ks < 4; ++ks)
-                            umma_i8(d_tmem, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, (kc | ks) ? 1u : 0u);
-                        if (sg == NS - 1) umma_commit(&a_empty[st]);              // the stage is free once these MMAs retire
+                        const uint64_t da = umma_desc_k(sQ + ((size_t)kc * QG + (size_t)mb * 128u) * W, W);
+                        const uint64_t db = umma_desc_k(sA + (size_t)st * stage_bytes, W);
+                        for (uint32_t ks = 0; ks < ksteps; ++ks)
+                            umma_i8<CG>(d_tmem, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, (kc | ks) ? 1u : 0u);
+                        if (mb == MB - 1) umma_commit<CG>(&a_empty[st]);           // the stage is free once these MMAs retire
                     }
-                    umma_commit(&acc_full[ab]);
+                    umma_commit<CG>(&acc_full[ab]);
                 }
-                it = it0 + KC;
+                it0 += KC;
             }
         }
     } else {
-        // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 (a hardware rule) and 32 of the 128 columns of every
-        // accumulator stage (slice).  The MMA warp may run up to four stages ahead of the slowest epilogue warp. =====
+        // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 (a hardware rule) = 32 queries of every 128-query block,
+        // and columns [slice * TN/4, +TN/4) = corpus rows of the tile.  The MMA thread may run AS stages ahead.
+        // Everything per-query or per-row is re-read from shared memory where it is used: the loop carries almost no
+        // state besides the scores, because a spilled register costs an L2 round trip here (the L1 that would catch it
+        // is the few KB the shared-memory carve-out leaves). =====
+        const uint32_t e = (uint32_t)warp - 2u;
         const uint32_t quarter = (uint32_t)warp & 3u;
-        const uint32_t slice = (uint32_t)(warp - 2) >> 2;            // 0..3
+        const uint32_t slice = e >> 2;                                // 0..3
+        const uint32_t cols_per_slice = TN / 4u;
+        const uint32_t col_base = slice * cols_per_slice;
         uint32_t tile_iter = 0, acc_it = 0;
         const int dterm = -255 * (int)p.dim;
-        u64* my_key = st_key[warp - 2];
-        uint32_t* my_q = st_q[warp - 2];
-        int* my_u = s_uw + (size_t)(warp - 2) * 128;
-        uint32_t staged = 0;                                         // warp-uniform
-        auto flush = [&]() {
-            __syncwarp();
-            for (uint32_t base = 0; base < staged; base += 32) {
-                const uint32_t e = base + (uint32_t)lane;
-                if (e < staged) {
-                    const uint32_t qi = my_q[e];
-                    const u64 key = my_key[e];
-                    const uint32_t slot = atomicAdd(p.cand_cnt + qi, 1u);
-                    if (slot < p.cap) p.cand[(size_t)qi * p.cap + slot] = key;
-                    else p.overflow[qi] = 1u;
-                    // every accepted key is counted once in its query's kappa histogram
-                    const float kap = __fmul_rn(key64_kappa(key), p.inv_q[qi]);
-                    const int bin = min(max(__float2int_rd(__fmul_rn(__fadd_rn(kap, 1.0f), (float)(kBatchHistBins / 2))), 0), (int)kBatchHistBins - 1);
-                    atomicAdd(p.bhist + (size_t)qi * kBatchHistBins + bin, 1u);
-                }
+        u64* my_key = st_key + e * kBatchStage;
+        uint32_t* my_q = st_q + e * kBatchStage;
+        uint32_t* my_cnt = &st_cnt[e];
+        int* my_scr = s_scr + e * (2 * kBatchScrWords);              // two survivor slots: 32 scores + {v, thr, ct, qi}
+        const uint32_t acc_empty0 = CG == 1 ? smem_u32(&acc_empty[0]) : mapa_u32(smem_u32(&acc_empty[0]), 0);
+
+        // Accepted candidates are staged per warp in shared memory and leave in two steps that never wait for each other
+        // inside one accumulator stage: `flush_issue` sends the slot atomics of up to 32 staged records (their results stay
+        // in registers, unread), `flush_complete`, one or more stages later, stores the keys to the slots that have arrived
+        // by then.  A warp that waited ~2 us for its atomics right away would hold back the whole CTA pair: the MMA thread
+        // needs every epilogue warp's arrival to reuse an accumulator.
+        u64 pend_key = 0ull;
+        uint32_t pend_q = 0, pend_slot = 0xFFFFFFFFu;                // 0xFFFFFFFF: nothing in flight
+        auto hist_count = [&](u64 key, uint32_t qi) {                // every accepted key is counted once in its query's kappa histogram
+            const float kap = __fmul_rn(key64_kappa(key), s_invq[qi - qbase]);
+            const int bin = min(max(__float2int_rd(__fmul_rn(__fadd_rn(kap, 1.0f), (float)(kBatchHistBins / 2))), 0), (int)kBatchHistBins - 1);
+            atomicAdd(p.bhist + (size_t)qi * kBatchHistBins + bin, 1u);
+        };
+        auto flush_complete = [&]() {
+            if (pend_slot != 0xFFFFFFFFu) {
+                if (pend_slot < p.cap) p.cand[(size_t)pend_q * p.cap + pend_slot] = pend_key;
+                else p.overflow[pend_q] = 1u;
+                pend_slot = 0xFFFFFFFFu;
             }
-            staged = 0;
+        };
+        auto flush_issue = [&]() {                                   // warp-converged; nothing may be in flight
+            __syncwarp();
+            const uint32_t staged = min(*reinterpret_cast<volatile uint32_t*>(my_cnt), kBatchStage);
+            if ((uint32_t)lane < staged) {
+                pend_key = my_key[lane];
+                pend_q = my_q[lane];
+                pend_slot = min(atomicAdd(p.cand_cnt + pend_q, 1u), 0xFFFFFFFEu);
+                hist_count(pend_key, pend_q);
+            }
+            __syncwarp();
+            if (lane == 0) *my_cnt = 0;
             __syncwarp();
         };
-        // In-round tightening.  At refresh points this CTA turns the histograms of the queries it is responsible for
-        // (column j with j % CTAs-in-group == its index) into thresholds -- the lower edge of the highest bin with at
+        auto flush = [&]() { flush_complete(); flush_issue(); flush_complete(); };     // synchronous: refresh points, end of the pass
+        // a record that does not fit the staging area (a burst of hits in one block): straight to global memory
+        auto push_global = [&](u64 key, uint32_t qi) {
+            const uint32_t slot = atomicAdd(p.cand_cnt + qi, 1u);
+            if (slot < p.cap) p.cand[(size_t)qi * p.cap + slot] = key;
+            else p.overflow[qi] = 1u;
+            hist_count(key, qi);
+        };
+        // In-pass tightening.  At refresh points this CTA turns the histograms of the queries it is responsible for
+        // (query j with j % clusters-in-group == its index) into thresholds -- the lower edge of the highest bin with at
         // least `keep` accepted keys at or above it, a valid bound because those keys are real rows -- publishes them
-        // with an atomic max, and every epilogue thread re-reads the published threshold of one column.
-        const uint32_t ethread = (uint32_t)threadIdx.x - 64u;          // 0 .. 32 * kBatchEpiWarps - 1
+        // with an atomic max, and re-reads the published thresholds of all its queries.  One warp per histogram: the
+        // 256 bins are one 16-byte load per lane pair, the suffix scan runs on shuffles.
         auto refresh = [&]() {
             flush();
-            for (uint32_t j = ethread; j < QG; j += 32u * kBatchEpiWarps) {
-                const uint32_t qi = g * QG + j;
-                if (j % cstride == ci % cstride && s_invq[j] > 0.0f) {
-                    const uint4* hp = reinterpret_cast<const uint4*>(p.bhist + (size_t)qi * kBatchHistBins);
-                    uint32_t run = 0;
-                    int bstar = -1;
-                    for (int c4 = (int)kBatchHistBins / 4 - 1; c4 >= 0 && bstar < 0; --c4) {
-                        const uint4 v = __ldcg(hp + c4);
-                        const uint32_t h[4] = {v.x, v.y, v.z, v.w};
+            for (uint32_t j = ci % cstride + e * cstride; j < QG; j += kBatchEpiWarps * cstride) {     // warp-uniform
+                const uint32_t qi = qbase + j;
+                if (!(s_invq[j] > 0.0f)) continue;
+                const uint4* hp = reinterpret_cast<const uint4*>(p.bhist + (size_t)qi * kBatchHistBins);
+                const uint4 va = __ldcg(hp + lane), vb = __ldcg(hp + 32 + lane);        // bins 4 lane .. +3 and 128 + 4 lane .. +3
+                const uint32_t hb[4] = {vb.x, vb.y, vb.z, vb.w}, ha[4] = {va.x, va.y, va.z, va.w};
+                const uint32_t sum_b = hb[0] + hb[1] + hb[2] + hb[3], sum_a = ha[0] + ha[1] + ha[2] + ha[3];
+                // entries in higher bins than this lane's: upper half first (lanes hold ascending bins)
+                uint32_t incl_b = sum_b, incl_a = sum_a;
 #pragma unroll
-                        for (int i = 3; i >= 0; --i) {
-                            run += h[i];
-                            if (bstar < 0 && run >= p.keep) bstar = 4 * c4 + i;
+                for (int off = 1; off < 32; off <<= 1) {
+                    const uint32_t xb = __shfl_down_sync(0xFFFFFFFFu, incl_b, off), xa = __shfl_down_sync(0xFFFFFFFFu, incl_a, off);
+                    if (lane + off < 32) { incl_b += xb; incl_a += xa; }
+                }
+                const uint32_t total_b = __shfl_sync(0xFFFFFFFFu, incl_b, 0);
+                const uint32_t above_b = incl_b - sum_b, above_a = total_b + incl_a - sum_a;
+                int bstar = -1;
+                {
+                    uint32_t run = above_b;
+#pragma unroll
+                    for (int i = 3; i >= 0; --i) { run += hb[i]; if (bstar < 0 && above_b < p.keep && run >= p.keep) bstar = 128 + 4 * lane + i; }
+                    run = above_a;
+#pragma unroll
+                    for (int i = 3; i >= 0; --i) { run += ha[i]; if (bstar < 0 && above_a < p.keep && run >= p.keep) bstar = 4 * lane + i; }
+                }
+                bstar = __reduce_max_sync(0xFFFFFFFFu, bstar);
+                if (bstar > 0 && lane == 0) {
+                    // kappa-bin edge back to kappa' units, nudged down so that no key of bin >= b* falls below it
+                    const float edge = (float)bstar * (2.0f / (float)kBatchHistBins) - 1.0f;
+                    float t = edge / s_invq[j];
+                    t = t - fabsf(t) * 4.0e-6f - 1.0e-3f;
+                    // float atomic max (thresholds may be negative): compare-and-swap on the bit pattern
+                    float* addr = p.thr_live + qi;
+                    float old = *reinterpret_cast<volatile float*>(addr);
+                    while (t > old) {
+                        const uint32_t prev = atomicCAS(reinterpret_cast<uint32_t*>(addr), __float_as_uint(old), __float_as_uint(t));
+                        if (prev == __float_as_uint(old)) break;
+                        old = __uint_as_float(prev);
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(32 * kBatchEpiWarps) : "memory");       // the epilogue warps only
+            for (uint32_t j = (uint32_t)threadIdx.x - 64u; j < QG; j += 32u * kBatchEpiWarps) {
+                const float live = *reinterpret_cast<volatile float*>(p.thr_live + qbase + j);
+                if (live > s_thr[j]) s_thr[j] = live;
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(32 * kBatchEpiWarps) : "memory");
+        };
+
+        // max of 32 scores: a tree of three-input maxima (16 instructions, depth 4)
+        auto max32 = [](const uint32_t* r) {
+            int t[11];
+#pragma unroll
+            for (int i = 0; i < 10; ++i) t[i] = max3((int)r[3 * i], (int)r[3 * i + 1], (int)r[3 * i + 2]);
+            t[10] = max((int)r[30], (int)r[31]);
+            const int u0 = max3(t[0], t[1], t[2]), u1 = max3(t[3], t[4], t[5]), u2 = max3(t[6], t[7], t[8]), u3 = max(t[9], t[10]);
+            return max(max3(u0, u1, u2), u3);
+        };
+        // A score passes when fl(fl(dot_i) * inv_r) >= thr with dot_i = 4 S + rowterm + colterm.  With norm = 1 / inv_r inside
+        // [norm_lo, norm_hi] and rowterm <= rt_max over the 32 rows of a block, passing implies
+        //     S >= (thr * (thr >= 0 ? norm_lo : norm_hi) - colterm - rt_max - slack) / 4 =: v
+        // (slack covers every rounding; the float -> int conversion saturates, so the clamped +-1e30 thresholds -- -inf: no
+        // bound known, +inf: padding query -- become INT_MIN / INT_MAX).  rowterm = 2 sum r - 255 d moves little from row to
+        // row, so the bound loses almost nothing to rt_max; what it loses to the norm spread of 32 rows is the price of one
+        // compare per 32 scores.
+        auto bound = [](const float thr, const int ct, const float4 bm) {
+            const float rt_f = (float)__float_as_int(bm.z);             // |rowterm| < 2^24: exact
+            const float ctf = (float)ct;
+            const float tt = thr * (thr >= 0.0f ? bm.x : bm.y);
+            const float y = (tt - ctf) - rt_f;
+            const float m = fabsf(tt) + fabsf(ctf) + fabsf(rt_f);       // every rounding above is relative to one of these
+            return __float2int_rd(0.25f * (fmaf(m, -4.0e-6f, y) - 8.0f));
+        };
+        // Rare: `pass` lanes (queries) may have a hit among the 32 rows [row0, row0 + 32) whose scores they hold in r.  Two
+        // lanes at a time dump their scores and their {bound, threshold, colterm, query} into the warp's scratch, then the
+        // whole warp tests one dumped query per step, one ROW per lane, against the per-row metadata the producer left in
+        // shared memory.  No unrolled per-register code, no register carried across.
+        auto resolve = [&](const uint32_t* r, const bool pass, const int v, const float thr, const int ct, const uint32_t qi,
+                           const uint32_t row0, const float* inv_s, const int* rs_s) {
+            uint32_t mask = __ballot_sync(0xFFFFFFFFu, pass);
+            while (mask) {
+                const int o1 = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int o2 = mask ? __ffs(mask) - 1 : -1;
+                mask &= mask - 1;                                        // (0 & anything) stays 0
+                if (lane == o1 || lane == o2) {
+                    int* dst = my_scr + (lane == o2 ? kBatchScrWords : 0);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        *reinterpret_cast<int4*>(dst + 4 * i) = make_int4((int)r[4 * i], (int)r[4 * i + 1], (int)r[4 * i + 2], (int)r[4 * i + 3]);
+                    *reinterpret_cast<int4*>(dst + 32) = make_int4(v, __float_as_int(thr), ct, (int)qi);
+                }
+                __syncwarp();
+                const int n_slots = o2 >= 0 ? 2 : 1;
+                for (int sl = 0; sl < n_slots; ++sl) {
+                    const int* src = my_scr + sl * kBatchScrWords;
+                    const int4 h = *reinterpret_cast<const int4*>(src + 32);           // broadcast
+                    const int sc = src[lane];
+                    if (sc >= h.x && row0 + (uint32_t)lane < p.n) {
+                        const int dot_i = 4 * sc + dterm + 2 * rs_s[lane] + h.z;
+                        const float kf = __fmul_rn((float)dot_i, inv_s[lane]);
+                        if (kf >= __int_as_float(h.y)) {
+                            const u64 key = make_key64(kf, row0 + (uint32_t)lane);
+                            const uint32_t slot = atomicAdd(my_cnt, 1u);
+                            if (slot < kBatchStage) { my_key[slot] = key; my_q[slot] = (uint32_t)h.w; }
+                            else push_global(key, (uint32_t)h.w);
                         }
                     }
-                    if (bstar > 0) {
-                        // kappa-bin edge back to kappa' units, nudged down so that no key of bin >= b* falls below it
-                        const float edge = (float)bstar * (2.0f / (float)kBatchHistBins) - 1.0f;
-                        float t = edge / s_invq[j];
-                        t = t - fabsf(t) * 4.0e-6f - 1.0e-3f;
-                        // float atomic max (thresholds may be negative): compare-and-swap on the bit pattern
-                        float* addr = p.thr_live + qi;
-                        float old = *reinterpret_cast<volatile float*>(addr);
-                        while (t > old) {
-                            const uint32_t prev = atomicCAS(reinterpret_cast<uint32_t*>(addr), __float_as_uint(old), __float_as_uint(t));
-                            if (prev == __float_as_uint(old)) break;
-                            old = __uint_as_float(prev);
-                        }
-                    }
-                }
-                const float live = *reinterpret_cast<volatile float*>(p.thr_live + qi);
-                if (live > s_thr[j]) { s_thr[j] = live; s_pre[j].x = fminf(fmaxf(live, -1.0e30f), 1.0e30f); }
-            }
-            __syncwarp();
-        };
-        // per-row metadata of a tile: fetched one tile ahead, so its L2 round trip hides behind the current tile
-        auto fetch_meta = [&](uint32_t tile, float& inv, int& rs) {
-            const uint32_t rw = tile * kBatchTileRows + quarter * 32u + (uint32_t)lane;
-            const bool ok = tile < p.tile_end && rw < p.n;
-            inv = ok ? __ldg(p.inv_norm + rw) : 0.0f;
-            rs = ok ? __ldg(p.row_sum + rw) : 0;
-        };
-        float inv_next;
-        int rs_next;
-        fetch_meta(p.tile_begin + ci, inv_next, rs_next);
-        for (uint32_t t = p.tile_begin + ci; t < p.tile_end; t += cstride, ++tile_iter) {
-            if (tile_iter >= 4 && ((tile_iter & (tile_iter - 1)) == 0 || (tile_iter & 63u) == 0)) refresh();
-            const uint32_t row = t * kBatchTileRows + quarter * 32u + (uint32_t)lane;
-            const bool row_ok = row < p.n;
-            const float inv_r = inv_next;
-            const int rowterm = dterm + 2 * rs_next;
-            fetch_meta(t + cstride, inv_next, rs_next);
-            if constexpr (!FLOOD) {
-                // Integer pre-test on the raw accumulator.  A score passes when fl(fl(dot_i) * inv_r) >= thr with
-                // dot_i = 4 S + rowterm + colterm.  With norm = 1 / inv_r inside [norm_lo, norm_hi] and rowterm <= rt_max
-                // over the 32 rows of this warp, passing implies
-                //     S >= (thr * (thr >= 0 ? norm_lo : norm_hi) - colterm - rt_max - slack) / 4 =: v[col]
-                // (slack covers every rounding), so ONE integer compare per score never rejects a passing one; the
-                // survivors take the exact test.  rowterm = 2 sum r - 255 d moves little from row to row, so the bound
-                // loses almost nothing to rt_max; what it loses to the norm spread is the price of a per-warp bound.
-                float inv_lo = row_ok ? inv_r : __int_as_float(0x7f800000), inv_hi = row_ok ? inv_r : 0.0f;
-                int rt_max = row_ok ? rowterm : INT_MIN;
-#pragma unroll
-                for (int off = 16; off; off >>= 1) {
-                    inv_lo = fminf(inv_lo, __shfl_xor_sync(0xFFFFFFFFu, inv_lo, off));
-                    inv_hi = fmaxf(inv_hi, __shfl_xor_sync(0xFFFFFFFFu, inv_hi, off));
-                    rt_max = max(rt_max, __shfl_xor_sync(0xFFFFFFFFu, rt_max, off));
-                }
-                const float norm_lo = inv_hi > 0.0f ? 1.0f / inv_hi : 0.0f;
-                const float norm_hi = inv_hi > 0.0f ? 1.0f / inv_lo : 0.0f;
-                const float rt_f = (float)rt_max;                       // |rowterm| < 2^24: exact
-                __syncwarp();
-                // a handful of float ops per column; the float -> int conversion saturates, so the clamped +-1e30
-                // thresholds (-inf: nothing seen yet, +inf: padding column) become INT_MIN / INT_MAX
-#pragma unroll
-                for (uint32_t sg = 0; sg < (uint32_t)kBatchAccStages; ++sg) {
-                    if (sg < NS) {
-                        const uint32_t col = sg * kBatchAccCols + slice * 32u + (uint32_t)lane;
-                        const float2 pc = s_pre[col];
-                        const float tt = pc.x * (pc.x >= 0.0f ? norm_lo : norm_hi);
-                        const float y = (tt - pc.y) - rt_f;
-                        const float m = fabsf(tt) + fabsf(pc.y) + fabsf(rt_f);   // every rounding above is relative to one of these
-                        my_u[sg * 32u + (uint32_t)lane] = __float2int_rd(0.25f * (fmaf(m, -4.0e-6f, y) - 8.0f));
-                    }
                 }
                 __syncwarp();
             }
-            for (uint32_t sg = 0; sg < NS; ++sg, ++acc_it) {
-                const uint32_t ab = acc_it % kBatchAccStages;
-                mbar_wait(&acc_full[ab], (acc_it / kBatchAccStages) & 1u);
+        };
+
+        for (uint32_t i = ci; i < p.n_tiles; i += cstride, ++tile_iter) {
+            const uint32_t t = i * p.tile_step;
+            // refresh points: every tile at first (the starting thresholds are loose), then ever more rarely
+            if (!SEED && tile_iter >= 1 && (tile_iter <= 8 || (tile_iter & (tile_iter - 1)) == 0 || (tile_iter & 31u) == 0)) refresh();
+            const uint32_t ms = tile_iter % kBatchMetaSlots;
+            mbar_wait(&m_full[ms], (tile_iter / kBatchMetaSlots) & 1u);             // this tile's row / block metadata has landed
+            const float4* bm_s = s_mblk + ms * (TN / 32u) + (col_base >> 5);
+            for (uint32_t mb = 0; mb < MB; ++mb, ++acc_it) {
+                const uint32_t ab = acc_it % AS;
+                const uint32_t j = mb * 128u + quarter * 32u + (uint32_t)lane;      // this lane's query in the block
+                const uint32_t qi = qbase + j;
+                const float thr = fminf(fmaxf(s_thr[j], -1.0e30f), 1.0e30f);
+                const int ct = s_colterm[j];
+                mbar_wait(&acc_full[ab], (acc_it / AS) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                do {                                                  // one 32-column block per warp and stage
-                    uint32_t r[32];
-                    tmem_ld32(tmem + ((quarter * 32u) << 16) + ab * kBatchAccCols + slice * 32u, r);
-                    // the scores are in registers: hand the accumulator back to the MMA warp before looking at them
+                const uint32_t taddr = tmem + ((quarter * 32u) << 16) + ab * TN + col_base;
+                const uint32_t row0 = t * TN + col_base;
+                if (CPS == 2) {
+                    uint32_t r[64];
+                    tmem_ld64_issue(taddr, r);
+                    tmem_ld_wait64(r);
+                    // the scores are in registers: hand the accumulator back to the MMA thread before looking at them
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&acc_empty[ab]);
-                    const uint32_t colbase = sg * kBatchAccCols + slice * 32u;
-                    const int* my_us = my_u + sg * 32u;
-                    if constexpr (FLOOD) {
-                        // round 0: every score of a real query is a candidate; its slot in the query's buffer is its row
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const uint32_t col = colbase + (uint32_t)i;
-                            const int dot_i = 4 * (int)r[i] + rowterm + s_colterm[col];
-                            const float kf = __fmul_rn((float)dot_i, inv_r);
-                            if (row_ok && s_invq[col] > 0.0f) p.cand[(size_t)(g * QG + col) * p.cap + row] = make_key64(kf, row);
+                    if (lane == 0) mbar_arrive_at(acc_empty0 + ab * 8u);
+                    const float4 bm0 = bm_s[0], bm1 = bm_s[1];
+                    const int mx0 = max32(r), mx1 = max32(r + 32);
+                    if constexpr (SEED) {
+                        // The block's best raw score belongs to a real row r* with dot_i = 4 S + rowterm + colterm >= 4 mx + rt_min
+                        // + ct =: d and kappa' = fl(fl(dot_i) * inv_r), 1 / norm_hi <= inv_r <= 1 / norm_lo: kappa'(r*) >= d / norm_hi
+                        // for d >= 0 and >= d / norm_lo otherwise (minus the roundings: relative 4e-6 and an absolute crumb).
+                        const float d0 = (float)(4 * mx0 + __float_as_int(bm0.w) + ct), d1 = (float)(4 * mx1 + __float_as_int(bm1.w) + ct);
+                        float lb0 = d0 >= 0.0f ? __fdiv_rn(d0, bm0.y) : __fdiv_rn(d0, bm0.x);
+                        float lb1 = d1 >= 0.0f ? __fdiv_rn(d1, bm1.y) : __fdiv_rn(d1, bm1.x);
+                        const size_t blk = (size_t)((i * TN + col_base) >> 5);
+                        p.seed_lb[blk * p.nq_pad + qi] = lb0 - fabsf(lb0) * 4.0e-6f - 1.0e-3f;     // 32 consecutive queries per warp: one line
+                        p.seed_lb[(blk + 1) * p.nq_pad + qi] = lb1 - fabsf(lb1) * 4.0e-6f - 1.0e-3f;
+                    } else {
+                        const int v0 = bound(thr, ct, bm0), v1 = bound(thr, ct, bm1);
+                        const bool p0 = mx0 >= v0, p1 = mx1 >= v1;
+                        if (__any_sync(0xFFFFFFFFu, p0 || p1)) {
+                            resolve(r, p0, v0, thr, ct, qi, row0, s_minv + ms * TN + col_base, s_mrs + ms * TN + col_base);
+                            resolve(r + 32, p1, v1, thr, ct, qi, row0 + 32u, s_minv + ms * TN + col_base + 32u, s_mrs + ms * TN + col_base + 32u);
                         }
-                        continue;
                     }
-                    // one compare per score against the raw accumulator, OR-ed into two predicates (two dependency chains)
-                    bool some = false, some2 = false;
-#pragma unroll
-                    for (int i4 = 0; i4 < 8; ++i4) {
-                        const int4 u4 = *reinterpret_cast<const int4*>(my_us + 4 * i4);
-                        some |= ((int)r[4 * i4 + 0] >= u4.x);
-                        some2 |= ((int)r[4 * i4 + 1] >= u4.y);
-                        some |= ((int)r[4 * i4 + 2] >= u4.z);
-                        some2 |= ((int)r[4 * i4 + 3] >= u4.w);
+                } else {
+                    uint32_t r[32];
+                    tmem_ld32_issue(taddr, r);
+                    tmem_ld_wait(r);
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_at(acc_empty0 + ab * 8u);
+                    const float4 bm0 = bm_s[0];
+                    const int mx0 = max32(r);
+                    if constexpr (SEED) {
+                        const float d0 = (float)(4 * mx0 + __float_as_int(bm0.w) + ct);
+                        const float lb0 = d0 >= 0.0f ? __fdiv_rn(d0, bm0.y) : __fdiv_rn(d0, bm0.x);
+                        p.seed_lb[(size_t)((i * TN + col_base) >> 5) * p.nq_pad + qi] = lb0 - fabsf(lb0) * 4.0e-6f - 1.0e-3f;
+                    } else {
+                        const int v0 = bound(thr, ct, bm0);
+                        const bool p0 = mx0 >= v0;
+                        if (__any_sync(0xFFFFFFFFu, p0)) resolve(r, p0, v0, thr, ct, qi, row0, s_minv + ms * TN + col_base, s_mrs + ms * TN + col_base);
                     }
-                    if (!__any_sync(0xFFFFFFFFu, (some || some2) && row_ok)) continue;
-                    // some lane passed the pre-test in some column: find which (bounds re-read through an opaque pointer,
-                    // so that the compiler does not keep the 32 bounds of the fast pass alive across the branch)
-                    uint32_t mask = 0;
-                    const int* u_s = my_us;
-                    asm volatile("" : "+l"(u_s));
-#pragma unroll
-                    for (int i4 = 0; i4 < 8; ++i4) {
-                        const int4 u4 = *reinterpret_cast<const int4*>(u_s + 4 * i4);
-                        const int us[4] = {u4.x, u4.y, u4.z, u4.w};
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if ((int)r[4 * i4 + j] >= us[j]) mask |= 1u << (4 * i4 + j);
-                    }
-                    if (!row_ok) mask = 0;
-                    // rare: for every column in which some lane survived the pre-test, those lanes take the exact test
-                    uint32_t any = __reduce_or_sync(0xFFFFFFFFu, mask);
-                    while (any) {
-                        const uint32_t i = (uint32_t)__ffs(any) - 1u;       // warp-uniform
-                        any &= any - 1u;
-                        uint32_t sv = 0;
-                        switch (i) {
-#define PBX_SEL(n) case n: sv = r[n]; break;
-                            PBX_SEL(0) PBX_SEL(1) PBX_SEL(2) PBX_SEL(3) PBX_SEL(4) PBX_SEL(5) PBX_SEL(6) PBX_SEL(7)
-                            PBX_SEL(8) PBX_SEL(9) PBX_SEL(10) PBX_SEL(11) PBX_SEL(12) PBX_SEL(13) PBX_SEL(14) PBX_SEL(15)
-                            PBX_SEL(16) PBX_SEL(17) PBX_SEL(18) PBX_SEL(19) PBX_SEL(20) PBX_SEL(21) PBX_SEL(22) PBX_SEL(23)
-                            PBX_SEL(24) PBX_SEL(25) PBX_SEL(26) PBX_SEL(27) PBX_SEL(28) PBX_SEL(29) PBX_SEL(30) PBX_SEL(31)
-#undef PBX_SEL
-                        }
-                        const uint32_t col = colbase + i;
-                        bool hit = false;
-                        float kf = 0.0f;
-                        if (mask & (1u << i)) {
-                            const int dot_i = 4 * (int)sv + rowterm + s_colterm[col];
-                            kf = __fmul_rn((float)dot_i, inv_r);
-                            hit = kf >= s_thr[col];
-                        }
-                        const uint32_t hb = __ballot_sync(0xFFFFFFFFu, hit);
-                        if (hit) {
-                            const uint32_t pos = staged + (uint32_t)__popc(hb & ((1u << lane) - 1u));
-                            my_key[pos] = make_key64(kf, row);
-                            my_q[pos] = g * QG + col;
-                        }
-                        staged += (uint32_t)__popc(hb);
-                        if (staged >= 32) flush();
-                    }
-                } while (false);
+                }
+                if constexpr (!SEED) {
+                    // staged candidates: complete the flush issued a stage ago, issue the next one when enough are waiting
+                    __syncwarp();
+                    if (*reinterpret_cast<volatile uint32_t*>(my_cnt) >= kBatchStage / 2) { flush_complete(); flush_issue(); }
+                }
             }
+            __syncwarp();                                            // done with this tile's metadata
+            if (lane == 0) mbar_arrive_at(smem_u32(&m_empty[ms]));
         }
-        flush();
+        if (!SEED) flush();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+    if constexpr (CG == 2) cluster_sync_all();          // the pair's MMAs read both shared memories: leave together
+    if (warp == 1) {
+        if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+    }
+}
+
+// ---- starting thresholds from the seed pass: thr[q] = the keep-th largest block bound of query q ---------------------
+struct BatchSeedSelectParams {
+    const float* seed_lb;       // [n_blocks][nq_pad]
+    uint32_t n_blocks, nq_pad, keep;
+    float* thr;                 // [nq_pad]
+};
+
+__global__ void __launch_bounds__(256)
+batch_seed_select_kernel(const BatchSeedSelectParams p) {
+    extern __shared__ __align__(16) unsigned char ssm[];
+    u64* buf = reinterpret_cast<u64*>(ssm);              // [n_blocks] unique keys (ord(lb) << 32 | ~block)
+    __shared__ uint32_t s_cnt;
+    __shared__ u64 s_tau;
+    __shared__ SelectScratch sel;
+    const uint32_t q = blockIdx.x;
+    if (p.n_blocks < p.keep) return;                     // fewer bounds than keep: no threshold (stays -inf)
+    for (uint32_t i = threadIdx.x; i < p.n_blocks; i += blockDim.x) buf[i] = make_key64(__ldg(p.seed_lb + (size_t)i * p.nq_pad + q), i);
+    if (threadIdx.x == 0) { s_cnt = p.n_blocks; s_tau = 0; }
+    __syncthreads();
+    if (p.n_blocks > p.keep) {
+        TopBuf<u64> tb{buf, &s_cnt, &s_tau, p.n_blocks, p.keep};
+        block_select_top(tb, &sel);
+        if (threadIdx.x == 0) p.thr[q] = key64_kappa(s_tau);
+    } else {
+        __shared__ u64 s_min, s_scratch[32];
+        block_min_key(buf, p.n_blocks, &s_min, s_scratch);
+        if (threadIdx.x == 0) p.thr[q] = key64_kappa(s_min);
+    }
 }
 
 // ---- between rounds: cut every query's candidate buffer back to `keep` and tighten its threshold ----------
@@ -527,6 +771,147 @@ batch_tighten_kernel(const BatchTightenParams p) {
     if (threadIdx.x == 0) {
         p.cand_cnt[q] = kept;
         p.thr[q] = key64_kappa(s_tau);                   // every kept key has kappa' >= this
+    }
+}
+
+// ---- batched finalize for keep <= 256: one 256-thread CTA per query, several per SM -------------------------------------
+// The same steps as finalize_kernel (candidate order, bit-exact replay, ORDER BY (dist, image_id), filter, LIMIT,
+// certificate), sized for what a batched query leaves behind: at most `keep` candidates, one per thread.  Every thread
+// replays its candidate row straight from global memory (the rows are random: no staging helps), ranks are counted
+// against shared memory, and the query's own norm fold comes from batch_prep_kernel (QueryHeader.sa).  1024 queries
+// finish in one wave of small CTAs instead of seven waves of one 1024-thread CTA per SM (406 us -> tens of us).
+constexpr uint32_t kBfThreads = 256;
+struct BatchFinalizeParams {
+    ExactLaunch x;              // exact-pass launch template (query 0); the launching CTA offsets the per-query pointers
+    const u64* bcand;           // [nq][bcap] candidate keys (kappa' = dot_i * inv_norm_r, row)
+    const uint32_t* bcnt;       // [nq]
+    const uint32_t* boverflow;  // [nq]
+    uint32_t* bticket;          // zero on entry and on exit
+    uint32_t bcap, nq, keep, k, n, dim, pitch;
+    const uint8_t* rows;
+    const int64_t* ids;
+    const uint8_t* qbytes;      // [nq][pitch]
+    const int16_t* q16;         // [nq][pitch]
+    const QueryHeader* qh;      // [nq] (sa filled by batch_prep_kernel)
+    double max_dist;
+    float margin;
+    pbx_hit* hits;              // [nq][k]
+    uint32_t* count;            // [nq]
+    SearchStatus* status;       // [nq]
+};
+
+__global__ void __launch_bounds__(kBfThreads, 4)
+batch_finalize_kernel(const BatchFinalizeParams p) {
+    extern __shared__ __align__(16) unsigned char bf_sm[];
+    uint8_t* s_qb = bf_sm;                                              // [pitch] raw query bytes
+    int16_t* s_q16 = reinterpret_cast<int16_t*>(bf_sm + p.pitch);       // [pitch] centred query
+    __shared__ u64 s_key[kBfThreads];
+    __shared__ RerankEntry s_ent[kBfThreads];
+    __shared__ float s_lut[256];
+    __shared__ float s_kappa_k, s_kappa_last;
+    __shared__ uint32_t s_pass, s_nonplateau;
+    const uint32_t tid = threadIdx.x, q = blockIdx.x;
+    const uint32_t c = min(min(p.bcnt[q], p.bcap), kBfThreads);         // <= keep after the last batch_tighten
+    const QueryHeader qh = p.qh[q];
+    s_lut[tid] = ref_decode(tid);
+    for (uint32_t i = tid; i < p.pitch / 16; i += blockDim.x) {
+        reinterpret_cast<uint4*>(s_qb)[i] = __ldg(reinterpret_cast<const uint4*>(p.qbytes + (size_t)q * p.pitch) + i);
+        reinterpret_cast<uint4*>(s_q16)[2 * i] = __ldg(reinterpret_cast<const uint4*>(p.q16 + (size_t)q * p.pitch) + 2 * i);
+        reinterpret_cast<uint4*>(s_q16)[2 * i + 1] = __ldg(reinterpret_cast<const uint4*>(p.q16 + (size_t)q * p.pitch) + 2 * i + 1);
+    }
+    u64 key = 0ull;
+    if (tid < c) {
+        const u64 e = p.bcand[(size_t)q * p.bcap + tid];
+        key = make_key64(__fmul_rn(key64_kappa(e), qh.inv_q), key64_row(e));
+    }
+    s_key[tid] = key;
+    if (tid == 0) { s_kappa_k = 0.0f; s_kappa_last = 0.0f; s_pass = 0; s_nonplateau = 0; }
+    __syncthreads();
+    // candidate order by (kappa desc, row asc): what the certificate's two kappas are read from
+    const uint32_t nc = min(c, p.keep);
+    if (tid < c) {
+        uint32_t rank = 0;
+#pragma unroll 8
+        for (uint32_t j = 0; j < c; ++j) rank += (s_key[j] > key) ? 1u : 0u;
+        if (p.k > 0 && rank == p.k - 1 && nc >= p.k) s_kappa_k = key64_kappa(key);
+        if (rank == nc - 1) s_kappa_last = key64_kappa(key);
+        if (rank >= nc) key = 0ull;                                     // beyond keep (cannot happen after the tighten)
+    }
+    // kernel C: bit-exact replay of the reference distance for this thread's candidate
+    float dist = __int_as_float(0x7f800000);
+    int idot = 0, inorm = 0;
+    int64_t id = INT64_MAX;
+    const bool have = tid < c && key != 0ull;
+    if (have) {
+        const uint32_t row = key64_row(key);
+        const ReplayOut ro = replay_row<true>(p.rows + (size_t)row * p.pitch, s_qb, s_q16, p.dim, qh.sum_cq, s_lut);
+        dist = ref_distance(qh.sa, ro.sb, ro.dot);
+        idot = ro.idot; inorm = ro.inorm;
+        id = p.ids[row];
+    }
+    RerankEntry me;
+    me.od = have ? ord_f32(dist) : 0xFFFFFFFFu;
+    me.slot = have ? tid : 0xFFFFFFFFu;
+    me.id = id;
+    s_ent[tid] = me;
+    __syncthreads();
+    // ORDER BY dist ASC (ties by image_id), WHERE dist < ?, LIMIT k   (src/engine.rs:379-381)
+    pbx_hit* hits_g = p.hits + (size_t)q * p.k;
+    if (have) {
+        uint32_t pos = 0;
+#pragma unroll 4
+        for (uint32_t j = 0; j < c; ++j) pos += rerank_before(s_ent[j], me) ? 1u : 0u;
+        const bool ok = (double)dist < p.max_dist;
+        if (ok) atomicAdd(&s_pass, 1u);
+        if (dist < PBX_PLATEAU_DIST) atomicAdd(&s_nonplateau, 1u);
+        if (pos < p.k) {
+            pbx_hit hh;
+            if (ok) { hh.image_id = id; hh.dist = dist; hh.dot = idot; hh.norm2 = inorm; hh.flags = 0; }
+            else { hh.image_id = INT64_MAX; hh.dist = __int_as_float(0x7f800000); hh.dot = 0; hh.norm2 = 0; hh.flags = 0; }
+            hits_g[pos] = hh;
+        }
+    }
+    for (uint32_t i = nc + tid; i < p.k; i += blockDim.x) {
+        pbx_hit hh; hh.image_id = INT64_MAX; hh.dist = __int_as_float(0x7f800000); hh.dot = 0; hh.norm2 = 0; hh.flags = 0;
+        hits_g[i] = hh;
+    }
+    __syncthreads();
+    // certificate, as in finalize_kernel
+    if (tid == 0) {
+        const uint32_t passing = s_pass;
+        p.count[q] = passing < p.k ? passing : p.k;
+        SearchStatus st;
+        st.n_candidates = nc; st.reserved = 0; st.need_exact = 0; st.theta = 0.0f;
+        if (p.n > nc) {
+            const bool plateau_reachable = p.max_dist > (double)PBX_PLATEAU_DIST && s_nonplateau < p.k;
+            const bool separated = (double)s_kappa_last < (double)s_kappa_k - (double)p.margin;
+            if (plateau_reachable) { st.need_exact = 1; st.theta = -__int_as_float(0x7f800000); }
+            else if (!separated) { st.need_exact = 1; st.theta = (float)((double)s_kappa_k - (double)p.margin - 1e-7); }
+        }
+        if (p.boverflow[q] || p.bcnt[q] > kBfThreads) { st.need_exact = 1; st.theta = -__int_as_float(0x7f800000); }   // candidates were dropped
+        p.status[q] = st;
+        // the last CTA to finish tail-launches the exact pass of every query that needs one, one after the other
+        // (they share the scan scratch), from a single thread so that their order is well defined
+        __threadfence();
+        if (atomicAdd(p.bticket, 1u) == gridDim.x - 1) {
+            *p.bticket = 0;
+#ifdef PBX_USE_CDP
+            __threadfence();
+            for (uint32_t qq = 0; qq < p.nq; ++qq) {
+                if (*reinterpret_cast<volatile uint32_t*>(&p.status[qq].need_exact) == 0) continue;
+                ExactLaunch x = p.x;
+                x.scan.q16 += (size_t)qq * p.pitch;
+                x.scan.qbytes += (size_t)qq * p.pitch;
+                x.scan.qh += qq;
+                x.scan.status += qq;
+                x.fin.qbytes += (size_t)qq * p.pitch;
+                x.fin.hits += (size_t)qq * p.k;
+                x.fin.count += qq;
+                x.fin.status += qq;
+                if (!launch_exact_tail(x)) p.count[qq] = PBX_COUNT_EXACT_LAUNCH_FAILED;
+            }
+#endif
+        }
     }
 }
 

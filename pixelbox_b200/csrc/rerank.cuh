@@ -267,8 +267,14 @@ replay_kernel(const ReplayParams p) {
     }
 }
 
+// out_count marker of a query whose exact pass could not be launched from the device (the pending-launch pool was
+// exhausted): the fast-pass hits in the output are NOT certified.  The host-buffer API re-runs the exact pass from the
+// host when it sees it; callers of the device-resident API must treat it as PBX_E_INTERNAL for that query.
+// (PBX_COUNT_EXACT_LAUNCH_FAILED, include/pixelbox_b200.h)
+
 #ifdef PBX_USE_CDP
-__device__ inline void launch_exact_tail(const ExactLaunch& x) {
+// Returns false if either tail launch was refused (cudaGetLastError is part of the device runtime).
+__device__ inline bool launch_exact_tail(const ExactLaunch& x) {
 #define PBX_X_CASE(LL, CC) \
     case LL * CC: scan_kernel<LL, CC, true><<<x.grid, kScanThreads, x.scan_smem, cudaStreamTailLaunch>>>(x.scan); break;
     switch (x.scan.pitch16) {
@@ -283,7 +289,9 @@ __device__ inline void launch_exact_tail(const ExactLaunch& x) {
             break;
     }
 #undef PBX_X_CASE
+    if (cudaGetLastError() != cudaSuccess) return false;
     finalize_exact_kernel<<<1, kFinalThreads, x.fin_smem, cudaStreamTailLaunch>>>(x.fin);
+    return cudaGetLastError() == cudaSuccess;
 }
 #endif
 
@@ -797,7 +805,7 @@ finalize_kernel(const FinalizeParams p) {
             p.tile_counter[0] = 0;                        // chunk scheduler
             p.tile_counter[32] = 0;                       // global bin threshold of the scan
 #ifdef PBX_USE_CDP
-            if (st.need_exact) { __threadfence(); launch_exact_tail(p.x); }
+            if (st.need_exact) { __threadfence(); if (!launch_exact_tail(p.x)) *count_g = PBX_COUNT_EXACT_LAUNCH_FAILED; }
 #endif
         } else {
             // the last CTA to finish tail-launches the exact pass of every query that needs one, one after the
@@ -818,7 +826,7 @@ finalize_kernel(const FinalizeParams p) {
                     x.fin.hits += (size_t)qq * p.k;
                     x.fin.count += qq;
                     x.fin.status += qq;
-                    launch_exact_tail(x);
+                    if (!launch_exact_tail(x)) p.count[qq] = PBX_COUNT_EXACT_LAUNCH_FAILED;
                 }
 #endif
             }

@@ -81,7 +81,11 @@ __global__ void __launch_bounds__(128) umma_test(const __grid_constant__ CUtenso
         mbar_wait(&bar_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // instruction descriptor: c=S32 (2<<4), a,b = u8 (0), K-major both, N>>3 at bit 17, M>>4 at bit 24
+#ifdef SWAP_SIGN      // A = s8 (1 at bit 7), B = u8: the operand roles of the transposed batched kernel (queries are A)
+        const uint32_t idesc = (2u << 4) | (1u << 7) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+#else
         const uint32_t idesc = (2u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+#endif
         for (int ks = 0; ks < K / 32; ++ks) {
             const int sub = ks / 4, koff = (ks % 4) * 32;
             const uint64_t da = make_desc_sw128(sa + sub * M * 128) + (uint64_t)(koff >> 4);
@@ -156,7 +160,11 @@ int main() {
     for (int m = 0; m < M; ++m)
         for (int n = 0; n < N; ++n) {
             int s = 0;
+#ifdef SWAP_SIGN
+            for (int k = 0; k < K; ++k) s += (int)(int8_t)ha[m * K + k] * (int)hb[n * K + k];
+#else
             for (int k = 0; k < K; ++k) s += (int)ha[m * K + k] * (int)hb[n * K + k];
+#endif
             if (s != ho[m * N + n]) { if (bad < 5) printf("mismatch m=%d n=%d want %d got %d\n", m, n, s, ho[m * N + n]); ++bad; }
         }
     printf("umma_i8_test: %s (%ld mismatches of %d)\n", bad ? "FAILED" : "OK", bad, M * N);
