@@ -130,6 +130,16 @@ static uint32_t default_keep(uint32_t k, uint32_t slack) {
     return std::min<uint32_t>(keep, kMaxKeep);
 }
 
+// Candidates per query of the batched path.  Its cost grows with keep (every candidate is a push from the tensor-core
+// epilogue and the thresholds sit at the keep-th best), so the default slack is the smallest that keeps the certificate
+// cheap to pass: max(28, k / 4) rows beyond k (keep = 128 for k = 100).  A certificate that fails -- ties or near-ties
+// around rank k -- costs that query one exact pass, as in the single-query path.
+static uint32_t batch_keep(uint32_t k, uint32_t slack) {
+    if (slack) return std::min<uint32_t>(k + slack, kMaxKeep);
+    const uint32_t keep = (k + std::max<uint32_t>(28u, k / 4u) + 31u) & ~31u;
+    return std::min<uint32_t>(keep, kMaxKeep);
+}
+
 static float certificate_margin(uint32_t dim) {
     // 2 * (eps_d + 5u) + 2^-21 with eps_d = (2d + 1600) u, u = 2^-24   
     return (float)((4.0 * dim + 3232.0) * std::ldexp(1.0, -24));
@@ -713,7 +723,7 @@ static void batch_seed_geometry(uint32_t n, uint32_t tn, uint32_t* n_tiles, uint
 static bool batch_eligible(const pbx_corpus* c, uint32_t nq, uint32_t n, uint32_t k) {
     // per-query candidate buffers hold kBatchCap keys and are cut back to keep = k + slack at the end: the scheme
     // needs keep well below the capacity, larger k loops over the single-query scan
-    const uint32_t keep = default_keep(k, c->slack);
+    const uint32_t keep = batch_keep(k, c->slack);
     BatchPlan bp;
     if (nq < c->batch_min || keep * 8u > kBatchCapLarge || !batch_plan(c, std::min<uint32_t>(nq, 1024u), &bp)) return false;
     uint32_t seed_tiles, seed_step;
@@ -819,7 +829,7 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
     if (!batch_plan(c, nq, &bp)) return fail(PBX_E_INTERNAL, "batched path: no launch shape for pitch %u", pitch);
     int rc = ensure_query_scratch(c, nq);
     if (rc != PBX_OK) return rc;
-    const uint32_t keep = std::min<uint32_t>(default_keep(k, c->slack), kMaxKeep);
+    const uint32_t keep = batch_keep(k, c->slack);
     const uint32_t cap = batch_cap_for(keep);
     rc = ensure_batch_scratch(c, bp.nq_pad, cap);
     if (rc != PBX_OK) return rc;
@@ -866,6 +876,12 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
     sp.seed_lb = c->d_seedlb; sp.n_blocks = seed_tiles * (bp.tn / 32u); sp.nq_pad = bp.nq_pad; sp.keep = keep; sp.thr = c->d_thr;
     batch_seed_select_kernel<<<nq, 256, (size_t)sp.n_blocks * sizeof(u64), s>>>(sp);
     CU_TRY(cudaGetLastError());
+    if (getenv("PBX_BATCH_EXP")) {
+        // experiment: the bare pipeline (TMA, MMA, TMEM loads, max trees; nothing stored) over every tile
+        BatchMmaParams xp = mp;
+        xp.seed_lb = nullptr; xp.n_tiles = (n + bp.tn - 1) / bp.tn; xp.tile_step = 1;
+        CU_TRY((bp.cg == 2 ? launch_batch_mma<2, true>(bp, xp, s) : launch_batch_mma<1, true>(bp, xp, s)));
+    }
     // 3. the main pass over every tile; thresholds keep tightening from the per-query histograms of accepted keys
     mp.n_tiles = (n + bp.tn - 1) / bp.tn; mp.tile_step = 1;
     CU_TRY((bp.cg == 2 ? launch_batch_mma<2, false>(bp, mp, s) : launch_batch_mma<1, false>(bp, mp, s)));
@@ -1490,6 +1506,17 @@ extern "C" int pbx_set_scan_ctas_per_sm(pbx_corpus* c, uint32_t ctas_per_sm) {
     return PBX_OK;
 }
 
+#ifdef PBX_BATCH_PROF
+// experiment builds only (not declared in the public header): per-CTA role counters of batch_mma_kernel
+extern "C" __attribute__((visibility("default"))) int pbx_debug_batch_profile(unsigned long long* out, int reset) {
+    if (out && cudaMemcpyFromSymbol(out, g_batch_prof, sizeof(unsigned long long) * 2048 * 12) != cudaSuccess) return -1;
+    if (reset) {
+        static unsigned long long zeros[2048 * 12];
+        if (cudaMemcpyToSymbol(g_batch_prof, zeros, sizeof(zeros)) != cudaSuccess) return -1;
+    }
+    return 0;
+}
+#endif
 #ifdef PBX_EXP_PROFILE
 extern "C" __attribute__((visibility("default"))) int pbx_debug_fin_profile(long long* out) {
     return cudaMemcpyFromSymbol(out, g_fin_prof, sizeof(long long) * 16) == cudaSuccess ? 0 : -1;

@@ -20,9 +20,9 @@
 // hold both a whole batch of queries and two corpus tiles; a CTA pair splits the tile (128 rows each, fetched by the
 // hardware from both shared memories) and holds 2 x 512 queries, so the corpus is streamed once per batch of 1024.
 //
-// Warp roles per CTA: warp 0 streams corpus K-chunks with TMA into an mbarrier ring; one thread of warp 1 (leader CTA
-// only) issues the MMAs into a ring of TMEM accumulators (2 x 256 columns); warps 2..17 are the epilogue: warp w owns
-// TMEM lanes 32 (w % 4) .. +31 (queries) and a quarter of the columns (rows) of every accumulator.  Survivors of the
+// Warp roles per CTA: warp 8 streams corpus K-chunks with TMA into an mbarrier ring; one thread of warp 9 (leader CTA
+// only) issues the MMAs into a ring of TMEM accumulators (2 x 256 columns); warps 0..7 are the epilogue: warp w owns
+// TMEM lanes 32 (w % 4) .. +31 (queries) and half of the columns (rows) of every accumulator, read 64 at a time.  Survivors of the
 // bound take the exact float test; the few that beat the threshold are staged per warp and pushed to the per-query
 // candidate buffers.  Starting thresholds come from a seed pass of the same kernel over a strided sample of tiles (one
 // bound per query and 32-row block, nothing pushed; batch_seed_select_kernel takes each query's keep-th largest); inside
@@ -36,13 +36,16 @@
 
 namespace pbx {
 
-constexpr int kBatchEpiWarps = 16;           // four per TMEM lane quarter, each takes a quarter of an accumulator's columns
-constexpr int kBatchThreads = 64 + 32 * kBatchEpiWarps;   // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
+constexpr int kBatchEpiWarps = 8;            // two per TMEM lane quarter, each takes half of an accumulator's columns
+constexpr int kBatchThreads = 64 + 32 * kBatchEpiWarps;   // warps 0..7 epilogue, warp 8 TMA producer, warp 9 MMA issuer
+// The two single-thread roles sit on the HIGHEST warp ids: the warp scheduler prefers high warp ids among eligible
+// warps, and an MMA issuer that shares its scheduler with four polling epilogue warps of higher priority starves.
+constexpr int kBatchTmaWarp = kBatchEpiWarps, kBatchMmaWarp = kBatchEpiWarps + 1;
 constexpr int kBatchMaxStages = 8;           // corpus K-chunk ring depth (the host sizes it to the shared memory left)
 constexpr uint32_t kBatchMaxQG = 512;        // resident queries per CTA
 constexpr uint32_t kBatchCap = 4096;         // candidate buffer entries per query (small k)
 constexpr uint32_t kBatchCapLarge = 16384;   // ... for keep > 512 (k = 1000 class)
-constexpr uint32_t kBatchHistBins = 256;     // per-query histogram of accepted keys over kappa in [-1, 1]
+constexpr uint32_t kBatchHistBins = 1024;    // per-query histogram of accepted keys over kappa in [-1, 1]
 constexpr uint32_t kBatchStage = 32;         // staged candidates per epilogue warp
 
 // ---- PTX helpers -------------------------------------------------------------------------------------
@@ -300,7 +303,19 @@ struct BatchMmaParams {
     uint32_t tile_step;         // 1: every tile (MAIN); > 1: a strided sample (SEED)
 };
 
-constexpr uint32_t kBatchMetaSlots = 4;      // ring of per-tile metadata (inv_norm, row_sum, block metadata of the tile's rows)
+#ifdef PBX_BATCH_PROF
+// experiment builds only: per-CTA cycle counters of the three roles
+// [0] producer: wait a_empty  [1] producer: wait m_empty  [2] mma: wait acc_empty  [3] mma: wait a_full  [4] mma: total
+// [5] epi warp 2: wait acc_full  [6] epi: ld  [7] epi: after arrive (process)  [8] epi: wait m_full  [9] epi total  [10] stages
+__device__ unsigned long long g_batch_prof[2048][12];
+#define PBX_BP_T() clock64()
+#define PBX_BP_ADD(i, t0) bp_acc[(i) % 5] += (unsigned long long)(clock64() - (t0))       // register accumulators, written once per role
+#else
+#define PBX_BP_T() 0ll
+#define PBX_BP_ADD(i, t0) do { (void)(t0); } while (0)
+#endif
+static_assert(true, "");
+constexpr uint32_t kBatchMetaSlots = 4;      // (power of two) ring of per-tile metadata (inv_norm, row_sum, block metadata of the tile's rows)
 constexpr uint32_t kBatchScrWords = 36;      // survivor scratch slot: 32 scores + {bound, threshold, colterm, query}
 
 // Dynamic shared memory of batch_mma_kernel after the 1024-byte alignment fix-up; the host sizes the ring with it.
@@ -323,11 +338,13 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
     // the swizzle of TMA and UMMA is a function of the shared-memory address: tiles must sit on 1024-byte boundaries,
     // and dynamic shared memory only starts after the static variables (the host adds 1 KB of slack)
     uint8_t* bsm = bsm_raw + ((1024u - (smem_u32(bsm_raw) & 1023u)) & 1023u);
-    const uint32_t QG = p.qg, KC = p.kc, W = p.w, TN = p.tn;
+    constexpr uint32_t TN = CG == 2 ? 256u : 128u;      // corpus rows per tile = UMMA N: pairs take 256-row tiles (p.tn agrees)
+    constexpr uint32_t NB = TN / CG;                    // corpus rows of a tile in THIS CTA's shared memory (128)
+    constexpr uint32_t AS = 512u / TN;                  // TMEM accumulator ring: 2 x 256 or 4 x 128 columns
+    constexpr uint32_t AS_LOG = AS == 2 ? 1u : 2u;
+    constexpr uint32_t CPS = TN / 128u;                 // 32-column blocks per epilogue warp and accumulator
+    const uint32_t QG = p.qg, KC = p.kc, W = p.w;
     const uint32_t MB = QG / 128u;                      // 128-query blocks = accumulator stages per tile
-    const uint32_t NB = TN / CG;                        // corpus rows of a tile in THIS CTA's shared memory
-    const uint32_t AS = 512u / TN;                      // TMEM accumulator ring: 2 x 256 or 4 x 128 columns
-    const uint32_t CPS = TN / 128u;                     // 32-column blocks per epilogue warp and accumulator
     const uint32_t STAGES = p.stages;
     const uint32_t stage_bytes = NB * W;
     uint8_t* sQ = bsm;                                  // [KC][QG][W]
@@ -346,14 +363,20 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
     __shared__ __align__(8) uint64_t m_full[kBatchMetaSlots], m_empty[kBatchMetaSlots];
     __shared__ uint32_t tmem_base;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: provably warp-uniform, so that the role loops below (executed by whole warps, one
+    // elected lane issues) keep their descriptors and addresses in uniform registers; with per-thread values every
+    // UTCIMMA / UTMALDG is wrapped in an ELECT + R2UR waterfall loop (measured: ~350 cycles per MMA issue instead of ~20)
+    const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+#ifdef PBX_BATCH_PROF
+    unsigned long long bp_acc[5] = {0, 0, 0, 0, 0};
+#endif
     const uint32_t rank = CG == 1 ? 0u : cluster_ctarank();
     const uint32_t cluster_id = blockIdx.x / CG;
     const uint32_t g = cluster_id % p.groups;                                   // query group of this cluster
     const uint32_t ci = cluster_id / p.groups, cstride = (gridDim.x / CG) / p.groups;
     const uint32_t qbase = (g * CG + rank) * QG;                                // first query of this CTA
 
-    if (warp == 1) {
+    if (warp == kBatchMmaWarp) {
         if constexpr (CG == 1) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512u));
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -382,70 +405,97 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base;
 
-    if (warp == 0) {
-        // ===== TMA producer: this CTA's queries (once), its NB rows of every tile, and the tile's row metadata =====
-        if (lane == 0) {
+    if (warp == kBatchTmaWarp) {
+        // ===== TMA producer (whole warp runs the loop, lane 0 issues): this CTA's queries (once), its NB rows of every
+        // tile, and the tile's row / block metadata =====
+        {
             const uint32_t qbox = (QG % 256u) ? 128u : 256u;       // rows per TMA box of the query operand: divides QG
             const uint32_t qfull_l = CG == 1 ? smem_u32(&q_full) : mapa_u32(smem_u32(&q_full), 0);
-            mbar_expect_tx_at(qfull_l, QG * KC * W);
+            if (lane == 0) mbar_expect_tx_at(qfull_l, QG * KC * W);
             for (uint32_t kc = 0; kc < KC; ++kc)
                 for (uint32_t h = 0; h < QG; h += qbox)
-                    tma_load_2d<CG>(sQ + ((size_t)kc * QG + h) * W, &p.map_q, qfull_l, (int)(kc * W), (int)(qbase + h));
-            uint32_t it = 0, ti = 0;
+                    if (lane == 0) tma_load_2d<CG>(sQ + ((size_t)kc * QG + h) * W, &p.map_q, qfull_l, (int)(kc * W), (int)(qbase + h));
+            uint32_t st = 0, ph = 0, ti = 0;
             for (uint32_t i = ci; i < p.n_tiles; i += cstride, ++ti) {
                 const uint32_t t = i * p.tile_step;
                 {
                     // inv_norm / row_sum / block metadata of the tile's TN rows (every CTA of a pair sees all of them):
                     // plain bulk copies into a small ring the epilogue reads in place
-                    const uint32_t ms = ti % kBatchMetaSlots;
-                    mbar_wait(&m_empty[ms], ((ti / kBatchMetaSlots) & 1u) ^ 1u);
-                    mbar_expect_tx_at(smem_u32(&m_full[ms]), TN * 8u + (TN / 32u) * 16u);
-                    bulk_load(s_minv + ms * TN, p.inv_norm + (size_t)t * TN, TN * 4u, &m_full[ms]);
-                    bulk_load(s_mrs + ms * TN, p.row_sum + (size_t)t * TN, TN * 4u, &m_full[ms]);
-                    bulk_load(s_mblk + ms * (TN / 32u), p.blk_meta + ((size_t)t * TN >> 5), (TN / 32u) * 16u, &m_full[ms]);
+                    const uint32_t ms = ti & (kBatchMetaSlots - 1u);
+                    const long long tp0 = PBX_BP_T();
+                    mbar_wait(&m_empty[ms], ((ti >> 2) & 1u) ^ 1u);
+                    PBX_BP_ADD(1, tp0);
+                    if (lane == 0) {
+                        mbar_expect_tx_at(smem_u32(&m_full[ms]), TN * 8u + (TN / 32u) * 16u);
+                        bulk_load(s_minv + ms * TN, p.inv_norm + (size_t)t * TN, TN * 4u, &m_full[ms]);
+                        bulk_load(s_mrs + ms * TN, p.row_sum + (size_t)t * TN, TN * 4u, &m_full[ms]);
+                        bulk_load(s_mblk + ms * (TN / 32u), p.blk_meta + ((size_t)t * TN >> 5), (TN / 32u) * 16u, &m_full[ms]);
+                    }
                 }
-                for (uint32_t kc = 0; kc < KC; ++kc, ++it) {
-                    const uint32_t st = it % STAGES, ph = (it / STAGES) & 1u;
+                for (uint32_t kc = 0; kc < KC; ++kc) {
+                    const long long tp1 = PBX_BP_T();
                     mbar_wait(&a_empty[st], ph ^ 1u);
+                    PBX_BP_ADD(0, tp1);
                     const uint32_t full_l = CG == 1 ? smem_u32(&a_full[st]) : mapa_u32(smem_u32(&a_full[st]), 0);
-                    mbar_expect_tx_at(full_l, stage_bytes);
-                    tma_load_2d<CG>(sA + (size_t)st * stage_bytes, &p.map_rows, full_l, (int)(kc * W), (int)(t * TN + rank * NB));
+                    if (lane == 0) {
+                        mbar_expect_tx_at(full_l, stage_bytes);
+                        tma_load_2d<CG>(sA + (size_t)st * stage_bytes, &p.map_rows, full_l, (int)(kc * W), (int)(t * TN + rank * NB));
+                    }
+                    if (++st == STAGES) { st = 0; ph ^= 1u; }
                 }
             }
+#ifdef PBX_BATCH_PROF
+            if (lane == 0) { g_batch_prof[blockIdx.x][0] += bp_acc[0]; g_batch_prof[blockIdx.x][1] += bp_acc[1]; }
+#endif
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer (one thread; of the pair leader with cta_group::2) =====
-        if (lane == 0 && rank == 0) {
+    } else if (warp == kBatchMmaWarp) {
+        // ===== MMA issuer (the whole warp of the pair leader runs the loop, lane 0 issues) =====
+        if (rank == 0) {
             // instruction descriptor: D = s32 (2 << 4), A = s8 (1 at bit 7), B = u8 (0 at bit 10), both K-major,
             // N >> 3 at bit 17, M >> 4 at bit 24
             const uint32_t idesc = (2u << 4) | (1u << 7) | ((TN >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
             const uint32_t ksteps = W / 32u;
             mbar_wait(&q_full, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t it0 = 0, acc_it = 0;
+            uint32_t st0 = 0, ph0 = 0, acc_it = 0;
+            const uint64_t da0 = umma_desc_k(sQ, W), db0 = umma_desc_k(sA, W);
+            const uint32_t a_kc = (QG * W) >> 4, a_mb = (128u * W) >> 4, b_st = stage_bytes >> 4;    // descriptor steps (16-byte units)
+            const long long tm_all = PBX_BP_T();
             for (uint32_t i = ci; i < p.n_tiles; i += cstride) {
+                uint32_t st = st0, ph = ph0;
                 for (uint32_t mb = 0; mb < MB; ++mb, ++acc_it) {
-                    const uint32_t ab = acc_it % AS, par = (acc_it / AS) & 1u;
+                    const uint32_t ab = acc_it & (AS - 1u), par = (acc_it >> AS_LOG) & 1u;
+                    const long long tm0 = PBX_BP_T();
                     mbar_wait(&acc_empty[ab], par ^ 1u);                          // the epilogues have drained its previous use
+                    PBX_BP_ADD(2, tm0);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t d_tmem = tmem + ab * TN;
+                    st = st0; ph = ph0;
                     for (uint32_t kc = 0; kc < KC; ++kc) {
-                        const uint32_t itk = it0 + kc;
-                        const uint32_t st = itk % STAGES, ph = (itk / STAGES) & 1u;
                         if (mb == 0) {
+                            const long long tm1 = PBX_BP_T();
                             mbar_wait(&a_full[st], ph);
+                            PBX_BP_ADD(3, tm1);
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         }
-                        const uint64_t da = umma_desc_k(sQ + ((size_t)kc * QG + (size_t)mb * 128u) * W, W);
-                        const uint64_t db = umma_desc_k(sA + (size_t)st * stage_bytes, W);
-                        for (uint32_t ks = 0; ks < ksteps; ++ks)
-                            umma_i8<CG>(d_tmem, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, (kc | ks) ? 1u : 0u);
-                        if (mb == MB - 1) umma_commit<CG>(&a_empty[st]);           // the stage is free once these MMAs retire
+                        const uint64_t da = da0 + (uint64_t)(kc * a_kc + mb * a_mb), db = db0 + (uint64_t)(st * b_st);
+                        if (lane == 0) {
+                            for (uint32_t ks = 0; ks < ksteps; ++ks)
+                                umma_i8<CG>(d_tmem, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, (kc | ks) ? 1u : 0u);
+                            if (mb == MB - 1) umma_commit<CG>(&a_empty[st]);       // the stage is free once these MMAs retire
+                        }
+                        __syncwarp();
+                        if (++st == STAGES) { st = 0; ph ^= 1u; }
                     }
-                    umma_commit<CG>(&acc_full[ab]);
+                    if (lane == 0) umma_commit<CG>(&acc_full[ab]);
+                    __syncwarp();
                 }
-                it0 += KC;
+                st0 = st; ph0 = ph;
             }
+            PBX_BP_ADD(4, tm_all);
+#ifdef PBX_BATCH_PROF
+            if (lane == 0) { g_batch_prof[blockIdx.x][2] += bp_acc[2]; g_batch_prof[blockIdx.x][3] += bp_acc[3]; g_batch_prof[blockIdx.x][4] += bp_acc[4]; }
+#endif
         }
     } else {
         // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 (a hardware rule) = 32 queries of every 128-query block,
@@ -453,10 +503,11 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
         // Everything per-query or per-row is re-read from shared memory where it is used: the loop carries almost no
         // state besides the scores, because a spilled register costs an L2 round trip here (the L1 that would catch it
         // is the few KB the shared-memory carve-out leaves). =====
-        const uint32_t e = (uint32_t)warp - 2u;
+        const uint32_t e = (uint32_t)warp;
         const uint32_t quarter = (uint32_t)warp & 3u;
-        const uint32_t slice = e >> 2;                                // 0..3
-        const uint32_t cols_per_slice = TN / 4u;
+        const uint32_t slice = e >> 2;                                // 0 or 1
+        constexpr uint32_t cols_per_slice = TN / 2u;                  // 128 (pairs) or 64 columns, read 64 at a time
+        constexpr uint32_t HALVES = cols_per_slice / 64u;
         const uint32_t col_base = slice * cols_per_slice;
         uint32_t tile_iter = 0, acc_it = 0;
         const int dterm = -255 * (int)p.dim;
@@ -516,27 +567,30 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
             for (uint32_t j = ci % cstride + e * cstride; j < QG; j += kBatchEpiWarps * cstride) {     // warp-uniform
                 const uint32_t qi = qbase + j;
                 if (!(s_invq[j] > 0.0f)) continue;
-                const uint4* hp = reinterpret_cast<const uint4*>(p.bhist + (size_t)qi * kBatchHistBins);
-                const uint4 va = __ldcg(hp + lane), vb = __ldcg(hp + 32 + lane);        // bins 4 lane .. +3 and 128 + 4 lane .. +3
-                const uint32_t hb[4] = {vb.x, vb.y, vb.z, vb.w}, ha[4] = {va.x, va.y, va.z, va.w};
-                const uint32_t sum_b = hb[0] + hb[1] + hb[2] + hb[3], sum_a = ha[0] + ha[1] + ha[2] + ha[3];
-                // entries in higher bins than this lane's: upper half first (lanes hold ascending bins)
-                uint32_t incl_b = sum_b, incl_a = sum_a;
+                // lane l holds bins [l * PER, (l + 1) * PER): a suffix scan over lanes, then inside the crossing lane
+                constexpr uint32_t PER = kBatchHistBins / 32u;
+                const uint4* hp = reinterpret_cast<const uint4*>(p.bhist + (size_t)qi * kBatchHistBins + (size_t)lane * PER);
+                uint32_t h[PER];
+#pragma unroll
+                for (uint32_t i4 = 0; i4 < PER / 4u; ++i4) {
+                    const uint4 v4 = __ldcg(hp + i4);
+                    h[4 * i4] = v4.x; h[4 * i4 + 1] = v4.y; h[4 * i4 + 2] = v4.z; h[4 * i4 + 3] = v4.w;
+                }
+                uint32_t mine = 0;
+#pragma unroll
+                for (uint32_t i = 0; i < PER; ++i) mine += h[i];
+                uint32_t incl = mine;
 #pragma unroll
                 for (int off = 1; off < 32; off <<= 1) {
-                    const uint32_t xb = __shfl_down_sync(0xFFFFFFFFu, incl_b, off), xa = __shfl_down_sync(0xFFFFFFFFu, incl_a, off);
-                    if (lane + off < 32) { incl_b += xb; incl_a += xa; }
+                    const uint32_t x = __shfl_down_sync(0xFFFFFFFFu, incl, off);
+                    if (lane + off < 32) incl += x;
                 }
-                const uint32_t total_b = __shfl_sync(0xFFFFFFFFu, incl_b, 0);
-                const uint32_t above_b = incl_b - sum_b, above_a = total_b + incl_a - sum_a;
+                const uint32_t above = incl - mine;                      // entries in higher bins than this lane's
                 int bstar = -1;
-                {
-                    uint32_t run = above_b;
+                if (above < p.keep && above + mine >= p.keep) {
+                    uint32_t run = above;
 #pragma unroll
-                    for (int i = 3; i >= 0; --i) { run += hb[i]; if (bstar < 0 && above_b < p.keep && run >= p.keep) bstar = 128 + 4 * lane + i; }
-                    run = above_a;
-#pragma unroll
-                    for (int i = 3; i >= 0; --i) { run += ha[i]; if (bstar < 0 && above_a < p.keep && run >= p.keep) bstar = 4 * lane + i; }
+                    for (int i = (int)PER - 1; i >= 0; --i) { run += h[i]; if (bstar < 0 && run >= p.keep) bstar = lane * (int)PER + i; }
                 }
                 bstar = __reduce_max_sync(0xFFFFFFFFu, bstar);
                 if (bstar > 0 && lane == 0) {
@@ -555,7 +609,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                 }
             }
             asm volatile("bar.sync 1, %0;" ::"r"(32 * kBatchEpiWarps) : "memory");       // the epilogue warps only
-            for (uint32_t j = (uint32_t)threadIdx.x - 64u; j < QG; j += 32u * kBatchEpiWarps) {
+            for (uint32_t j = (uint32_t)threadIdx.x; j < QG; j += 32u * kBatchEpiWarps) {
                 const float live = *reinterpret_cast<volatile float*>(p.thr_live + qbase + j);
                 if (live > s_thr[j]) s_thr[j] = live;
             }
@@ -626,32 +680,48 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
             }
         };
 
+#ifdef PBX_BATCH_PROF
+        unsigned long long bp_stages = 0;
+        auto g_prof_stage = [&]() { bp_stages += 1; };
+        const long long te_all = clock64();
+#else
+        auto g_prof_stage = []() {};
+#endif
         for (uint32_t i = ci; i < p.n_tiles; i += cstride, ++tile_iter) {
             const uint32_t t = i * p.tile_step;
             // refresh points: every tile at first (the starting thresholds are loose), then ever more rarely
             if (!SEED && tile_iter >= 1 && (tile_iter <= 8 || (tile_iter & (tile_iter - 1)) == 0 || (tile_iter & 31u) == 0)) refresh();
-            const uint32_t ms = tile_iter % kBatchMetaSlots;
-            mbar_wait(&m_full[ms], (tile_iter / kBatchMetaSlots) & 1u);             // this tile's row / block metadata has landed
-            const float4* bm_s = s_mblk + ms * (TN / 32u) + (col_base >> 5);
+            const uint32_t ms = tile_iter & (kBatchMetaSlots - 1u);
+            const long long te8 = PBX_BP_T();
+            mbar_wait(&m_full[ms], (tile_iter >> 2) & 1u);             // this tile's row / block metadata has landed
+            if (threadIdx.x == 0) PBX_BP_ADD(8, te8);
             for (uint32_t mb = 0; mb < MB; ++mb, ++acc_it) {
-                const uint32_t ab = acc_it % AS;
+                const uint32_t ab = acc_it & (AS - 1u);
                 const uint32_t j = mb * 128u + quarter * 32u + (uint32_t)lane;      // this lane's query in the block
                 const uint32_t qi = qbase + j;
                 const float thr = fminf(fmaxf(s_thr[j], -1.0e30f), 1.0e30f);
                 const int ct = s_colterm[j];
-                mbar_wait(&acc_full[ab], (acc_it / AS) & 1u);
+                const long long te5 = PBX_BP_T();
+                mbar_wait(&acc_full[ab], (acc_it >> AS_LOG) & 1u);
+                if (threadIdx.x == 0) { PBX_BP_ADD(5, te5); g_prof_stage(); }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t taddr = tmem + ((quarter * 32u) << 16) + ab * TN + col_base;
-                const uint32_t row0 = t * TN + col_base;
-                if (CPS == 2) {
+#pragma unroll 1
+                for (uint32_t hf = 0; hf < HALVES; ++hf) {             // 64 columns = two 32-row blocks at a time
+                    const uint32_t col0 = col_base + 64u * hf, row0 = t * TN + col0;
                     uint32_t r[64];
-                    tmem_ld64_issue(taddr, r);
+                    const long long te6b = PBX_BP_T();
+                    tmem_ld64_issue(taddr + 64u * hf, r);
                     tmem_ld_wait64(r);
-                    // the scores are in registers: hand the accumulator back to the MMA thread before looking at them
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_at(acc_empty0 + ab * 8u);
-                    const float4 bm0 = bm_s[0], bm1 = bm_s[1];
+                    if (hf == HALVES - 1) {
+                        // the last scores are in registers: hand the accumulator back to the MMA thread before looking at them
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_at(acc_empty0 + ab * 8u);
+                    }
+                    if (threadIdx.x == 0) PBX_BP_ADD(6, te6b);
+                    const long long te7 = PBX_BP_T();
+                    const float4 bm0 = s_mblk[ms * (TN / 32u) + (col0 >> 5)], bm1 = s_mblk[ms * (TN / 32u) + (col0 >> 5) + 1u];
                     const int mx0 = max32(r), mx1 = max32(r + 32);
                     if constexpr (SEED) {
                         // The block's best raw score belongs to a real row r* with dot_i = 4 S + rowterm + colterm >= 4 mx + rt_min
@@ -660,35 +730,24 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                         const float d0 = (float)(4 * mx0 + __float_as_int(bm0.w) + ct), d1 = (float)(4 * mx1 + __float_as_int(bm1.w) + ct);
                         float lb0 = d0 >= 0.0f ? __fdiv_rn(d0, bm0.y) : __fdiv_rn(d0, bm0.x);
                         float lb1 = d1 >= 0.0f ? __fdiv_rn(d1, bm1.y) : __fdiv_rn(d1, bm1.x);
-                        const size_t blk = (size_t)((i * TN + col_base) >> 5);
-                        p.seed_lb[blk * p.nq_pad + qi] = lb0 - fabsf(lb0) * 4.0e-6f - 1.0e-3f;     // 32 consecutive queries per warp: one line
-                        p.seed_lb[(blk + 1) * p.nq_pad + qi] = lb1 - fabsf(lb1) * 4.0e-6f - 1.0e-3f;
+                        const size_t blk = (size_t)((i * TN + col0) >> 5);
+                        if (p.seed_lb) {                                  // (null only in the pipeline-rate experiment, PBX_BATCH_EXP)
+                            p.seed_lb[blk * p.nq_pad + qi] = lb0 - fabsf(lb0) * 4.0e-6f - 1.0e-3f;     // 32 consecutive queries per warp: one line
+                            p.seed_lb[(blk + 1) * p.nq_pad + qi] = lb1 - fabsf(lb1) * 4.0e-6f - 1.0e-3f;
+                        }
                     } else {
-                        const int v0 = bound(thr, ct, bm0), v1 = bound(thr, ct, bm1);
-                        const bool p0 = mx0 >= v0, p1 = mx1 >= v1;
+                        // one bound for the 64 rows from the union of the two blocks' ranges
+                        float4 bm;
+                        bm.x = fminf(bm0.x, bm1.x); bm.y = fmaxf(bm0.y, bm1.y);
+                        bm.z = __int_as_float(max(__float_as_int(bm0.z), __float_as_int(bm1.z))); bm.w = 0.0f;
+                        const int v = bound(thr, ct, bm);
+                        const bool p0 = mx0 >= v, p1 = mx1 >= v;
                         if (__any_sync(0xFFFFFFFFu, p0 || p1)) {
-                            resolve(r, p0, v0, thr, ct, qi, row0, s_minv + ms * TN + col_base, s_mrs + ms * TN + col_base);
-                            resolve(r + 32, p1, v1, thr, ct, qi, row0 + 32u, s_minv + ms * TN + col_base + 32u, s_mrs + ms * TN + col_base + 32u);
+                            resolve(r, p0, v, thr, ct, qi, row0, s_minv + ms * TN + col0, s_mrs + ms * TN + col0);
+                            resolve(r + 32, p1, v, thr, ct, qi, row0 + 32u, s_minv + ms * TN + col0 + 32u, s_mrs + ms * TN + col0 + 32u);
                         }
                     }
-                } else {
-                    uint32_t r[32];
-                    tmem_ld32_issue(taddr, r);
-                    tmem_ld_wait(r);
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_at(acc_empty0 + ab * 8u);
-                    const float4 bm0 = bm_s[0];
-                    const int mx0 = max32(r);
-                    if constexpr (SEED) {
-                        const float d0 = (float)(4 * mx0 + __float_as_int(bm0.w) + ct);
-                        const float lb0 = d0 >= 0.0f ? __fdiv_rn(d0, bm0.y) : __fdiv_rn(d0, bm0.x);
-                        p.seed_lb[(size_t)((i * TN + col_base) >> 5) * p.nq_pad + qi] = lb0 - fabsf(lb0) * 4.0e-6f - 1.0e-3f;
-                    } else {
-                        const int v0 = bound(thr, ct, bm0);
-                        const bool p0 = mx0 >= v0;
-                        if (__any_sync(0xFFFFFFFFu, p0)) resolve(r, p0, v0, thr, ct, qi, row0, s_minv + ms * TN + col_base, s_mrs + ms * TN + col_base);
-                    }
+                    if (threadIdx.x == 0) PBX_BP_ADD(7, te7);
                 }
                 if constexpr (!SEED) {
                     // staged candidates: complete the flush issued a stage ago, issue the next one when enough are waiting
@@ -700,11 +759,18 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
             if (lane == 0) mbar_arrive_at(smem_u32(&m_empty[ms]));
         }
         if (!SEED) flush();
+#ifdef PBX_BATCH_PROF
+        if (threadIdx.x == 0) {
+            g_batch_prof[blockIdx.x][9] += (unsigned long long)(clock64() - te_all);
+            g_batch_prof[blockIdx.x][5] += bp_acc[0]; g_batch_prof[blockIdx.x][6] += bp_acc[1]; g_batch_prof[blockIdx.x][7] += bp_acc[2];
+            g_batch_prof[blockIdx.x][8] += bp_acc[3]; g_batch_prof[blockIdx.x][10] += bp_stages;
+        }
+#endif
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if constexpr (CG == 2) cluster_sync_all();          // the pair's MMAs read both shared memories: leave together
-    if (warp == 1) {
+    if (warp == kBatchMmaWarp) {
         if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
         else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
     }

@@ -67,7 +67,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 // CG = cta_group (1 or 2), NT = UMMA N (total), KB = K bytes per tile (multiple of 128), SWAP = A is s8 and B u8.
 // cta_group::2: UMMA M = 256 (128 rows of A per CTA), each CTA holds NT / 2 rows of B.
 template <int CG, int NT, int KB, bool SWAP>
-__global__ void __launch_bounds__(128) peak_kernel(int iters, unsigned long long* cycles) {
+__global__ void __launch_bounds__(640) peak_kernel(int iters, unsigned long long* cycles) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     constexpr int KC = KB / 128;
@@ -99,6 +99,31 @@ __global__ void __launch_bounds__(128) peak_kernel(int iters, unsigned long long
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base;
     const bool leader = CG == 1 || cluster_ctarank() == 0;
+    __shared__ volatile int stop_flag;
+    if (threadIdx.x == 0) stop_flag = 0;
+    __syncthreads();
+    if (warp >= 4) {
+        // contention warps: read the accumulators with tcgen05.ld.32x32b.x32 as fast as they can until the MMA loop ends
+        unsigned acc = 0;
+        const uint32_t lane_base = ((uint32_t)(warp & 3) * 32u) << 16;
+        uint32_t c = (uint32_t)(warp >> 2) * 64u;
+        while (!stop_flag) {
+            uint32_t r[32];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                  "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                  "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                  "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(tmem + lane_base + (c & 511u)));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            acc ^= r[0] ^ r[31];
+            c += 32;
+        }
+        if (acc == 0x12345u) cycles[0] = acc;
+    }
     if (threadIdx.x == 0 && leader) {
         const uint32_t idesc = (2u << 4) | (SWAP ? (1u << 7) : (1u << 10)) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
         const long long t0 = clock64();
@@ -119,7 +144,9 @@ __global__ void __launch_bounds__(128) peak_kernel(int iters, unsigned long long
             if (it >= STAGES) mbar_wait(&bars[s], ((it / STAGES) - 1) & 1);
         }
         cycles[blockIdx.x] = (unsigned long long)(clock64() - t0);
+        stop_flag = 1;
     }
+    if constexpr (CG == 2) { if (!leader && threadIdx.x == 0) { /* the peer's readers stop when the pair leaves the loop */ } }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if constexpr (CG == 2) cluster_sync_all();
@@ -130,7 +157,7 @@ __global__ void __launch_bounds__(128) peak_kernel(int iters, unsigned long long
 }
 
 template <int CG, int NT, int KB, bool SWAP>
-static double run(const char* name, int iters, int sms) {
+static double run(const char* name, int iters, int sms, int extra_warps = 0) {
     constexpr int KC = KB / 128, NB = NT / CG;
     const size_t smem = (size_t)KC * (128 + NB) * 128 + 1024;
     auto kern = peak_kernel<CG, NT, KB, SWAP>;
@@ -140,7 +167,7 @@ static double run(const char* name, int iters, int sms) {
     CK(cudaMemset(dcyc, 0, sizeof(unsigned long long) * sms));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)sms);
-    cfg.blockDim = dim3(128);
+    cfg.blockDim = dim3(128 + 32 * extra_warps);
     cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -162,9 +189,9 @@ static double run(const char* name, int iters, int sms) {
     // every accumulator tile: (128 * CG) x NT x KB MACs per pair of CG CTAs, i.e. 128 x NT x KB per CTA
     const double ops = 2.0 * 128.0 * NT * KB * (double)iters * sms;
     const double tops = ops / (best * 1e-3) / 1e12;
-    printf("{\"shape\": \"%s\", \"cta_group\": %d, \"umma_m\": %d, \"umma_n\": %d, \"k_bytes\": %d, \"a_s8_b_u8\": %s, \"ms\": %.4f, "
+    printf("{\"ldtm_warps\": %d, \"shape\": \"%s\", \"cta_group\": %d, \"umma_m\": %d, \"umma_n\": %d, \"k_bytes\": %d, \"a_s8_b_u8\": %s, \"ms\": %.4f, "
            "\"int8_tops\": %.1f, \"cycles_per_tile\": %.1f, \"macs_per_clk_per_sm\": %.0f}\n",
-           name, CG, 128 * CG, NT, KB, SWAP ? "true" : "false", best, tops, (double)cyc / iters, 128.0 * NT * KB / ((double)cyc / iters));
+           extra_warps, name, CG, 128 * CG, NT, KB, SWAP ? "true" : "false", best, tops, (double)cyc / iters, 128.0 * NT * KB / ((double)cyc / iters));
     fflush(stdout);
     cudaFree(dcyc);
     return tops;
@@ -183,6 +210,7 @@ int main(int argc, char** argv) {
     run<1, 128, 512, true>("cg1 128x128 s8*u8 k512", iters / 2, sms);
     run<1, 192, 256, true>("cg1 128x192 s8*u8", iters / 2, sms);
     if (argc > 2) {
+        run<1, 256, 256, true>("cg1 128x256 s8*u8 + ldtm", iters / 2, sms, 16);
         run<2, 256, 256, true>("cg2 256x256 s8*u8", iters / 2, sms);
         run<2, 128, 256, true>("cg2 256x128 s8*u8", iters, sms);
     }
