@@ -291,7 +291,7 @@ static cudaError_t init_kernel_attributes() {
     if (e == cudaSuccess) e = allow_smem(batch_mma_kernel<1, true>, kBatchSmemLimit);
     if (e == cudaSuccess) e = allow_smem(batch_mma_kernel<2, false>, kBatchSmemLimit);
     if (e == cudaSuccess) e = allow_smem(batch_mma_kernel<2, true>, kBatchSmemLimit);
-    if (e == cudaSuccess) e = allow_smem(batch_finalize_kernel, (size_t)PBX_MAX_DIM * 3);
+    if (e == cudaSuccess) e = allow_smem(batch_finalize_kernel, batch_finalize_smem(1024));
     if (e == cudaSuccess) e = allow_smem(batch_seed_select_kernel, (size_t)kBatchSeedTiles * 8u * sizeof(u64));
     if (e == cudaSuccess) e = allow_smem(batch_tighten_kernel, kBatchCapLarge * sizeof(u64));
     if (e == cudaSuccess) e = allow_smem(finalize_exact_kernel, fin_cap);
@@ -900,7 +900,7 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
         fp.rows = c->d_rows; fp.ids = c->d_ids; fp.qbytes = c->d_qbytes; fp.q16 = c->d_q16; fp.qh = c->d_qh;
         fp.max_dist = max_dist; fp.margin = certificate_margin(c->dim);
         fp.hits = d_hits; fp.count = d_count; fp.status = c->d_status;
-        batch_finalize_kernel<<<nq, kBfThreads, (size_t)pitch * 3, s>>>(fp);
+        batch_finalize_kernel<<<nq, (keep + 31u) & ~31u, batch_finalize_smem(pitch), s>>>(fp);
         CU_TRY(cudaGetLastError());
     } else {
         const uint32_t chunk = kFinalThreads;

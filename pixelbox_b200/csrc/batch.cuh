@@ -36,7 +36,12 @@
 
 namespace pbx {
 
-constexpr int kBatchEpiWarps = 8;            // two per TMEM lane quarter, each takes half of an accumulator's columns
+#ifndef PBX_BATCH_EPI_WARPS
+#define PBX_BATCH_EPI_WARPS 16
+#endif
+constexpr int kBatchEpiWarps = PBX_BATCH_EPI_WARPS;   // 16: four per TMEM lane quarter, a quarter of an accumulator's columns each, read 32
+                                                      // at a time (<= 96 registers); 8: two per quarter, 64 at a time (up to 168 registers).
+                                                      // Measured at 10M x 256 x 1024: 2.44 ms with 16 warps, 2.64 ms with 8.
 constexpr int kBatchThreads = 64 + 32 * kBatchEpiWarps;   // warps 0..7 epilogue, warp 8 TMA producer, warp 9 MMA issuer
 // The two single-thread roles sit on the HIGHEST warp ids: the warp scheduler prefers high warp ids among eligible
 // warps, and an MMA issuer that shares its scheduler with four polling epilogue warps of higher priority starves.
@@ -183,6 +188,11 @@ __device__ __forceinline__ void tmem_ld_wait64(uint32_t (&r)[64]) {
                    "+r"(r[55]), "+r"(r[56]), "+r"(r[57]), "+r"(r[58]), "+r"(r[59]), "+r"(r[60]), "+r"(r[61]), "+r"(r[62]), "+r"(r[63])
                  :: "memory");
 }
+// overloads by register count
+__device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32_issue(taddr, r); }
+__device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t (&r)[64]) { tmem_ld64_issue(taddr, r); }
+__device__ __forceinline__ void tmem_ld_done(uint32_t (&r)[32]) { tmem_ld_wait(r); }
+__device__ __forceinline__ void tmem_ld_done(uint32_t (&r)[64]) { tmem_ld_wait64(r); }
 __device__ __forceinline__ int max3(int a, int b, int c) { return max(max(a, b), c); }      // VIMNMX3 on sm_100
 
 // ---- per-32-row block metadata (load time): what the epilogue's one-compare test needs from the rows --------------------
@@ -505,9 +515,11 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
         // is the few KB the shared-memory carve-out leaves). =====
         const uint32_t e = (uint32_t)warp;
         const uint32_t quarter = (uint32_t)warp & 3u;
-        const uint32_t slice = e >> 2;                                // 0 or 1
-        constexpr uint32_t cols_per_slice = TN / 2u;                  // 128 (pairs) or 64 columns, read 64 at a time
-        constexpr uint32_t HALVES = cols_per_slice / 64u;
+        const uint32_t slice = e >> 2;
+        constexpr uint32_t cols_per_slice = TN / (kBatchEpiWarps / 4);     // columns of this warp in every accumulator
+        constexpr uint32_t WIDTH = kBatchEpiWarps == 8 ? 64u : 32u;        // columns per tcgen05.ld (the live score registers)
+        constexpr uint32_t STEPS = cols_per_slice / WIDTH;
+        static_assert(cols_per_slice % WIDTH == 0 && STEPS >= 1, "epilogue column split");
         const uint32_t col_base = slice * cols_per_slice;
         uint32_t tile_iter = 0, acc_it = 0;
         const int dterm = -255 * (int)p.dim;
@@ -707,13 +719,13 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t taddr = tmem + ((quarter * 32u) << 16) + ab * TN + col_base;
 #pragma unroll 1
-                for (uint32_t hf = 0; hf < HALVES; ++hf) {             // 64 columns = two 32-row blocks at a time
-                    const uint32_t col0 = col_base + 64u * hf, row0 = t * TN + col0;
-                    uint32_t r[64];
+                for (uint32_t hf = 0; hf < STEPS; ++hf) {              // WIDTH columns = one or two 32-row blocks at a time
+                    const uint32_t col0 = col_base + WIDTH * hf, row0 = t * TN + col0;
+                    uint32_t r[WIDTH];
                     const long long te6b = PBX_BP_T();
-                    tmem_ld64_issue(taddr + 64u * hf, r);
-                    tmem_ld_wait64(r);
-                    if (hf == HALVES - 1) {
+                    tmem_ld_issue(taddr + WIDTH * hf, r);
+                    tmem_ld_done(r);
+                    if (hf == STEPS - 1) {
                         // the last scores are in registers: hand the accumulator back to the MMA thread before looking at them
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                         __syncwarp();
@@ -721,30 +733,33 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                     }
                     if (threadIdx.x == 0) PBX_BP_ADD(6, te6b);
                     const long long te7 = PBX_BP_T();
-                    const float4 bm0 = s_mblk[ms * (TN / 32u) + (col0 >> 5)], bm1 = s_mblk[ms * (TN / 32u) + (col0 >> 5) + 1u];
-                    const int mx0 = max32(r), mx1 = max32(r + 32);
+                    const float4 bm0 = s_mblk[ms * (TN / 32u) + (col0 >> 5)];
+                    const float4 bm1 = WIDTH == 64 ? s_mblk[ms * (TN / 32u) + (col0 >> 5) + 1u] : bm0;
+                    const int mx0 = max32(r), mx1 = WIDTH == 64 ? max32(r + WIDTH - 32) : mx0;
                     if constexpr (SEED) {
                         // The block's best raw score belongs to a real row r* with dot_i = 4 S + rowterm + colterm >= 4 mx + rt_min
                         // + ct =: d and kappa' = fl(fl(dot_i) * inv_r), 1 / norm_hi <= inv_r <= 1 / norm_lo: kappa'(r*) >= d / norm_hi
                         // for d >= 0 and >= d / norm_lo otherwise (minus the roundings: relative 4e-6 and an absolute crumb).
-                        const float d0 = (float)(4 * mx0 + __float_as_int(bm0.w) + ct), d1 = (float)(4 * mx1 + __float_as_int(bm1.w) + ct);
-                        float lb0 = d0 >= 0.0f ? __fdiv_rn(d0, bm0.y) : __fdiv_rn(d0, bm0.x);
-                        float lb1 = d1 >= 0.0f ? __fdiv_rn(d1, bm1.y) : __fdiv_rn(d1, bm1.x);
                         const size_t blk = (size_t)((i * TN + col0) >> 5);
-                        if (p.seed_lb) {                                  // (null only in the pipeline-rate experiment, PBX_BATCH_EXP)
-                            p.seed_lb[blk * p.nq_pad + qi] = lb0 - fabsf(lb0) * 4.0e-6f - 1.0e-3f;     // 32 consecutive queries per warp: one line
-                            p.seed_lb[(blk + 1) * p.nq_pad + qi] = lb1 - fabsf(lb1) * 4.0e-6f - 1.0e-3f;
+                        const float d0 = (float)(4 * mx0 + __float_as_int(bm0.w) + ct);
+                        const float lb0 = d0 >= 0.0f ? __fdiv_rn(d0, bm0.y) : __fdiv_rn(d0, bm0.x);
+                        if (p.seed_lb) p.seed_lb[blk * p.nq_pad + qi] = lb0 - fabsf(lb0) * 4.0e-6f - 1.0e-3f;   // 32 queries per warp: one line
+                        if constexpr (WIDTH == 64) {                      // (seed_lb is null only in the pipeline-rate experiment)
+                            const float d1 = (float)(4 * mx1 + __float_as_int(bm1.w) + ct);
+                            const float lb1 = d1 >= 0.0f ? __fdiv_rn(d1, bm1.y) : __fdiv_rn(d1, bm1.x);
+                            if (p.seed_lb) p.seed_lb[(blk + 1) * p.nq_pad + qi] = lb1 - fabsf(lb1) * 4.0e-6f - 1.0e-3f;
                         }
                     } else {
-                        // one bound for the 64 rows from the union of the two blocks' ranges
+                        // one bound for the WIDTH rows from the union of the blocks' ranges
                         float4 bm;
                         bm.x = fminf(bm0.x, bm1.x); bm.y = fmaxf(bm0.y, bm1.y);
                         bm.z = __int_as_float(max(__float_as_int(bm0.z), __float_as_int(bm1.z))); bm.w = 0.0f;
                         const int v = bound(thr, ct, bm);
-                        const bool p0 = mx0 >= v, p1 = mx1 >= v;
+                        const bool p0 = mx0 >= v, p1 = WIDTH == 64 && mx1 >= v;
                         if (__any_sync(0xFFFFFFFFu, p0 || p1)) {
                             resolve(r, p0, v, thr, ct, qi, row0, s_minv + ms * TN + col0, s_mrs + ms * TN + col0);
-                            resolve(r + 32, p1, v, thr, ct, qi, row0 + 32u, s_minv + ms * TN + col0 + 32u, s_mrs + ms * TN + col0 + 32u);
+                            if constexpr (WIDTH == 64)
+                                resolve(r + WIDTH - 32, p1, v, thr, ct, qi, row0 + 32u, s_minv + ms * TN + col0 + 32u, s_mrs + ms * TN + col0 + 32u);
                         }
                     }
                     if (threadIdx.x == 0) PBX_BP_ADD(7, te7);
@@ -840,12 +855,14 @@ batch_tighten_kernel(const BatchTightenParams p) {
     }
 }
 
-// ---- batched finalize for keep <= 256: one 256-thread CTA per query, several per SM -------------------------------------
+// ---- batched finalize for keep <= 256: one small CTA per query, several per SM ----------------------------------------
 // The same steps as finalize_kernel (candidate order, bit-exact replay, ORDER BY (dist, image_id), filter, LIMIT,
-// certificate), sized for what a batched query leaves behind: at most `keep` candidates, one per thread.  Every thread
-// replays its candidate row straight from global memory (the rows are random: no staging helps), ranks are counted
-// against shared memory, and the query's own norm fold comes from batch_prep_kernel (QueryHeader.sa).  1024 queries
-// finish in one wave of small CTAs instead of seven waves of one 1024-thread CTA per SM (406 us -> tens of us).
+// certificate), sized for what a batched query leaves behind: at most `keep` candidates, one per thread (blockDim =
+// keep rounded up to a warp).  Every thread replays its candidate row straight from global memory (the rows are random:
+// no staging helps) against the decoded query in shared memory, with a byte -> float table replicated per lane
+// (lut[v][lane]: one bank per lane, no conflicts whatever the bytes are); ranks are counted against shared memory with
+// branch-free comparisons; the query's own norm fold comes from batch_prep_kernel (QueryHeader.sa).  1024 queries
+// finish in two waves of small CTAs instead of seven waves of one 1024-thread CTA per SM.
 constexpr uint32_t kBfThreads = 256;
 struct BatchFinalizeParams {
     ExactLaunch x;              // exact-pass launch template (query 0); the launching CTA offsets the per-query pointers
@@ -866,24 +883,27 @@ struct BatchFinalizeParams {
     SearchStatus* status;       // [nq]
 };
 
-__global__ void __launch_bounds__(kBfThreads, 4)
+// dynamic shared memory: decoded query [pitch] f32 | centred query [pitch] s16 | per-lane table [256][32] f32
+__host__ __device__ inline size_t batch_finalize_smem(uint32_t pitch) { return (size_t)pitch * 6 + 256 * 32 * 4; }
+
+__global__ void __launch_bounds__(kBfThreads, 3)
 batch_finalize_kernel(const BatchFinalizeParams p) {
     extern __shared__ __align__(16) unsigned char bf_sm[];
-    uint8_t* s_qb = bf_sm;                                              // [pitch] raw query bytes
-    int16_t* s_q16 = reinterpret_cast<int16_t*>(bf_sm + p.pitch);       // [pitch] centred query
+    float* s_qa = reinterpret_cast<float*>(bf_sm);                                   // [pitch] decoded query (0 in the padding)
+    int16_t* s_q16 = reinterpret_cast<int16_t*>(bf_sm + (size_t)p.pitch * 4);        // [pitch] centred query
+    float* s_lut = reinterpret_cast<float*>(bf_sm + (size_t)p.pitch * 6);            // [256][32]
     __shared__ u64 s_key[kBfThreads];
-    __shared__ RerankEntry s_ent[kBfThreads];
-    __shared__ float s_lut[256];
+    __shared__ uint32_t s_od[kBfThreads];
+    __shared__ long long s_id[kBfThreads];
     __shared__ float s_kappa_k, s_kappa_last;
     __shared__ uint32_t s_pass, s_nonplateau;
-    const uint32_t tid = threadIdx.x, q = blockIdx.x;
-    const uint32_t c = min(min(p.bcnt[q], p.bcap), kBfThreads);         // <= keep after the last batch_tighten
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, q = blockIdx.x;
+    const uint32_t c = min(min(p.bcnt[q], p.bcap), blockDim.x);          // <= keep after the last batch_tighten
     const QueryHeader qh = p.qh[q];
-    s_lut[tid] = ref_decode(tid);
-    for (uint32_t i = tid; i < p.pitch / 16; i += blockDim.x) {
-        reinterpret_cast<uint4*>(s_qb)[i] = __ldg(reinterpret_cast<const uint4*>(p.qbytes + (size_t)q * p.pitch) + i);
-        reinterpret_cast<uint4*>(s_q16)[2 * i] = __ldg(reinterpret_cast<const uint4*>(p.q16 + (size_t)q * p.pitch) + 2 * i);
-        reinterpret_cast<uint4*>(s_q16)[2 * i + 1] = __ldg(reinterpret_cast<const uint4*>(p.q16 + (size_t)q * p.pitch) + 2 * i + 1);
+    for (uint32_t i = tid; i < 256u * 32u; i += blockDim.x) s_lut[i] = ref_decode(i >> 5);
+    for (uint32_t i = tid; i < p.pitch; i += blockDim.x) {
+        s_qa[i] = i < p.dim ? ref_decode(p.qbytes[(size_t)q * p.pitch + i]) : 0.0f;
+        s_q16[i] = p.q16[(size_t)q * p.pitch + i];
     }
     u64 key = 0ull;
     if (tid < c) {
@@ -903,30 +923,74 @@ batch_finalize_kernel(const BatchFinalizeParams p) {
         if (rank == nc - 1) s_kappa_last = key64_kappa(key);
         if (rank >= nc) key = 0ull;                                     // beyond keep (cannot happen after the tighten)
     }
-    // kernel C: bit-exact replay of the reference distance for this thread's candidate
+    // kernel C: bit-exact replay of the reference distance for this thread's candidate (src/engine.rs:572-588): the two
+    // f32 folds strictly in element order, the exact integer sums beside them
     float dist = __int_as_float(0x7f800000);
     int idot = 0, inorm = 0;
-    int64_t id = INT64_MAX;
+    long long id = INT64_MAX;
     const bool have = tid < c && key != 0ull;
     if (have) {
         const uint32_t row = key64_row(key);
-        const ReplayOut ro = replay_row<true>(p.rows + (size_t)row * p.pitch, s_qb, s_q16, p.dim, qh.sum_cq, s_lut);
-        dist = ref_distance(qh.sa, ro.sb, ro.dot);
-        idot = ro.idot; inorm = ro.inorm;
+        const uint4* r4 = reinterpret_cast<const uint4*>(p.rows + (size_t)row * p.pitch);
+        const float* lut = s_lut + lane;
+        const uint32_t chunks = p.pitch >> 4, full = p.dim >> 4;
+        float sb = 0.0f, fd = 0.0f;
+        int acc = 0;
+        unsigned s1 = 0, s2 = 0;
+        uint4 cur = __ldg(r4), nxt = cur;
+        for (uint32_t ch = 0; ch < chunks; ++ch) {
+            if (ch + 1 < chunks) nxt = __ldg(r4 + ch + 1);
+            const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+            if (ch < full) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 a = *reinterpret_cast<const float4*>(s_qa + 16 * ch + 4 * i);
+                    const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const float fb = lut[((w[i] >> (8 * b)) & 255u) << 5];
+                        sb = ref_fold(sb, fb, fb);
+                        fd = ref_fold(fd, av[b], fb);
+                    }
+                }
+            } else {                                            // ragged tail: dim is not a multiple of 16
+                for (uint32_t i = 16 * ch; i < p.dim; ++i) {
+                    const uint32_t o = i - 16 * ch;
+                    const float fb = lut[((w[o >> 2] >> (8 * (o & 3))) & 255u) << 5];
+                    sb = ref_fold(sb, fb, fb);
+                    fd = ref_fold(fd, s_qa[i], fb);
+                }
+            }
+            const int4 qa4 = *reinterpret_cast<const int4*>(s_q16 + 16 * ch), qb4 = *reinterpret_cast<const int4*>(s_q16 + 16 * ch + 8);
+            const int qq[8] = {qa4.x, qa4.y, qa4.z, qa4.w, qb4.x, qb4.y, qb4.z, qb4.w};
+            acc = dot16(cur, qq, acc);
+            s1 = dp4a_uu(cur.x, 0x01010101u, s1); s1 = dp4a_uu(cur.y, 0x01010101u, s1);
+            s1 = dp4a_uu(cur.z, 0x01010101u, s1); s1 = dp4a_uu(cur.w, 0x01010101u, s1);
+            s2 = dp4a_uu(cur.x, cur.x, s2); s2 = dp4a_uu(cur.y, cur.y, s2);
+            s2 = dp4a_uu(cur.z, cur.z, s2); s2 = dp4a_uu(cur.w, cur.w, s2);
+            cur = nxt;
+        }
+        dist = ref_distance(qh.sa, sb, fd);
+        idot = 2 * acc - 255 * qh.sum_cq;
+        inorm = (int)(4u * s2 - 1020u * s1 + 65025u * p.dim);
         id = p.ids[row];
     }
-    RerankEntry me;
-    me.od = have ? ord_f32(dist) : 0xFFFFFFFFu;
-    me.slot = have ? tid : 0xFFFFFFFFu;
-    me.id = id;
-    s_ent[tid] = me;
+    const uint32_t od = have ? ord_f32(dist) : 0xFFFFFFFFu;
+    s_od[tid] = od;
+    s_id[tid] = id;
     __syncthreads();
-    // ORDER BY dist ASC (ties by image_id), WHERE dist < ?, LIMIT k   (src/engine.rs:379-381)
+    // ORDER BY dist ASC (ties by image_id), WHERE dist < ?, LIMIT k   (src/engine.rs:379-381).  Candidates are distinct
+    // rows; equal (dist, id) pairs (duplicate ids in the table) fall back to the slot order.
     pbx_hit* hits_g = p.hits + (size_t)q * p.k;
     if (have) {
         uint32_t pos = 0;
 #pragma unroll 4
-        for (uint32_t j = 0; j < c; ++j) pos += rerank_before(s_ent[j], me) ? 1u : 0u;
+        for (uint32_t j = 0; j < c; ++j) {
+            const uint32_t oj = s_od[j];
+            const long long ij = s_id[j];
+            const bool before = (oj < od) | ((oj == od) & ((ij < id) | ((ij == id) & (j < tid))));
+            pos += before ? 1u : 0u;
+        }
         const bool ok = (double)dist < p.max_dist;
         if (ok) atomicAdd(&s_pass, 1u);
         if (dist < PBX_PLATEAU_DIST) atomicAdd(&s_nonplateau, 1u);
@@ -954,16 +1018,21 @@ batch_finalize_kernel(const BatchFinalizeParams p) {
             if (plateau_reachable) { st.need_exact = 1; st.theta = -__int_as_float(0x7f800000); }
             else if (!separated) { st.need_exact = 1; st.theta = (float)((double)s_kappa_k - (double)p.margin - 1e-7); }
         }
-        if (p.boverflow[q] || p.bcnt[q] > kBfThreads) { st.need_exact = 1; st.theta = -__int_as_float(0x7f800000); }   // candidates were dropped
+        if (p.boverflow[q] || p.bcnt[q] > blockDim.x) { st.need_exact = 1; st.theta = -__int_as_float(0x7f800000); }   // candidates were dropped
         p.status[q] = st;
         // the last CTA to finish tail-launches the exact pass of every query that needs one, one after the other
-        // (they share the scan scratch), from a single thread so that their order is well defined
+        // (they share the scan scratch), from a single thread so that their order is well defined.  bticket[1] counts
+        // the queries that need one: normally zero, and then nobody walks the 1024 status words (a single thread
+        // reading them one L2 round trip at a time was 250 us of the batch).
+        if (st.need_exact) atomicAdd(p.bticket + 1, 1u);
         __threadfence();
         if (atomicAdd(p.bticket, 1u) == gridDim.x - 1) {
             *p.bticket = 0;
-#ifdef PBX_USE_CDP
             __threadfence();
-            for (uint32_t qq = 0; qq < p.nq; ++qq) {
+            const uint32_t n_need = *reinterpret_cast<volatile uint32_t*>(p.bticket + 1);
+            p.bticket[1] = 0;
+#ifdef PBX_USE_CDP
+            for (uint32_t qq = 0; n_need && qq < p.nq; ++qq) {
                 if (*reinterpret_cast<volatile uint32_t*>(&p.status[qq].need_exact) == 0) continue;
                 ExactLaunch x = p.x;
                 x.scan.q16 += (size_t)qq * p.pitch;

@@ -85,7 +85,7 @@ struct FinalizeParams {
     const u64* bcand;           // [nq][kBatchCapacity] candidate keys (kappa' = dot_i * inv_norm_r, row)
     const uint32_t* bcnt;       // [nq]
     const uint32_t* boverflow;  // [nq] the candidate buffer overflowed: the exact pass must answer this query
-    uint32_t* bticket;          // zero on entry and on exit: the last CTA launches the exact passes
+    uint32_t* bticket;          // [2] zero on entry and on exit: ticket of the finished CTAs, count of queries needing the exact pass
     uint32_t bcap;              // entries per query in bcand
     uint32_t nq;
 };
@@ -810,12 +810,15 @@ finalize_kernel(const FinalizeParams p) {
         } else {
             // the last CTA to finish tail-launches the exact pass of every query that needs one, one after the
             // other (they share the scan scratch), from a single thread so that their order is well defined
+            if (st.need_exact) atomicAdd(p.bticket + 1, 1u);      // bticket[1]: queries that need the exact pass (normally none)
             __threadfence();
             if (atomicAdd(p.bticket, 1u) == gridDim.x - 1) {
                 *p.bticket = 0;
-#ifdef PBX_USE_CDP
                 __threadfence();
-                for (uint32_t qq = 0; qq < p.nq; ++qq) {
+                const uint32_t n_need = *reinterpret_cast<volatile uint32_t*>(p.bticket + 1);
+                p.bticket[1] = 0;
+#ifdef PBX_USE_CDP
+                for (uint32_t qq = 0; n_need && qq < p.nq; ++qq) {
                     if (*reinterpret_cast<volatile uint32_t*>(&p.status[qq].need_exact) == 0) continue;
                     ExactLaunch x = p.x;
                     x.scan.q16 += (size_t)qq * p.pitch;
