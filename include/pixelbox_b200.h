@@ -222,13 +222,19 @@ PBX_API int pbx_set_candidate_slack(pbx_corpus* c, uint32_t slack);
  * scan kernel of its last query (pbx_stats.last_search_ms / last_scan_ms).  Off by default: an event between two
  * kernels serialises launches that otherwise overlap (programmatic dependent launch). */
 PBX_API int pbx_set_profiling(pbx_corpus* c, int enabled);
-/* Batches of at least `min_queries` queries (per call) take the tensor-core path (tcgen05 kind::i8 contraction with
- * the top-k fused into the epilogue) when the row pitch allows it (dim a multiple of 128, <= 1024); smaller batches loop
- * over the single-query scan.  0 restores the default (16); UINT32_MAX disables the batched path.  Results are identical
- * either way. */
+/* Calls with at least `min_queries` queries take the tensor-core path (tcgen05 kind::i8 contraction with the top-k
+ * fused into the epilogue) when the shape allows it (row pitch a multiple of 32 bytes, <= 1024; enough rows to seed the
+ * thresholds); fewer queries, or other shapes, loop over the single-query scan.  0 restores the default (2: one
+ * streaming pass over the corpus serves all queries of the call, 2 queries cost ~1.5x one); UINT32_MAX disables the
+ * batched path.  Results are identical either way. */
 PBX_API int pbx_set_batch_min(pbx_corpus* c, uint32_t min_queries);
 /* CTAs per SM of the persistent scan kernel (0 = default). */
 PBX_API int pbx_set_scan_ctas_per_sm(pbx_corpus* c, uint32_t ctas_per_sm);
+/* Measures the int8 tensor-pipe ceiling of `device` for the batched path's MMA shape (tcgen05.mma.cta_group::2.kind::i8,
+ * 256 x 256 x 32 per instruction, operands resident in shared memory, accumulators never read): dense int8 TOP/s, best of
+ * three ~10 ms launches.  This is the measured denominator of the batched path's roofline (bench.py); the nominal
+ * figure is 4500. */
+PBX_API int pbx_int8_peak(int device, double* out_tops);
 PBX_API const char* pbx_last_error(void);
 PBX_API const char* pbx_version(void);
 PBX_API int pbx_device_count(void); /* number of sm_100 devices visible; 0 if none */

@@ -29,7 +29,7 @@ EXPORTS = [
     "pbx_corpus_size", "pbx_corpus_dim", "pbx_corpus_read_rows", "pbx_corpus_synchronize", "pbx_search", "pbx_search_hits", "pbx_search_device",
     "pbx_merge_hits", "pbx_merge_hits_device", "pbx_exchange_create", "pbx_exchange_handle", "pbx_exchange_connect",
     "pbx_exchange_allgather_merge", "pbx_exchange_destroy", "pbx_cosine_distance_pairs", "pbx_byte_distance_pairs", "pbx_hamming_distance_pairs", "pbx_quantize", "pbx_get_stats", "pbx_set_candidate_slack",
-    "pbx_set_profiling", "pbx_set_batch_min", "pbx_set_scan_ctas_per_sm", "pbx_last_error", "pbx_version", "pbx_device_count",
+    "pbx_set_profiling", "pbx_set_batch_min", "pbx_set_scan_ctas_per_sm", "pbx_int8_peak", "pbx_last_error", "pbx_version", "pbx_device_count",
 ]
 
 HIT_DTYPE = np.dtype([("image_id", "<i8"), ("dist", "<f4"), ("dot", "<i4"), ("norm2", "<i4"), ("flags", "<u4")], align=True)
@@ -96,6 +96,7 @@ def lib() -> ctypes.CDLL:
         "pbx_set_profiling": (i32, [vp, i32]),
         "pbx_set_batch_min": (i32, [vp, u32]),
         "pbx_set_scan_ctas_per_sm": (i32, [vp, u32]),
+        "pbx_int8_peak": (i32, [i32, ctypes.POINTER(ctypes.c_double)]),
         "pbx_last_error": (ctypes.c_char_p, []),
         "pbx_version": (ctypes.c_char_p, []),
         "pbx_device_count": (i32, []),

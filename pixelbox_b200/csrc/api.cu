@@ -117,7 +117,7 @@ struct pbx_corpus {
     uint32_t map_q_pad = 0, map_q_box = 0, map_rows_box = 0;
     uint32_t batch_cg = 2;            // CTAs per cluster of the batched kernel: 2 = cta_group::2 pairs; PBX_BATCH_CG=1: single CTAs
 
-    uint32_t batch_min = 16;          // batches at least this large use the tensor-core path
+    uint32_t batch_min = 2;           // calls with at least this many queries use the tensor-core path
     uint64_t batched_queries = 0;
     bool scan_timed = false;          // ev_s0/ev_s1 were recorded by the last enqueue
     bool profiling = false;           // record CUDA events around the search / the scan (pbx_set_profiling)
@@ -1453,6 +1453,46 @@ extern "C" int pbx_quantize(int device, const float* embeddings, uint64_t n, uin
     return PBX_OK;
 }
 
+extern "C" int pbx_int8_peak(int device, double* out_tops) {
+    if (!out_tops) return fail(PBX_E_INVALID, "out_tops is NULL");
+    if (pbx_device_count() == 0) return fail(PBX_E_NO_DEVICE, "no sm_100 device: pixelbox_b200 has no CPU fallback");
+    CU_TRY(cudaSetDevice(device));
+    int sms = 0;
+    CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    sms &= ~1;
+    const size_t smem = 4 * 128 * 128 + 1024;
+    CU_TRY(cudaFuncSetAttribute(batch_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)sms);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    const int iters = 20000;                         // ~10 ms per launch
+    float best = 0.f;
+    cudaError_t e = cudaSuccess;
+    for (int rep = 0; rep < 4 && e == cudaSuccess; ++rep) {
+        e = cudaEventRecord(e0);
+        if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, batch_peak_kernel, iters);
+        if (e == cudaSuccess) e = cudaEventRecord(e1);
+        if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+        float ms = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        if (e == cudaSuccess && rep > 0 && (best == 0.f || ms < best)) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e != cudaSuccess) return fail(PBX_E_CUDA, "int8 peak measurement failed: %s", cudaGetErrorString(e));
+    // per accumulator and CTA: 128 x 256 x 256 multiply-accumulates
+    *out_tops = 2.0 * 128.0 * 256.0 * 256.0 * (double)iters * (double)sms / ((double)best * 1e-3) / 1e12;
+    return PBX_OK;
+}
+
 extern "C" int pbx_get_stats(const pbx_corpus* cc, pbx_stats* out) {
     pbx_corpus* c = const_cast<pbx_corpus*>(cc);
     if (!c || !out) return fail(PBX_E_INVALID, "NULL argument");
@@ -1494,7 +1534,7 @@ extern "C" int pbx_set_profiling(pbx_corpus* c, int enabled) {
 extern "C" int pbx_set_batch_min(pbx_corpus* c, uint32_t min_queries) {
     if (!c) return fail(PBX_E_INVALID, "corpus is NULL");
     std::lock_guard<std::mutex> lk(c->mu);
-    c->batch_min = min_queries ? min_queries : 16u;
+    c->batch_min = min_queries ? min_queries : 2u;
     return PBX_OK;
 }
 

@@ -855,6 +855,60 @@ batch_tighten_kernel(const BatchTightenParams p) {
     }
 }
 
+// ---- the int8 tensor-pipe ceiling, measured (the denominator of the batched path's roofline) ---------------------------
+// The batched kernel's MMA shape and nothing else: operands resident in shared memory (filled once, contents irrelevant),
+// one thread per CTA pair issues tcgen05.mma.cta_group::2.kind::i8 (M = 256, N = 256, K = 256 bytes per accumulator) back
+// to back into the ring of two TMEM accumulators; nobody reads them.  What is left is the tensor pipe and its
+// shared-memory operand fetch.  pbx_int8_peak() times it; tools/umma_i8_peak.cu is the stand-alone form with more shapes.
+__global__ void __launch_bounds__(128, 1)
+batch_peak_kernel(int iters) {
+    extern __shared__ __align__(16) uint8_t psm_raw[];
+    uint8_t* psm = psm_raw + ((1024u - (smem_u32(psm_raw) & 1023u)) & 1023u);
+    uint8_t* sa = psm;                                  // [2][128][128]
+    uint8_t* sb = psm + 2 * 128 * 128;                  // [2][128][128]  (this CTA's half of the 256-row tile)
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ uint32_t tmem_base;
+    const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    for (uint32_t i = threadIdx.x; i < 4u * 128u * 128u / 4u; i += blockDim.x) reinterpret_cast<uint32_t*>(psm)[i] = 0x01020304u * (i | 1u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base;
+    if (warp == 1 && cluster_ctarank() == 0) {
+        const uint32_t idesc = (2u << 4) | (1u << 7) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
+        const uint64_t da0 = umma_desc_k(sa, 128), db0 = umma_desc_k(sb, 128);
+        for (int it = 0; it < iters + 2; ++it) {
+            const int s = it & 1;
+            if (it >= 2) mbar_wait(&bars[s], ((it >> 1) - 1) & 1);
+            if (it >= iters) continue;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+#pragma unroll
+                for (uint32_t kc = 0; kc < 2; ++kc)
+#pragma unroll
+                    for (uint32_t ks = 0; ks < 4; ++ks)
+                        umma_i8<2>(tmem + s * 256u, da0 + (uint64_t)(kc * 1024u + ks * 2u), db0 + (uint64_t)(kc * 1024u + ks * 2u), idesc, (kc | ks) ? 1u : 0u);
+                umma_commit<2>(&bars[s]);
+            }
+            __syncwarp();
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+}
+
 // ---- batched finalize for keep <= 256: one small CTA per query, several per SM ----------------------------------------
 // The same steps as finalize_kernel (candidate order, bit-exact replay, ORDER BY (dist, image_id), filter, LIMIT,
 // certificate), sized for what a batched query leaves behind: at most `keep` candidates, one per thread (blockDim =

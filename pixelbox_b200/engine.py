@@ -58,12 +58,14 @@ class IndexedImage:
 
 
 class Engine:
-    def __init__(self, db_path: str, device: int = 0):
+    def __init__(self, db_path: str, device: int = 0, _create: bool = False):
         """Engine::open (src/engine.rs:117-145): opens the DB and -- the GPU hook after :129 -- loads
         `SELECT image_id, hash FROM semantic_hashes ORDER BY image_id` into the device corpus."""
         self.db_path = db_path
         self.device = device
         self.write_connection = sqlite3.connect(db_path, check_same_thread=False)
+        if _create:                     # Engine::new, on the connection that is kept (a ':memory:' DB lives and dies with it)
+            self._create_tables(self.write_connection)
         self.read_connection = sqlite3.connect(f"file:{db_path}?mode=ro", uri=True, check_same_thread=False) \
             if db_path != ":memory:" else self.write_connection
         if db_path != ":memory:":
@@ -79,15 +81,16 @@ class Engine:
     @classmethod
     def new(cls, db_path: str, device: int = 0) -> "Engine":
         """Engine::new (src/engine.rs:98-115): creates the tables, then opens."""
-        conn = sqlite3.connect(db_path)
-        conn.execute(IMAGE_SCHEMA_V1)
+        return cls(db_path, device, _create=True)
+
+    @staticmethod
+    def _create_tables(conn: sqlite3.Connection) -> None:
+        conn.execute(IMAGE_SCHEMA_V1)                                                    # :105-109
         conn.execute(WATCHED_DIRECTORIES_SCHEMA_V1)
         conn.execute(TAG_SCHEMA_V1)
         conn.execute(HASH_TABLE_SCHEMA_V1.replace("$tablename$", "phashes"))
         conn.execute(HASH_TABLE_SCHEMA_V1.replace("$tablename$", "semantic_hashes"))
         conn.commit()
-        conn.close()
-        return cls(db_path, device)
 
     @classmethod
     def open(cls, db_path: str, device: int = 0) -> "Engine":
@@ -100,7 +103,15 @@ class Engine:
         # The BLOB column is length-agnostic (:48); the device corpus has one dim.  Rows of another
         # length cannot be represented (the reference would zip-truncate them, :585): they are skipped
         # and counted, never silently mis-scored.
-        dim = len(rows[0][1])
+        # dim = the modal blob length among the non-NULL rows.
+        lengths: Dict[int, int] = {}
+        for _, h in rows:
+            if h is not None and len(h) > 0:
+                lengths[len(h)] = lengths.get(len(h), 0) + 1
+        if not lengths:
+            self.skipped_rows = len(rows)
+            return
+        dim = max(lengths.items(), key=lambda kv: (kv[1], -kv[0]))[0]
         keep = [(i, h) for i, h in rows if h is not None and len(h) == dim]
         self.skipped_rows = len(rows) - len(keep)
         self.corpus = Corpus(dim, capacity_hint=len(keep), device=self.device)
@@ -163,16 +174,24 @@ class Engine:
         append hook: the hash is appended only when the INSERT changed a row -- a duplicate path makes
         `INSERT OR IGNORE INTO images` a no-op, last_insert_rowid() stale (:234) and the hash INSERT ignored."""
         conn = self.write_connection
-        conn.execute("INSERT OR IGNORE INTO images (filename, path, image_width, image_height, thumbnail) VALUES (?, ?, ?, ?, ?)",
-                     (img.filename, img.path, img.resolution[0], img.resolution[1], img.thumbnail))
-        img.id = conn.execute("SELECT last_insert_rowid()").fetchone()[0]
-        if img.visual_hash is not None:
-            cur = conn.execute("INSERT OR IGNORE INTO semantic_hashes (image_id, hash) VALUES (?, ?)", (img.id, img.visual_hash))
-            if cur.rowcount == 1:
-                if self.corpus is None:
-                    self.corpus = Corpus(len(img.visual_hash), device=self.device)
-                if len(img.visual_hash) == self.corpus.dim:
-                    self.corpus.append(np.array([img.id], np.int64), np.frombuffer(img.visual_hash, np.uint8).reshape(1, -1))
-                else:
-                    self.skipped_rows += 1
-        conn.commit()
+        appended = None
+        try:
+            conn.execute("INSERT OR IGNORE INTO images (filename, path, image_width, image_height, thumbnail) VALUES (?, ?, ?, ?, ?)",
+                         (img.filename, img.path, img.resolution[0], img.resolution[1], img.thumbnail))
+            img.id = conn.execute("SELECT last_insert_rowid()").fetchone()[0]
+            if img.visual_hash is not None:
+                cur = conn.execute("INSERT OR IGNORE INTO semantic_hashes (image_id, hash) VALUES (?, ?)", (img.id, img.visual_hash))
+                if cur.rowcount == 1:
+                    appended = (img.id, img.visual_hash)
+            conn.commit()
+        except Exception:
+            conn.rollback()
+            raise
+        # the device corpus is a cache of the committed table: append only what the DB now holds
+        if appended is not None:
+            if self.corpus is None:
+                self.corpus = Corpus(len(appended[1]), device=self.device)
+            if len(appended[1]) == self.corpus.dim:
+                self.corpus.append(np.array([appended[0]], np.int64), np.frombuffer(appended[1], np.uint8).reshape(1, -1))
+            else:
+                self.skipped_rows += 1

@@ -46,11 +46,15 @@ class ShardedCorpus:
             raise nat.PbxError(-1, "at most 64 shards")
         self.backend = dist.get_backend(group)
         self.dim = int(dim)
-        self.on_gpu = self.backend == "nccl"
-        if local is None:
+        # GPU shards: always with NCCL; with gloo when a device is named (two ranks sharing one GPU in the 1-GPU test:
+        # NCCL refuses two ranks per device, the exchange over CUDA IPC mailboxes does not care)
+        self.on_gpu = self.backend == "nccl" or (local is None and device is not None)
+        if local is None and self.on_gpu:
             if device is None:
                 device = torch.cuda.current_device()
             local = Corpus(dim, capacity_hint=capacity_hint, device=device)
+        if local is None:
+            raise nat.PbxError(-1, "ShardedCorpus on CPU (gloo) needs an injected `local` shard object")
         self.local = local
         self.device = device if device is not None else 0
         self._bufs = {}
@@ -71,19 +75,31 @@ class ShardedCorpus:
         nat.check(L.pbx_exchange_create(self.device, self.rank, self.world, self.MAX_RECORDS, self.MAX_QUERIES, ctypes.byref(h)))
         mine = np.zeros(64, np.uint8)
         nat.check(L.pbx_exchange_handle(h, nat.ptr(mine)))
-        dev = self._dev()
-        t_mine = torch.from_numpy(mine).to(dev)
-        t_all = torch.empty(self.world * 64, dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(t_all, t_mine, group=self.group)
-        handles = np.ascontiguousarray(t_all.cpu().numpy())
+        handles = np.ascontiguousarray(self._all_gather_bytes(mine).reshape(-1))
         rc = L.pbx_exchange_connect(h, nat.ptr(handles))
-        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=dev)
+        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=self._comm_dev())
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)        # all ranks or none
         if int(ok.item()) == 1:
             self._exchange = h
         else:
             L.pbx_exchange_destroy(h)
         dist.barrier(group=self.group)
+
+    def _comm_dev(self):
+        """Device of the tensors handed to torch.distributed: the GPU with NCCL, the host with gloo."""
+        return torch.device("cuda", self.device) if self.backend == "nccl" else torch.device("cpu")
+
+    def _all_gather_bytes(self, mine: np.ndarray) -> np.ndarray:
+        """[world][len(mine)] uint8: every rank's small host buffer (IPC handles)."""
+        t_mine = torch.from_numpy(np.ascontiguousarray(mine)).to(self._comm_dev())
+        t_all = torch.empty(self.world * t_mine.numel(), dtype=torch.uint8, device=self._comm_dev())
+        if self.backend == "nccl":
+            dist.all_gather_into_tensor(t_all, t_mine, group=self.group)
+        else:
+            parts = [torch.empty_like(t_mine) for _ in range(self.world)]
+            dist.all_gather(parts, t_mine, group=self.group)
+            t_all = torch.cat(parts)
+        return t_all.cpu().numpy().reshape(self.world, -1)
 
     # -- contents ----------------------------------------------------------------------------------
     def load_table(self, image_ids, hashes) -> None:
@@ -97,7 +113,7 @@ class ShardedCorpus:
         self.local.fill_synthetic(rows_per_shard, seed, self.rank * rows_per_shard)
 
     def total_rows(self) -> int:
-        t = torch.tensor([len(self.local)], dtype=torch.int64, device=self._dev())
+        t = torch.tensor([len(self.local)], dtype=torch.int64, device=self._comm_dev())
         dist.all_reduce(t, group=self.group)
         return int(t.item())
 
@@ -138,7 +154,13 @@ class ShardedCorpus:
             nat.check(nat.lib().pbx_exchange_allgather_merge(self._exchange, b["local"].data_ptr(), nq, k, b["out"].data_ptr(),
                                                              b["out_cnt"].data_ptr(), stream if stream else 1))
             return b["out"], b["out_cnt"]
-        dist.all_gather_into_tensor(b["gathered"], b["local"], group=self.group)
+        if self.backend == "nccl":
+            dist.all_gather_into_tensor(b["gathered"], b["local"], group=self.group)
+        else:                                   # gloo has no device all-gather: stage the records through the host
+            torch.cuda.current_stream().synchronize()
+            parts = [torch.empty(b["local"].numel(), dtype=torch.uint8) for _ in range(self.world)]
+            dist.all_gather(parts, b["local"].cpu(), group=self.group)
+            b["gathered"].copy_(torch.cat(parts))
         nat.check(nat.lib().pbx_merge_hits_device(self.device, b["gathered"].data_ptr(), None, self.world, nq, k,
                                                   b["out"].data_ptr(), b["out_cnt"].data_ptr(), stream if stream else 1))
         return b["out"], b["out_cnt"]

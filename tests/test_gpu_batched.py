@@ -30,8 +30,12 @@ def check(corpus, ids, queries, k, md, c, oracle_every=1):
     return got
 
 
+# row pitches with 128-byte K-chunks, and (new in round 2) 64- and 32-byte chunks: dim 64, 192, 320 / 32, 96, 100 (pitch 112 is
+# not a multiple of 32 and must stay on the single-query path), 992
 @pytest.mark.parametrize("d,n,nq", [(256, 60_000, 40), (256, 150_001, 700), (128, 50_000, 64), (512, 40_000, 300), (1024, 30_000, 130),
-                                    (384, 40_000, 300), (640, 30_000, 130), (768, 30_000, 70), (896, 20_000, 33)])
+                                    (384, 40_000, 300), (640, 30_000, 130), (768, 30_000, 70), (896, 20_000, 33),
+                                    (64, 120_000, 1024), (192, 50_000, 200), (320, 40_000, 129), (32, 100_000, 500), (96, 60_000, 257),
+                                    (992, 20_000, 40), (250, 30_000, 64)])
 def test_batched_equals_oracle_and_single_path(d, n, nq):
     rng = np.random.default_rng(d + nq)
     corpus = rng.integers(0, 256, size=(n, d), dtype=np.uint8)

@@ -36,9 +36,14 @@ def check_against_oracle(corpus, ids, queries, ks=(10, 100), mds=(1e3,), slack=N
             c.set_candidate_slack(slack)
         for k in ks:
             for md in mds:
-                got = c.search(queries, k, md)
-                for qi, q in enumerate(queries):
-                    assert_same(got[qi], oracle.topk(corpus, ids, q, k, md), f"{ctx} n={n} d={d} k={k} md={md} q={qi}")
+                want = [oracle.topk(corpus, ids, q, k, md) for q in queries]
+                # every call both ways: looping over the single-query scan, and whatever the default dispatch picks
+                # (the tensor-core batched path from 2 queries on, where the shape allows it)
+                for batch_min, mode in ((0xFFFFFFFF, "single"), (0, "default")):
+                    c.set_batch_min(batch_min)
+                    got = c.search(queries, k, md)
+                    for qi in range(len(queries)):
+                        assert_same(got[qi], want[qi], f"{ctx} {mode} n={n} d={d} k={k} md={md} q={qi}")
         return c.stats()
 
 
