@@ -166,6 +166,31 @@ PBX_API int pbx_merge_hits(const pbx_hit* gathered, const uint32_t* counts, uint
 PBX_API int pbx_merge_hits_device(int device, const pbx_hit* d_gathered, const uint32_t* d_counts, uint32_t n_shards,
                                   uint32_t nq, uint32_t k, pbx_hit* d_out_hits, uint32_t* d_out_count, void* cuda_stream);
 
+/* ---- the row-sharded corpus of ONE process over several GPUs -------------------------------------------------------
+ * Replaces: the same table and query as pbx_corpus / pbx_search, for a corpus that needs more than one GPU (1B x 256 B =
+ * 256 GB).  The reference's host is a single process that calls Engine on the UI thread (src/ui/search.rs:20-31,
+ * src/engine.rs:117-145), so this is what its FFI crate binds when several devices are named.  `devices` lists CUDA
+ * ordinals (repeats allowed: several shards on one GPU); rows are partitioned by contiguous blocks of the id-ordered
+ * table at load, appended rows go to the emptiest shard; image ids stay global.  A search runs the complete local search
+ * on every shard (one worker thread and stream per shard), copies each shard's k records per query to the first device
+ * over NVLink and merges them there under (dist, image_id): results are identical to one pbx_corpus holding all rows. */
+typedef struct pbx_sharded pbx_sharded;
+PBX_API int pbx_sharded_create(uint32_t dim, uint64_t capacity_hint, const int* devices, int n_devices, pbx_sharded** out);
+PBX_API void pbx_sharded_destroy(pbx_sharded* s);
+PBX_API int pbx_sharded_load(pbx_sharded* s, const int64_t* image_ids, const uint8_t* hashes, uint64_t n);
+PBX_API int pbx_sharded_append(pbx_sharded* s, const int64_t* image_ids, const uint8_t* hashes, uint64_t n);
+/* Bench/test only: shard i holds rows [i * rows_per_shard, (i + 1) * rows_per_shard) of the synthetic corpus. */
+PBX_API int pbx_sharded_fill_synthetic(pbx_sharded* s, uint64_t rows_per_shard, uint64_t seed);
+PBX_API int pbx_sharded_size(const pbx_sharded* s, uint64_t* n_rows);
+PBX_API int pbx_sharded_shards(const pbx_sharded* s, uint32_t* n_shards);
+/* The i-th shard, for pbx_get_stats / the pbx_set_* knobs; owned by the sharded corpus. */
+PBX_API int pbx_sharded_shard(pbx_sharded* s, uint32_t index, pbx_corpus** out);
+/* Same contracts as pbx_search / pbx_search_hits (host buffers in, host buffers out, synchronous). */
+PBX_API int pbx_sharded_search(pbx_sharded* s, const uint8_t* queries, uint32_t nq, uint32_t k, double max_dist,
+                               int64_t* out_ids, float* out_dist, int32_t* out_dot, int32_t* out_norm2, uint32_t* out_count);
+PBX_API int pbx_sharded_search_hits(pbx_sharded* s, const uint8_t* queries, uint32_t nq, uint32_t k, double max_dist,
+                                    pbx_hit* out_hits, uint32_t* out_count);
+
 /* ---- the exchange step over NVLink peer memory (one process per GPU) ---------------------------------
  * Replaces: nothing upstream (PixelBox is single-process); it is the one exchange step of the row-sharded path
  * (SURVEY.md section 8e).  Each rank creates an exchange (a device mailbox for [world][nq][k] records, double

@@ -169,11 +169,87 @@ class Corpus:
         nat.check(nat.lib().pbx_set_profiling(self._h, 1 if enabled else 0))
 
     def set_batch_min(self, n: int) -> None:
-        """Batches of at least n queries per call use the tensor-core path (0 = default 16, 0xFFFFFFFF = never)."""
+        """Calls with at least n queries use the tensor-core path (0 = default 2, 0xFFFFFFFF = never)."""
         nat.check(nat.lib().pbx_set_batch_min(self._h, int(n)))
 
     def set_scan_ctas_per_sm(self, n: int) -> None:
         nat.check(nat.lib().pbx_set_scan_ctas_per_sm(self._h, int(n)))
+
+
+class MultiDeviceCorpus:
+    """pbx_sharded_*: the table row-sharded over several GPUs of this box by ONE process (one worker thread and
+    stream per shard inside the library, merge on the first device).  Same results as one Corpus holding all rows."""
+
+    def __init__(self, dim: int, devices: Sequence[int], capacity_hint: int = 0):
+        self._h = ctypes.c_void_p(0)
+        self.dim = int(dim)
+        self.devices = [int(d) for d in devices]
+        arr = (ctypes.c_int * len(self.devices))(*self.devices)
+        nat.check(nat.lib().pbx_sharded_create(self.dim, int(capacity_hint), ctypes.cast(arr, ctypes.c_void_p), len(self.devices), ctypes.byref(self._h)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            nat.lib().pbx_sharded_destroy(self._h)
+            self._h = ctypes.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __len__(self) -> int:
+        n = ctypes.c_uint64(0)
+        nat.check(nat.lib().pbx_sharded_size(self._h, ctypes.byref(n)))
+        return int(n.value)
+
+    def load(self, image_ids, hashes) -> None:
+        hashes = _as_u8_2d(hashes, self.dim, "load")
+        ids = np.ascontiguousarray(np.asarray(image_ids, dtype=np.int64))
+        if ids.shape != (hashes.shape[0],):
+            raise nat.PbxError(-1, "load: one image_id per hash row required")
+        nat.check(nat.lib().pbx_sharded_load(self._h, nat.ptr(ids), nat.ptr(hashes), hashes.shape[0]))
+
+    def append(self, image_ids, hashes) -> None:
+        hashes = _as_u8_2d(hashes, self.dim, "append")
+        ids = np.ascontiguousarray(np.asarray(image_ids, dtype=np.int64)).reshape(-1)
+        if ids.shape != (hashes.shape[0],):
+            raise nat.PbxError(-1, "append: one image_id per hash row required")
+        nat.check(nat.lib().pbx_sharded_append(self._h, nat.ptr(ids), nat.ptr(hashes), hashes.shape[0]))
+
+    def fill_synthetic(self, rows_per_shard: int, seed: int) -> None:
+        nat.check(nat.lib().pbx_sharded_fill_synthetic(self._h, int(rows_per_shard), int(seed)))
+
+    def shard_stats(self, index: int) -> nat.PbxStats:
+        h = ctypes.c_void_p(0)
+        nat.check(nat.lib().pbx_sharded_shard(self._h, int(index), ctypes.byref(h)))
+        s = nat.PbxStats()
+        nat.check(nat.lib().pbx_get_stats(h, ctypes.byref(s)))
+        return s
+
+    def set_candidate_slack(self, slack: int) -> None:
+        for i in range(len(self.devices)):
+            h = ctypes.c_void_p(0)
+            nat.check(nat.lib().pbx_sharded_shard(self._h, i, ctypes.byref(h)))
+            nat.check(nat.lib().pbx_set_candidate_slack(h, int(slack)))
+
+    def search(self, queries, k: int = nat.DEFAULT_K, max_dist: float = nat.DEFAULT_MAX_DIST) -> List[SearchResult]:
+        q = _as_u8_2d(queries, self.dim, "search")
+        nq, k = q.shape[0], int(k)
+        ids = np.zeros((nq, k), np.int64)
+        dist = np.zeros((nq, k), np.float32)
+        dot = np.zeros((nq, k), np.int32)
+        n2 = np.zeros((nq, k), np.int32)
+        cnt = np.zeros(nq, np.uint32)
+        nat.check(nat.lib().pbx_sharded_search(self._h, nat.ptr(q), nq, k, float(max_dist), nat.ptr(ids), nat.ptr(dist), nat.ptr(dot),
+                                               nat.ptr(n2), nat.ptr(cnt)))
+        return [SearchResult(ids[i, :c].copy(), dist[i, :c].copy(), dot[i, :c].copy(), n2[i, :c].copy()) for i, c in enumerate(cnt.tolist())]
 
 
 def merge_hits(gathered: np.ndarray, counts: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:

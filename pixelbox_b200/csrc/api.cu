@@ -1571,3 +1571,5 @@ extern "C" __attribute__((visibility("default"))) int pbx_debug_scan_profile(uns
     return 0;
 }
 #endif
+
+#include "sharded.inl"
