@@ -45,9 +45,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return SO
     os.makedirs(LIBDIR, exist_ok=True)
     extra = os.environ.get("PBX_NVCC_EXTRA", "").split()      # experiments only, e.g. -DPBX_EXP_NOMETA
+    flags = list(NVCC_FLAGS)
+    if os.environ.get("PBX_NO_CDP"):
+        # racecheck / synccheck / initcheck of compute-sanitizer do not support CUDA dynamic parallelism: this variant
+        # launches the exact pass from the host (always enqueued, returns at once unless a certificate failed)
+        flags = [f for f in flags if f not in ("-rdc=true", "-DPBX_USE_CDP")]
     out = os.environ.get("PBX_SO_OUT", SO)
-    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudadevrt"]
+    cmd = [_nvcc()] + flags + extra + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES] + ([] if os.environ.get("PBX_NO_CDP") else ["-lcudadevrt"])
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

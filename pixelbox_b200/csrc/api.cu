@@ -930,6 +930,21 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
         finalize_kernel<true><<<nq, kFinalThreads, fin_smem, s>>>(fp);
         CU_TRY(cudaGetLastError());
     }
+#ifndef PBX_USE_CDP
+    // build without device-side launches (sanitizer runs): the host reads the certificates and launches the exact passes
+    {
+        std::vector<SearchStatus> hs(nq);
+        CU_TRY(cudaStreamSynchronize(s));
+        CU_TRY(cudaMemcpy(hs.data(), c->d_status, (size_t)nq * sizeof(SearchStatus), cudaMemcpyDeviceToHost));
+        for (uint32_t q = 0; q < nq; ++q) {
+            if (!hs[q].need_exact) continue;
+            const ExactSetup xq = exact_setup(c, q, k, max_dist, n, d_hits, d_count);
+            CU_TRY(launch_scan<true>(c, xq.scan, xq.grid, xq.scan_smem, s));
+            finalize_exact_kernel<<<1, kFinalThreads, xq.fin_smem, s>>>(xq.fin);
+            CU_TRY(cudaGetLastError());
+        }
+    }
+#endif
     c->batched_queries += nq;
     c->last_grid = bp.grid;
     return PBX_OK;

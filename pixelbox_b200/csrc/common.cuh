@@ -292,6 +292,7 @@ __device__ inline void block_select_top(TopBuf<u64>& tb, SelectScratch* sc) {
                 if (lane + off < 32) incl += v;
             }
             const uint32_t above = incl - mine, need = sc->need;
+            __syncwarp();                                        // every lane has read `need` before the crossing lane rewrites it
             if (above < need && above + mine >= need) {          // exactly one lane
                 uint32_t greater = above;
 #pragma unroll

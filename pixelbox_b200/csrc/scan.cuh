@@ -223,7 +223,9 @@ scan_kernel(const ScanParams p) {
     float theta = 0.0f;
     if constexpr (EXACT) theta = p.status->theta;
 
-    if (threadIdx.x == 0) { sh.cnt = 0; sh.done = 0; sh.gb = 0; sh.tau = KeyOps<K>::lowest(); }   // sh.gb is re-seeded below
+    uint32_t* const gbin = p.tile_counter + 32;        // its own 128-byte line, away from the chunk counter
+    // sh.gb starts at the global bin threshold seeded by prep_seed_kernel from a strided sample of the shard (fast pass)
+    if (threadIdx.x == 0) { sh.cnt = 0; sh.done = 0; sh.gb = EXACT ? 0u : *reinterpret_cast<volatile uint32_t*>(gbin); sh.tau = KeyOps<K>::lowest(); }
     TopBuf<K> tb{buf, &sh.cnt, &sh.tau, p.cap, p.keep};
     __syncthreads();
 
@@ -232,12 +234,7 @@ scan_kernel(const ScanParams p) {
     // with at least `keep` entries at or above it and publishes it (atomicMax): rows below b* cannot be
     // among the best `keep` of the whole shard, whichever CTA sees them.  After the first few chunks the
     // push rate is ~keep / rows-seen-by-all-CTAs, so buffers almost never need cutting back mid-scan.
-    uint32_t* const gbin = p.tile_counter + 32;        // its own 128-byte line, away from the chunk counter
-    uint32_t gb = 0;
-    if constexpr (!EXACT) {                            // seeded by seed_kernel from a strided sample of the shard
-        gb = *reinterpret_cast<volatile uint32_t*>(gbin);
-        if (threadIdx.x == 0) sh.gb = gb;
-    }
+    uint32_t gb = sh.gb;                               // (published before the barrier above)
     const uint32_t total_warps = gridDim.x * kScanWarps;
 
     // Warp-autonomous scheduling: every warp claims chunks of kChunkRows rows from a global counter
