@@ -207,6 +207,11 @@ PBX_API int pbx_exchange_handle(pbx_exchange* x, void* out_handle_64_bytes);
 PBX_API int pbx_exchange_connect(pbx_exchange* x, const void* all_handles /* [world][64] */);
 PBX_API int pbx_exchange_allgather_merge(pbx_exchange* x, const pbx_hit* d_local, uint32_t nq, uint32_t k, pbx_hit* d_out,
                                          uint32_t* d_out_count, void* cuda_stream);
+/* The whole per-rank step with host buffers (what pbx_search_hits is for one GPU): H2D of the queries, this shard's
+ * search, the exchange + merge kernel, D2H of the merged records, one synchronisation.  Every rank calls it with the same
+ * queries and receives the global result.  nq <= 1024 per call. */
+PBX_API int pbx_exchange_search_hits(pbx_exchange* x, pbx_corpus* c, const uint8_t* queries, uint32_t nq, uint32_t k, double max_dist,
+                                     pbx_hit* out_hits, uint32_t* out_count);
 PBX_API void pbx_exchange_destroy(pbx_exchange* x);
 
 /* ---- the scalar function, for external users of the DB -----------------------------------

@@ -28,7 +28,7 @@ EXPORTS = [
     "pbx_corpus_create", "pbx_corpus_destroy", "pbx_corpus_load", "pbx_corpus_append", "pbx_corpus_fill_synthetic",
     "pbx_corpus_size", "pbx_corpus_dim", "pbx_corpus_read_rows", "pbx_corpus_synchronize", "pbx_search", "pbx_search_hits", "pbx_search_device",
     "pbx_merge_hits", "pbx_merge_hits_device", "pbx_exchange_create", "pbx_exchange_handle", "pbx_exchange_connect",
-    "pbx_exchange_allgather_merge", "pbx_exchange_destroy",
+    "pbx_exchange_allgather_merge", "pbx_exchange_search_hits", "pbx_exchange_destroy",
     "pbx_sharded_create", "pbx_sharded_destroy", "pbx_sharded_load", "pbx_sharded_append", "pbx_sharded_fill_synthetic", "pbx_sharded_size",
     "pbx_sharded_shards", "pbx_sharded_shard", "pbx_sharded_search", "pbx_sharded_search_hits", "pbx_cosine_distance_pairs", "pbx_byte_distance_pairs", "pbx_hamming_distance_pairs", "pbx_quantize", "pbx_get_stats", "pbx_set_candidate_slack",
     "pbx_set_profiling", "pbx_set_batch_min", "pbx_set_scan_ctas_per_sm", "pbx_int8_peak", "pbx_last_error", "pbx_version", "pbx_device_count",
@@ -88,6 +88,7 @@ def lib() -> ctypes.CDLL:
         "pbx_exchange_handle": (i32, [vp, vp]),
         "pbx_exchange_connect": (i32, [vp, vp]),
         "pbx_exchange_allgather_merge": (i32, [vp, vp, u32, u32, vp, vp, vp]),
+        "pbx_exchange_search_hits": (i32, [vp, vp, u8p, u32, u32, f64, vp, vp]),
         "pbx_exchange_destroy": (None, [vp]),
         "pbx_sharded_create": (i32, [u32, u64, vp, i32, ctypes.POINTER(vp)]),
         "pbx_sharded_destroy": (None, [vp]),

@@ -1283,6 +1283,9 @@ struct pbx_exchange {
     void* peer_base[PBX_MAX_SHARDS] = {};
     bool connected = false;
     uint32_t seq = 0;
+    pbx_hit* d_out = nullptr;                      // merged result of pbx_exchange_search_hits: [max_records] records, then [max_queries] counts
+    pbx_hit* h_out = nullptr;                      // pinned
+    size_t out_records = 0;
 };
 
 extern "C" int pbx_exchange_create(int device, uint32_t rank, uint32_t world, uint32_t max_records, uint32_t max_queries, pbx_exchange** out) {
@@ -1365,10 +1368,67 @@ extern "C" int pbx_exchange_allgather_merge(pbx_exchange* x, const pbx_hit* d_lo
     return PBX_OK;
 }
 
+// Host buffers in, host buffers out, for one rank of the row-sharded path: H2D of the queries, the shard's local search,
+// the fused exchange + merge kernel, D2H of the merged result, one synchronisation -- all on the corpus' stream, no
+// other host work in between (the Python driver's torch copies cost ~30 us per query more).  Every rank makes the same
+// call with the same queries; every rank receives the global result.
+extern "C" int pbx_exchange_search_hits(pbx_exchange* x, pbx_corpus* c, const uint8_t* queries, uint32_t nq, uint32_t k, double max_dist,
+                                        pbx_hit* out_hits, uint32_t* out_count) {
+    if (!x) return fail(PBX_E_INVALID, "exchange is NULL");
+    int rc = check_search_args(c, queries, nq, k);
+    if (rc != PBX_OK) return rc;
+    if (nq == 0) return PBX_OK;
+    if (!out_hits || !out_count) return fail(PBX_E_INVALID, "NULL output");
+    if (!x->connected) return fail(PBX_E_INVALID, "exchange is not connected");
+    if (x->device != c->device) return fail(PBX_E_INVALID, "exchange and corpus live on different devices");
+    if ((uint64_t)nq * k > x->max_records || nq > x->max_queries || nq > 1024)
+        return fail(PBX_E_INVALID, "exchange sized for %u records / %u queries per call, got %u x %u", x->max_records, x->max_queries, nq, k);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU_TRY(cudaSetDevice(c->device));
+    if (!x->d_out) {
+        x->out_records = (size_t)x->max_records + ((size_t)x->max_queries * sizeof(uint32_t) + sizeof(pbx_hit) - 1) / sizeof(pbx_hit) + 1;
+        CU_TRY(cudaMalloc(&x->d_out, x->out_records * sizeof(pbx_hit)));
+        CU_TRY(cudaMallocHost(&x->h_out, x->out_records * sizeof(pbx_hit)));
+    }
+    rc = ensure_query_scratch(c, nq);
+    if (rc != PBX_OK) return rc;
+    rc = ensure_hits(c, (size_t)nq * k, nq);
+    if (rc != PBX_OK) return rc;
+    const size_t qbytes = (size_t)nq * c->dim;
+    if (qbytes > c->h_queries_cap) {
+        cudaFreeHost(c->h_queries); c->h_queries = nullptr; c->h_queries_cap = 0;
+        CU_TRY(cudaMallocHost(&c->h_queries, std::max<size_t>(qbytes, 64 * 1024)));
+        c->h_queries_cap = std::max<size_t>(qbytes, 64 * 1024);
+    }
+    memcpy(c->h_queries, queries, qbytes);
+    CU_TRY(cudaMemcpyAsync(c->d_queries, c->h_queries, qbytes, cudaMemcpyHostToDevice, c->stream));
+    uint32_t* d_cnt_local = reinterpret_cast<uint32_t*>(c->d_hits + (size_t)nq * k);
+    rc = enqueue_search(c, c->d_queries, nq, k, max_dist, c->d_hits, d_cnt_local, c->stream, false);
+    if (rc != PBX_OK) return rc;
+    uint32_t* d_cnt_out = reinterpret_cast<uint32_t*>(x->d_out + (size_t)nq * k);
+    rc = pbx_exchange_allgather_merge(x, c->d_hits, nq, k, x->d_out, d_cnt_out, c->stream);
+    if (rc != PBX_OK) return rc;
+    const size_t out_bytes = (size_t)nq * k * sizeof(pbx_hit) + (size_t)nq * sizeof(uint32_t);
+    CU_TRY(cudaMemcpyAsync(x->h_out, x->d_out, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    // the local counts too: a refused device-side exact launch shows there (PBX_COUNT_EXACT_LAUNCH_FAILED)
+    CU_TRY(cudaMemcpyAsync(c->h_hits, d_cnt_local, (size_t)nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    const uint32_t* h_cnt = reinterpret_cast<const uint32_t*>(x->h_out + (size_t)nq * k);
+    const uint32_t* h_local = reinterpret_cast<const uint32_t*>(c->h_hits);
+    for (uint32_t q = 0; q < nq; ++q) {
+        if (h_cnt[q] == PBX_COUNT_EXCHANGE_TIMEOUT) return fail(PBX_E_INTERNAL, "peer exchange timed out: a rank did not post its records");
+        if (h_local[q] > k) return fail(PBX_E_INTERNAL, "this shard could not certify query %u (count marker 0x%x)", q, h_local[q]);
+    }
+    memcpy(out_hits, x->h_out, (size_t)nq * k * sizeof(pbx_hit));
+    memcpy(out_count, h_cnt, (size_t)nq * sizeof(uint32_t));
+    return PBX_OK;
+}
+
 extern "C" void pbx_exchange_destroy(pbx_exchange* x) {
     if (!x) return;
     cudaSetDevice(x->device);
     cudaDeviceSynchronize();
+    cudaFree(x->d_out); cudaFreeHost(x->h_out);
     for (uint32_t r = 0; r < x->world; ++r)
         if (r != x->rank && x->peer_base[r]) cudaIpcCloseMemHandle(x->peer_base[r]);
     cudaFree(x->base);

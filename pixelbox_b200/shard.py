@@ -173,7 +173,13 @@ class ShardedCorpus:
         if q.ndim != 2 or q.shape[1] != self.dim:
             raise nat.PbxError(-2, f"search: expected [nq][{self.dim}] bytes, got {tuple(q.shape)}")
         nq = q.shape[0]
-        if self.on_gpu:
+        if self.on_gpu and self._exchange is not None and nq * k <= self.MAX_RECORDS and nq <= self.MAX_QUERIES:
+            # the whole step inside the library: H2D, local search, exchange + merge kernel, D2H, one synchronisation
+            hits = np.empty((nq, k), nat.HIT_DTYPE)
+            cnt = np.empty(nq, np.uint32)
+            nat.check(nat.lib().pbx_exchange_search_hits(self._exchange, self.local.handle, nat.ptr(q), nq, int(k), float(max_dist),
+                                                         nat.ptr(hits), nat.ptr(cnt)))
+        elif self.on_gpu:
             b = self._buffers(nq, k)
             b["hq"].copy_(torch.from_numpy(q.reshape(-1)))
             b["q"].copy_(b["hq"], non_blocking=True)
