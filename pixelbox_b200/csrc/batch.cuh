@@ -326,13 +326,14 @@ __device__ unsigned long long g_batch_prof[2048][12];
 #endif
 static_assert(true, "");
 constexpr uint32_t kBatchMetaSlots = 4;      // (power of two) ring of per-tile metadata (inv_norm, row_sum, block metadata of the tile's rows)
-constexpr uint32_t kBatchScrWords = 36;      // survivor scratch slot: 32 scores + {bound, threshold, colterm, query}
+constexpr uint32_t kBatchScrWords = 40;      // survivor scratch slot: 32 scores + {bound, threshold, colterm, query, first row, first column}
+constexpr uint32_t kBatchScrSlots = 4;       // per epilogue warp: two for a deferred step, two for the step in hand
 
 // Dynamic shared memory of batch_mma_kernel after the 1024-byte alignment fix-up; the host sizes the ring with it.
 __host__ __device__ inline size_t batch_smem_fixed(uint32_t qg, uint32_t tn) {
     return (size_t)qg * 12                                            // s_colterm, s_thr, s_invq
            + (size_t)kBatchMetaSlots * (tn * 8 + tn / 2)              // metadata ring: inv_norm, row_sum, 16 B per 32 rows
-           + (size_t)kBatchEpiWarps * 2 * kBatchScrWords * 4          // survivor scratch
+           + (size_t)kBatchEpiWarps * kBatchScrSlots * kBatchScrWords * 4   // survivor scratch
            + (size_t)kBatchEpiWarps * kBatchStage * 12;               // staged candidates (key + query)
 }
 
@@ -362,8 +363,8 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
     float* s_minv = reinterpret_cast<float*>(sA + (size_t)STAGES * stage_bytes);   // [kBatchMetaSlots][TN] inv_norm of the tile's rows
     int* s_mrs = reinterpret_cast<int*>(s_minv + kBatchMetaSlots * TN);            // [kBatchMetaSlots][TN] row_sum
     float4* s_mblk = reinterpret_cast<float4*>(s_mrs + kBatchMetaSlots * TN);      // [kBatchMetaSlots][TN / 32] block metadata
-    int* s_scr = reinterpret_cast<int*>(s_mblk + kBatchMetaSlots * (TN / 32u));    // [epilogue warp][2][kBatchScrWords] survivor scratch
-    u64* st_key = reinterpret_cast<u64*>(s_scr + kBatchEpiWarps * 2 * kBatchScrWords);   // [epilogue warp][kBatchStage]
+    int* s_scr = reinterpret_cast<int*>(s_mblk + kBatchMetaSlots * (TN / 32u));    // [epilogue warp][kBatchScrSlots][kBatchScrWords] survivor scratch
+    u64* st_key = reinterpret_cast<u64*>(s_scr + kBatchEpiWarps * kBatchScrSlots * kBatchScrWords);   // [epilogue warp][kBatchStage]
     uint32_t* st_q = reinterpret_cast<uint32_t*>(st_key + kBatchEpiWarps * kBatchStage);
     int* s_colterm = reinterpret_cast<int*>(st_q + kBatchEpiWarps * kBatchStage);
     float* s_thr = reinterpret_cast<float*>(s_colterm + QG);
@@ -526,7 +527,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
         u64* my_key = st_key + e * kBatchStage;
         uint32_t* my_q = st_q + e * kBatchStage;
         uint32_t* my_cnt = &st_cnt[e];
-        int* my_scr = s_scr + e * (2 * kBatchScrWords);              // two survivor slots: 32 scores + {v, thr, ct, qi}
+        int* my_scr = s_scr + e * (kBatchScrSlots * kBatchScrWords);   // survivor slots: 32 scores + {v, thr, ct, qi, row0, col0}
         const uint32_t acc_empty0 = CG == 1 ? smem_u32(&acc_empty[0]) : mapa_u32(smem_u32(&acc_empty[0]), 0);
 
         // Accepted candidates are staged per warp in shared memory and leave in two steps that never wait for each other
@@ -652,43 +653,52 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
             const float m = fabsf(tt) + fabsf(ctf) + fabsf(rt_f);       // every rounding above is relative to one of these
             return __float2int_rd(0.25f * (fmaf(m, -4.0e-6f, y) - 8.0f));
         };
-        // Rare: `pass` lanes (queries) may have a hit among the 32 rows [row0, row0 + 32) whose scores they hold in r.  Two
-        // lanes at a time dump their scores and their {bound, threshold, colterm, query} into the warp's scratch, then the
-        // whole warp tests one dumped query per step, one ROW per lane, against the per-row metadata the producer left in
-        // shared memory.  No unrolled per-register code, no register carried across.
-        auto resolve = [&](const uint32_t* r, const bool pass, const int v, const float thr, const int ct, const uint32_t qi,
-                           const uint32_t row0, const float* inv_s, const int* rs_s) {
-            uint32_t mask = __ballot_sync(0xFFFFFFFFu, pass);
+        // Rare: some lanes (queries) may have a hit among the 32 rows [row0, row0 + 32) whose scores they hold in r.  Such a
+        // lane dumps its scores and {bound, threshold, colterm, query, first row, first column} into one of the warp's
+        // scratch slots (`dump_lane`); the whole warp then tests one dumped query per step, one ROW per lane, against the
+        // per-row metadata the producer left in shared memory (`test_slots`).  No unrolled per-register code, no register
+        // carried across -- and a dump can be tested later, after the accumulator has been handed back.
+        auto dump_lane = [&](const uint32_t* r, const int slot, const int v, const float thr, const int ct, const uint32_t qi,
+                             const uint32_t row0, const uint32_t col0) {
+            int* dst = my_scr + slot * kBatchScrWords;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<int4*>(dst + 4 * i) = make_int4((int)r[4 * i], (int)r[4 * i + 1], (int)r[4 * i + 2], (int)r[4 * i + 3]);
+            *reinterpret_cast<int4*>(dst + 32) = make_int4(v, __float_as_int(thr), ct, (int)qi);
+            *reinterpret_cast<int2*>(dst + 36) = make_int2((int)row0, (int)col0);
+        };
+        auto test_slots = [&](const int first, const int n_slots, const uint32_t ms) {      // warp-converged
+            __syncwarp();
+            for (int sl = first; sl < first + n_slots; ++sl) {
+                const int* src = my_scr + sl * kBatchScrWords;
+                const int4 h = *reinterpret_cast<const int4*>(src + 32);               // broadcast
+                const int2 rc = *reinterpret_cast<const int2*>(src + 36);
+                const int sc = src[lane];
+                const uint32_t row = (uint32_t)rc.x + (uint32_t)lane;
+                if (sc >= h.x && row < p.n) {
+                    const uint32_t mi = ms * TN + (uint32_t)rc.y + (uint32_t)lane;
+                    const int dot_i = 4 * sc + dterm + 2 * s_mrs[mi] + h.z;
+                    const float kf = __fmul_rn((float)dot_i, s_minv[mi]);
+                    if (kf >= __int_as_float(h.y)) {
+                        const u64 key = make_key64(kf, row);
+                        const uint32_t slot = atomicAdd(my_cnt, 1u);
+                        if (slot < kBatchStage) { my_key[slot] = key; my_q[slot] = (uint32_t)h.w; }
+                        else push_global(key, (uint32_t)h.w);
+                    }
+                }
+            }
+            __syncwarp();
+        };
+        // dump + test right away, two lanes at a time (slots 2 and 3)
+        auto resolve_now = [&](const uint32_t* r, uint32_t mask, const int v, const float thr, const int ct, const uint32_t qi,
+                               const uint32_t row0, const uint32_t col0, const uint32_t ms) {
             while (mask) {
                 const int o1 = __ffs(mask) - 1;
                 mask &= mask - 1;
                 const int o2 = mask ? __ffs(mask) - 1 : -1;
                 mask &= mask - 1;                                        // (0 & anything) stays 0
-                if (lane == o1 || lane == o2) {
-                    int* dst = my_scr + (lane == o2 ? kBatchScrWords : 0);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        *reinterpret_cast<int4*>(dst + 4 * i) = make_int4((int)r[4 * i], (int)r[4 * i + 1], (int)r[4 * i + 2], (int)r[4 * i + 3]);
-                    *reinterpret_cast<int4*>(dst + 32) = make_int4(v, __float_as_int(thr), ct, (int)qi);
-                }
-                __syncwarp();
-                const int n_slots = o2 >= 0 ? 2 : 1;
-                for (int sl = 0; sl < n_slots; ++sl) {
-                    const int* src = my_scr + sl * kBatchScrWords;
-                    const int4 h = *reinterpret_cast<const int4*>(src + 32);           // broadcast
-                    const int sc = src[lane];
-                    if (sc >= h.x && row0 + (uint32_t)lane < p.n) {
-                        const int dot_i = 4 * sc + dterm + 2 * rs_s[lane] + h.z;
-                        const float kf = __fmul_rn((float)dot_i, inv_s[lane]);
-                        if (kf >= __int_as_float(h.y)) {
-                            const u64 key = make_key64(kf, row0 + (uint32_t)lane);
-                            const uint32_t slot = atomicAdd(my_cnt, 1u);
-                            if (slot < kBatchStage) { my_key[slot] = key; my_q[slot] = (uint32_t)h.w; }
-                            else push_global(key, (uint32_t)h.w);
-                        }
-                    }
-                }
-                __syncwarp();
+                if (lane == o1 || lane == o2) dump_lane(r, lane == o2 ? 3 : 2, v, thr, ct, qi, row0, col0);
+                test_slots(2, o2 >= 0 ? 2 : 1, ms);
             }
         };
 
@@ -718,6 +728,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                 if (threadIdx.x == 0) { PBX_BP_ADD(5, te5); g_prof_stage(); }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t taddr = tmem + ((quarter * 32u) << 16) + ab * TN + col_base;
+                int deferred = 0;                                      // dumped survivors of an earlier step, not tested yet
 #pragma unroll 1
                 for (uint32_t hf = 0; hf < STEPS; ++hf) {              // WIDTH columns = one or two 32-row blocks at a time
                     const uint32_t col0 = col_base + WIDTH * hf, row0 = t * TN + col0;
@@ -755,11 +766,31 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                         bm.x = fminf(bm0.x, bm1.x); bm.y = fmaxf(bm0.y, bm1.y);
                         bm.z = __int_as_float(max(__float_as_int(bm0.z), __float_as_int(bm1.z))); bm.w = 0.0f;
                         const int v = bound(thr, ct, bm);
-                        const bool p0 = mx0 >= v, p1 = WIDTH == 64 && mx1 >= v;
-                        if (__any_sync(0xFFFFFFFFu, p0 || p1)) {
-                            resolve(r, p0, v, thr, ct, qi, row0, s_minv + ms * TN + col0, s_mrs + ms * TN + col0);
-                            if constexpr (WIDTH == 64)
-                                resolve(r + WIDTH - 32, p1, v, thr, ct, qi, row0 + 32u, s_minv + ms * TN + col0 + 32u, s_mrs + ms * TN + col0 + 32u);
+                        const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, mx0 >= v);
+                        if constexpr (WIDTH == 32) {
+#ifdef PBX_BATCH_DEFER        // measured: 2.42 ms instead of 2.23 at 10M x 256 x 1024, 3.29 instead of 2.66 at 12.5M x 64 -- off
+                            if (hf + 1 < STEPS) {
+#else
+                            if (false) {
+#endif
+                                // Experiment (PBX_BATCH_DEFER): in the steps before the last, one or two survivors are only dumped
+                                // and tested after the accumulator has been handed back.  Slower in every shape but dim 1024.
+                                if (m0) {
+                                    if (__popc(m0) <= 2) {
+                                        if (mx0 >= v) dump_lane(r, __popc(m0 & ((1u << lane) - 1u)), v, thr, ct, qi, row0, col0);
+                                        deferred = __popc(m0);
+                                    } else {
+                                        resolve_now(r, m0, v, thr, ct, qi, row0, col0, ms);
+                                    }
+                                }
+                            } else {
+                                if (deferred) { test_slots(0, deferred, ms); deferred = 0; }
+                                if (m0) resolve_now(r, m0, v, thr, ct, qi, row0, col0, ms);
+                            }
+                        } else {
+                            const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, mx1 >= v);
+                            if (m0) resolve_now(r, m0, v, thr, ct, qi, row0, col0, ms);
+                            if (m1) resolve_now(r + WIDTH - 32, m1, v, thr, ct, qi, row0 + 32u, col0 + 32u, ms);
                         }
                     }
                     if (threadIdx.x == 0) PBX_BP_ADD(7, te7);
