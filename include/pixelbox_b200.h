@@ -86,7 +86,7 @@ typedef struct pbx_stats {
     int32_t device;
     int32_t sm_count;
     int32_t scan_grid;         /* CTAs of the persistent scan kernel               */
-    int32_t reserved;
+    int32_t reserved;          /* 1: the shard grows by mapping memory into reserved address ranges (no copy) */
     uint64_t batched_queries;  /* queries answered by the tensor-core batched path */
 } pbx_stats;
 
@@ -108,6 +108,15 @@ PBX_API int pbx_corpus_load(pbx_corpus* c, const int64_t* image_ids, const uint8
  * loop src/engine.rs:188-200, after the INSERT reports a changed row.  Safe to call while
  * another thread is inside pbx_search: a search sees a committed prefix of the rows. */
 PBX_API int pbx_corpus_append(pbx_corpus* c, const int64_t* image_ids, const uint8_t* hashes, uint64_t n);
+/* Appends of fewer than 64 rows are collected on the host and uploaded 1024 at a time (the writer loop inserts one image
+ * at a time); they count as part of the table at once: pbx_corpus_size includes them and every search uploads them before
+ * it runs.  pbx_corpus_flush uploads them now.  The shard grows by mapping more device memory behind its arrays (CUDA
+ * virtual memory management): no copy, no moved pointer, searches keep running while it grows. */
+PBX_API int pbx_corpus_flush(pbx_corpus* c);
+/* The same for rows that are already in device memory on the corpus' device (e.g. produced by pbx_quantize_device):
+ * d_hashes is [n][dim] u8, d_image_ids [n] i64, both DEVICE pointers; the copy and the metadata kernels run on
+ * `cuda_stream` (a cudaStream_t; NULL = an internal stream), which is synchronised before the rows are published. */
+PBX_API int pbx_corpus_append_device(pbx_corpus* c, const int64_t* d_image_ids, const uint8_t* d_hashes, uint64_t n, void* cuda_stream);
 
 /* Bench/test only: fills the shard on the device with rows [first_row, first_row + n) of the
  * counter-based synthetic corpus (pixelbox_b200/synth.py), image_id = global row + 1. */
@@ -242,6 +251,10 @@ PBX_API int pbx_hamming_distance_pairs(int device, const uint8_t* a, const uint8
  * (src/image_hashes/efficientnet.rs:39; README.md:54 example [-1, 1, 0, 0.1] -> [0x00, 0xFF, 0x80, 0x8C]), for a batch
  * of n floats in host memory, so embeddings produced elsewhere can be appended in the table's encoding. */
 PBX_API int pbx_quantize(int device, const float* embeddings, uint64_t n, uint8_t* out);
+/* Device-resident, asynchronous form: both pointers are DEVICE pointers on `device`, the kernel is enqueued on
+ * `cuda_stream` (NULL = the legacy default stream) and the call does not wait -- embeddings produced on the GPU go to
+ * pbx_corpus_append_device without touching the host (src/image_hashes/efficientnet.rs:35-40). */
+PBX_API int pbx_quantize_device(int device, const float* d_embeddings, uint64_t n, uint8_t* d_out, void* cuda_stream);
 
 /* ---- diagnostics ------------------------------------------------------------------------- */
 PBX_API int pbx_get_stats(const pbx_corpus* c, pbx_stats* out);

@@ -83,6 +83,15 @@ class Corpus:
             raise nat.PbxError(-1, "append: one image_id per hash row required")
         nat.check(nat.lib().pbx_corpus_append(self._h, nat.ptr(ids), nat.ptr(hashes), hashes.shape[0]))
 
+    def flush(self) -> None:
+        """Uploads the coalesced small appends now (searches do it on their own)."""
+        nat.check(nat.lib().pbx_corpus_flush(self._h))
+
+    def append_device(self, d_ids_ptr: int, d_hashes_ptr: int, n: int, stream: Optional[int] = None) -> None:
+        """pbx_corpus_append_device: [n] int64 ids and [n][dim] u8 rows already in device memory (raw pointers)."""
+        nat.check(nat.lib().pbx_corpus_append_device(self._h, ctypes.c_void_p(d_ids_ptr), ctypes.c_void_p(d_hashes_ptr), int(n),
+                                                     ctypes.c_void_p(stream or 0)))
+
     def fill_synthetic(self, n: int, seed: int, first_row: int = 0) -> None:
         nat.check(nat.lib().pbx_corpus_fill_synthetic(self._h, int(n), int(seed), int(first_row)))
 
@@ -310,6 +319,11 @@ def hamming_distance_pairs(a, b, device: int = 0):
     dist, bits = np.zeros(n, np.float32), np.zeros(n, np.uint32)
     nat.check(nat.lib().pbx_hamming_distance_pairs(int(device), nat.ptr(a), nat.ptr(b), n, d, nat.ptr(dist), nat.ptr(bits)))
     return dist, bits
+
+
+def quantize_device(d_in_ptr: int, n: int, d_out_ptr: int, device: int = 0, stream: Optional[int] = None) -> None:
+    """pbx_quantize_device: n floats at d_in_ptr -> n bytes at d_out_ptr, both device memory; asynchronous on `stream`."""
+    nat.check(nat.lib().pbx_quantize_device(int(device), ctypes.c_void_p(d_in_ptr), int(n), ctypes.c_void_p(d_out_ptr), ctypes.c_void_p(stream or 0)))
 
 
 def quantize(embeddings, device: int = 0) -> np.ndarray:

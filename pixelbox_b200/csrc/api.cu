@@ -40,6 +40,94 @@ static int fail(int code, const char* fmt, ...) {
     } while (0)
 
 // ------------------------------------------------------------------------------------------------
+// growable device arrays on CUDA virtual memory management
+// ------------------------------------------------------------------------------------------------
+// A shard's arrays grow by MAPPING more physical memory at the end of an address range reserved once (cuMemAddressReserve
+// + cuMemCreate / cuMemMap on demand): the device pointers never move, nothing is copied, and a search that runs
+// concurrently with the growth is not disturbed (the first version re-allocated x1.5, copied the whole shard device to
+// device under the search lock and needed 2.5x the shard in HBM while doing so).  The driver entry points are fetched at
+// run time (the library does not link libcuda); if they are missing, or PBX_NO_VMM is set, plain cudaMalloc + copy is used.
+struct VmmApi {
+    CUresult (*reserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*free_)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+    CUresult (*release)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*unmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*set_access)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+    CUresult (*granularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+    bool ok = false;
+};
+static const VmmApi& vmm_api() {
+    static VmmApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        if (getenv("PBX_NO_VMM")) return;
+        cudaDriverEntryPointQueryResult q;
+        auto get = [&](const char* name, void** fn) { return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && *fn != nullptr; };
+        api.ok = get("cuMemAddressReserve", (void**)&api.reserve) && get("cuMemAddressFree", (void**)&api.free_) && get("cuMemCreate", (void**)&api.create) &&
+                 get("cuMemRelease", (void**)&api.release) && get("cuMemMap", (void**)&api.map) && get("cuMemUnmap", (void**)&api.unmap) &&
+                 get("cuMemSetAccess", (void**)&api.set_access) && get("cuMemGetAllocationGranularity", (void**)&api.granularity);
+        cudaGetLastError();
+    });
+    return api;
+}
+struct VmmArray {
+    CUdeviceptr base = 0;
+    size_t reserved = 0, mapped = 0, gran = 0;
+    std::vector<std::pair<CUmemGenericAllocationHandle, size_t>> chunks;
+};
+static CUmemAllocationProp vmm_prop(int device) {
+    CUmemAllocationProp prop = {};
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = device;
+    return prop;
+}
+static bool vmm_reserve(VmmArray& a, int device, size_t bytes) {
+    const VmmApi& api = vmm_api();
+    const CUmemAllocationProp prop = vmm_prop(device);
+    if (api.granularity(&a.gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || a.gran == 0) return false;
+    a.reserved = (bytes + a.gran - 1) / a.gran * a.gran;
+    return api.reserve(&a.base, a.reserved, 0, 0, 0) == CUDA_SUCCESS;
+}
+// Maps physical memory so that at least `need` bytes are backed.  Returns the newly mapped range in [*from, *to).
+static int vmm_grow(VmmArray& a, int device, size_t need, size_t* from, size_t* to) {
+    *from = *to = a.mapped;
+    if (need <= a.mapped) return PBX_OK;
+    if (need > a.reserved) return fail(PBX_E_CAPACITY, "shard outgrew the address range reserved for it (%zu > %zu bytes)", need, a.reserved);
+    const VmmApi& api = vmm_api();
+    const size_t add = (need - a.mapped + a.gran - 1) / a.gran * a.gran;
+    const CUmemAllocationProp prop = vmm_prop(device);
+    CUmemGenericAllocationHandle h;
+    CUresult r = api.create(&h, add, &prop, 0);
+    if (r != CUDA_SUCCESS) return fail(PBX_E_OOM, "cannot back %zu more bytes on device %d (cuMemCreate: %d)", add, device, (int)r);
+    r = api.map(a.base + a.mapped, add, 0, h, 0);
+    if (r == CUDA_SUCCESS) {
+        CUmemAccessDesc acc = {};
+        acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        acc.location.id = device;
+        acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        r = api.set_access(a.base + a.mapped, add, &acc, 1);
+        if (r != CUDA_SUCCESS) api.unmap(a.base + a.mapped, add);
+    }
+    if (r != CUDA_SUCCESS) { api.release(h); return fail(PBX_E_CUDA, "mapping %zu bytes failed (%d)", add, (int)r); }
+    a.chunks.emplace_back(h, add);
+    *to = a.mapped + add;
+    a.mapped += add;
+    return PBX_OK;
+}
+static void vmm_release(VmmArray& a) {
+    const VmmApi& api = vmm_api();
+    if (a.base) {
+        if (a.mapped) api.unmap(a.base, a.mapped);
+        for (auto& c : a.chunks) api.release(c.first);
+        api.free_(a.base, a.reserved);
+    }
+    a = VmmArray();
+}
+
+// ------------------------------------------------------------------------------------------------
 // corpus
 // ------------------------------------------------------------------------------------------------
 struct pbx_corpus {
@@ -52,6 +140,13 @@ struct pbx_corpus {
     float* d_inv = nullptr;
     int* d_rsum = nullptr;            // sum of the raw bytes of each row (batched tensor-core path)
     float4* d_bmeta = nullptr;        // per 32-row block {norm_lo, norm_hi, rowterm_max}: the batched epilogue's bound
+    bool use_vmm = false;             // the five arrays above live in reserved address ranges and grow by mapping (never move)
+    VmmArray v_rows, v_inv, v_rsum, v_ids, v_bmeta;
+    uint64_t reserved_rows = 0;       // rows the address ranges were reserved for
+    // small appends are coalesced on the host and uploaded in blocks (or when a search needs them)
+    std::vector<uint8_t> pend_rows;
+    std::vector<int64_t> pend_ids;
+    std::atomic<uint64_t> pending{0};
     int64_t* d_ids = nullptr;
 
     cudaStream_t stream = nullptr;    // default search stream
@@ -146,6 +241,13 @@ static float certificate_margin(uint32_t dim) {
 }
 
 static int free_corpus_buffers(pbx_corpus* c) {
+    if (c->use_vmm) {
+        vmm_release(c->v_rows); vmm_release(c->v_inv); vmm_release(c->v_rsum); vmm_release(c->v_ids); vmm_release(c->v_bmeta);
+        c->d_rows = nullptr; c->d_inv = nullptr; c->d_ids = nullptr; c->d_rsum = nullptr; c->d_bmeta = nullptr;
+        c->capacity = 0;
+        c->use_vmm = false;
+        return PBX_OK;
+    }
     cudaFree(c->d_rows); cudaFree(c->d_inv); cudaFree(c->d_ids); cudaFree(c->d_rsum); cudaFree(c->d_bmeta);
     c->d_rows = nullptr; c->d_inv = nullptr; c->d_ids = nullptr; c->d_rsum = nullptr; c->d_bmeta = nullptr;
     c->capacity = 0;
@@ -153,11 +255,39 @@ static int free_corpus_buffers(pbx_corpus* c) {
 }
 
 // (re)allocates row storage for at least `rows` rows, keeping the committed prefix.  Caller holds mu.
+// Growth on reserved address ranges: map more memory behind the arrays, zero it, done.  Pointers and committed rows stay
+// where they are, so no search has to be kept out.  Caller holds append_mu (appends among themselves).
+static int reserve_rows_vmm(pbx_corpus* c, uint64_t want) {
+    struct Arr { VmmArray* a; size_t elem; } arrs[5] = {{&c->v_rows, (size_t)c->pitch}, {&c->v_inv, sizeof(float)}, {&c->v_rsum, sizeof(int)},
+                                                        {&c->v_ids, sizeof(int64_t)}, {&c->v_bmeta, sizeof(float4)}};
+    for (int i = 0; i < 5; ++i) {
+        const size_t need = i == 4 ? (size_t)(want / 32) * arrs[i].elem : (size_t)want * arrs[i].elem;
+        size_t from = 0, to = 0;
+        int rc = vmm_grow(*arrs[i].a, c->device, need, &from, &to);
+        if (rc != PBX_OK) return rc;
+        // rows beyond the committed prefix are read (and ignored) by whole-tile loads: keep them defined
+        if (to > from) CU_TRY(cudaMemsetAsync(reinterpret_cast<void*>(arrs[i].a->base + from), 0, to - from, c->copy_stream));
+    }
+    CU_TRY(cudaStreamSynchronize(c->copy_stream));
+    c->capacity = want;
+    return PBX_OK;
+}
+
 static int reserve_rows(pbx_corpus* c, uint64_t rows) {
     if (rows <= c->capacity) return PBX_OK;
     if (rows > PBX_MAX_ROWS) return fail(PBX_E_CAPACITY, "shard would hold %llu rows (max %llu)", (unsigned long long)rows, (unsigned long long)PBX_MAX_ROWS);
     uint64_t want = std::max<uint64_t>(rows, c->capacity + c->capacity / 2);
     want = (want + kTileRows - 1) / kTileRows * kTileRows;
+    if (c->use_vmm) {
+        want = std::min<uint64_t>(want, c->reserved_rows);
+        if (rows > c->reserved_rows) return fail(PBX_E_CAPACITY, "shard would hold %llu rows; its address range was reserved for %llu", (unsigned long long)rows, (unsigned long long)c->reserved_rows);
+        int rc = reserve_rows_vmm(c, want);
+        if (rc != PBX_OK && want > rows) {           // retry without growth head-room
+            want = (rows + kTileRows - 1) / kTileRows * kTileRows;
+            rc = reserve_rows_vmm(c, want);
+        }
+        return rc;
+    }
     uint8_t* nr = nullptr; float* ni = nullptr; int64_t* nid = nullptr; int* ns = nullptr; float4* nb = nullptr;
     auto alloc_all = [&](uint64_t rows_) {
         cudaError_t e_ = cudaMalloc(&nr, rows_ * c->pitch);
@@ -260,6 +390,7 @@ template <typename Kern>
 static cudaError_t allow_smem(Kern kern, size_t bytes) {
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
+constexpr uint64_t kBatchMaxRows = 0x7FFFF000ull;    // rows the batched path can address (TMA row coordinate is a signed 32-bit int)
 constexpr uint32_t kBatchSeedTiles = 256;            // sample tiles of the batched path's seed pass
 constexpr size_t kBatchSmemLimit = 232448 - 1024;   // 227 KB per CTA minus the kernel's static shared memory
 static cudaError_t init_kernel_attributes() {
@@ -363,6 +494,25 @@ extern "C" int pbx_corpus_create(uint32_t dim, uint64_t capacity_hint, int devic
         pbx_corpus_destroy(c);
         return rc;
     }
+    if (vmm_api().ok) {
+        // address ranges for as many rows as the device could ever hold (HBM size / bytes per row), at most PBX_MAX_ROWS
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const uint64_t per_row = (uint64_t)c->pitch + 4 + 4 + 8 + 1;
+        uint64_t max_rows = std::min<uint64_t>(PBX_MAX_ROWS, std::max<uint64_t>((uint64_t)total_b / per_row, capacity_hint) + kTileRows);
+        max_rows = (max_rows + kTileRows - 1) / kTileRows * kTileRows;
+        c->use_vmm = vmm_reserve(c->v_rows, device, max_rows * c->pitch) && vmm_reserve(c->v_inv, device, max_rows * sizeof(float)) &&
+                     vmm_reserve(c->v_rsum, device, max_rows * sizeof(int)) && vmm_reserve(c->v_ids, device, max_rows * sizeof(int64_t)) &&
+                     vmm_reserve(c->v_bmeta, device, max_rows / 32 * sizeof(float4));
+        if (c->use_vmm) {
+            c->reserved_rows = max_rows;
+            c->d_rows = reinterpret_cast<uint8_t*>(c->v_rows.base); c->d_inv = reinterpret_cast<float*>(c->v_inv.base);
+            c->d_rsum = reinterpret_cast<int*>(c->v_rsum.base); c->d_ids = reinterpret_cast<int64_t*>(c->v_ids.base);
+            c->d_bmeta = reinterpret_cast<float4*>(c->v_bmeta.base);
+        } else {
+            vmm_release(c->v_rows); vmm_release(c->v_inv); vmm_release(c->v_rsum); vmm_release(c->v_ids); vmm_release(c->v_bmeta);
+        }
+    }
     {
         std::lock_guard<std::mutex> lk(c->mu);
         int rc = reserve_rows(c, std::max<uint64_t>(capacity_hint, 1));
@@ -395,7 +545,7 @@ extern "C" void pbx_corpus_destroy(pbx_corpus* c) {
 
 extern "C" int pbx_corpus_size(const pbx_corpus* c, uint64_t* n_rows) {
     if (!c || !n_rows) return fail(PBX_E_INVALID, "NULL argument");
-    *n_rows = c->n.load();
+    *n_rows = c->n.load() + c->pending.load(std::memory_order_acquire);      // pending (coalesced) appends are part of the table
     return PBX_OK;
 }
 extern "C" int pbx_corpus_synchronize(pbx_corpus* c) {
@@ -472,8 +622,13 @@ static int append_locked(pbx_corpus* c, const int64_t* image_ids, const uint8_t*
     CU_TRY(cudaSetDevice(c->device));
     const uint64_t at = c->n.load();
     if (at + n > c->capacity) {
-        std::lock_guard<std::mutex> lk(c->mu);      // growth moves the buffers: no search may be running
-        int rc = reserve_rows(c, at + n);
+        int rc;
+        if (c->use_vmm) {
+            rc = reserve_rows(c, at + n);               // maps more memory behind the arrays: searches keep running
+        } else {
+            std::lock_guard<std::mutex> lk(c->mu);      // growth moves the buffers: no search may be running
+            rc = reserve_rows(c, at + n);
+        }
         if (rc != PBX_OK) return rc;
     }
     // rows beyond the committed prefix are invisible to concurrent searches until n is published
@@ -483,12 +638,82 @@ static int append_locked(pbx_corpus* c, const int64_t* image_ids, const uint8_t*
     return PBX_OK;
 }
 
+// Small appends (the indexer inserts one image at a time, src/engine.rs:186-203) are collected on the host and uploaded
+// in blocks: one staged copy + metadata launch + synchronisation per kAppendBlock rows instead of per row.  Pending rows
+// are part of the table: the size includes them and every search uploads them first.  Caller holds append_mu.
+constexpr uint64_t kAppendCoalesceBelow = 64;       // appends of fewer rows than this are collected
+constexpr uint64_t kAppendBlock = 1024;             // ... and uploaded when this many are waiting
+static int flush_pending_locked(pbx_corpus* c) {
+    const uint64_t m = c->pend_ids.size();
+    if (m == 0) return PBX_OK;
+    int rc = append_locked(c, c->pend_ids.data(), c->pend_rows.data(), m);
+    if (rc != PBX_OK) return rc;                    // the rows stay pending
+    c->pend_ids.clear();
+    c->pend_rows.clear();
+    c->pending.store(0, std::memory_order_release);
+    return PBX_OK;
+}
+static int flush_pending(pbx_corpus* c) {
+    if (c->pending.load(std::memory_order_acquire) == 0) return PBX_OK;
+    std::lock_guard<std::mutex> alk(c->append_mu);
+    return flush_pending_locked(c);
+}
+
 extern "C" int pbx_corpus_append(pbx_corpus* c, const int64_t* image_ids, const uint8_t* hashes, uint64_t n) {
     if (!c) return fail(PBX_E_INVALID, "corpus is NULL");
     if (n == 0) return PBX_OK;
     if (!image_ids || !hashes) return fail(PBX_E_INVALID, "NULL ids or hashes with n > 0");
     std::lock_guard<std::mutex> alk(c->append_mu);
+    if (n < kAppendCoalesceBelow) {
+        try {
+            c->pend_ids.insert(c->pend_ids.end(), image_ids, image_ids + n);
+            c->pend_rows.insert(c->pend_rows.end(), hashes, hashes + n * c->dim);
+        } catch (...) { return fail(PBX_E_OOM, "host allocation failed"); }
+        c->pending.store(c->pend_ids.size(), std::memory_order_release);
+        return c->pend_ids.size() >= kAppendBlock ? flush_pending_locked(c) : PBX_OK;
+    }
+    int rc = flush_pending_locked(c);               // keep the order of arrival
+    if (rc != PBX_OK) return rc;
     return append_locked(c, image_ids, hashes, n);
+}
+
+extern "C" int pbx_corpus_flush(pbx_corpus* c) {
+    if (!c) return fail(PBX_E_INVALID, "corpus is NULL");
+    return flush_pending(c);
+}
+
+// Rows that are already on the device (embeddings quantized there): [n][dim] bytes and [n] ids, both DEVICE pointers on
+// the corpus' device.  Copies them behind the committed rows on `cuda_stream`, computes their metadata, waits for that
+// stream and publishes them.
+extern "C" int pbx_corpus_append_device(pbx_corpus* c, const int64_t* d_image_ids, const uint8_t* d_hashes, uint64_t n, void* cuda_stream) {
+    if (!c) return fail(PBX_E_INVALID, "corpus is NULL");
+    if (n == 0) return PBX_OK;
+    if (!d_image_ids || !d_hashes) return fail(PBX_E_INVALID, "NULL ids or hashes with n > 0");
+    std::lock_guard<std::mutex> alk(c->append_mu);
+    CU_TRY(cudaSetDevice(c->device));
+    int rc = flush_pending_locked(c);
+    if (rc != PBX_OK) return rc;
+    const uint64_t at = c->n.load();
+    if (at + n > c->capacity) {
+        if (c->use_vmm) {
+            rc = reserve_rows(c, at + n);
+        } else {
+            std::lock_guard<std::mutex> lk(c->mu);
+            rc = reserve_rows(c, at + n);
+        }
+        if (rc != PBX_OK) return rc;
+    }
+    cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->copy_stream;
+    // tight [n][dim] rows -> pitched rows (the padding of fresh capacity is zero already)
+    CU_TRY(cudaMemcpy2DAsync(c->d_rows + at * c->pitch, c->pitch, d_hashes, c->dim, c->dim, n, cudaMemcpyDeviceToDevice, s));
+    CU_TRY(cudaMemcpyAsync(c->d_ids + at, d_image_ids, n * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+    row_meta_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(reinterpret_cast<const uint4*>(c->d_rows), c->pitch16, c->dim, at, n, c->d_inv, c->d_rsum);
+    const uint64_t b0 = at / 32, b1 = (at + n + 31) / 32;
+    block_meta_kernel<<<(unsigned)((b1 - b0 + 7) / 8), 256, 0, s>>>(c->d_inv, c->d_rsum, c->dim, b0, b1 - b0, at + n, c->d_bmeta);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(s));
+    c->n.store(at + n);
+    return PBX_OK;
 }
 
 extern "C" int pbx_corpus_load(pbx_corpus* c, const int64_t* image_ids, const uint8_t* hashes, uint64_t n) {
@@ -500,6 +725,7 @@ extern "C" int pbx_corpus_load(pbx_corpus* c, const int64_t* image_ids, const ui
         CU_TRY(cudaSetDevice(c->device));
         CU_TRY(cudaDeviceSynchronize());
         c->n.store(0);
+        c->pend_ids.clear(); c->pend_rows.clear(); c->pending.store(0);
     }
     return n ? append_locked(c, image_ids, hashes, n) : PBX_OK;
 }
@@ -511,6 +737,7 @@ extern "C" int pbx_corpus_fill_synthetic(pbx_corpus* c, uint64_t n, uint64_t see
     CU_TRY(cudaSetDevice(c->device));
     CU_TRY(cudaDeviceSynchronize());
     c->n.store(0);
+    c->pend_ids.clear(); c->pend_rows.clear(); c->pending.store(0);
     int rc = reserve_rows(c, std::max<uint64_t>(n, 1));
     if (rc != PBX_OK) return rc;
     if (n == 0) return PBX_OK;
@@ -532,6 +759,7 @@ extern "C" int pbx_corpus_fill_synthetic(pbx_corpus* c, uint64_t n, uint64_t see
 extern "C" int pbx_corpus_read_rows(const pbx_corpus* cc, uint64_t first, uint64_t n, int64_t* image_ids, uint8_t* hashes) {
     pbx_corpus* c = const_cast<pbx_corpus*>(cc);
     if (!c) return fail(PBX_E_INVALID, "corpus is NULL");
+    { int frc = flush_pending(c); if (frc != PBX_OK) return frc; }
     const uint64_t size_now = c->n.load();
     if (n > size_now || first > size_now - n) return fail(PBX_E_INVALID, "rows [%llu, %llu) outside the corpus", (unsigned long long)first, (unsigned long long)(first + n));
     if (n == 0) return PBX_OK;
@@ -725,7 +953,7 @@ static bool batch_eligible(const pbx_corpus* c, uint32_t nq, uint32_t n, uint32_
     // needs keep well below the capacity, larger k loops over the single-query scan
     const uint32_t keep = batch_keep(k, c->slack);
     BatchPlan bp;
-    if (nq < c->batch_min || keep * 8u > kBatchCapLarge || !batch_plan(c, std::min<uint32_t>(nq, 1024u), &bp)) return false;
+    if (nq < c->batch_min || keep * 8u > kBatchCapLarge || n > kBatchMaxRows || !batch_plan(c, std::min<uint32_t>(nq, 1024u), &bp)) return false;
     uint32_t seed_tiles, seed_step;
     batch_seed_geometry(n, bp.tn, &seed_tiles, &seed_step);
     return seed_tiles * (bp.tn / 32u) >= keep + keep / 2u;
@@ -835,7 +1063,9 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
     if (rc != PBX_OK) return rc;
     const uint32_t box_rows = bp.tn / bp.cg, qbox = (bp.qg % 256u) ? 128u : 256u;
     if (c->map_rows_gen != c->rows_generation || c->map_rows_box != box_rows) {
-        rc = make_u8_map(&c->map_rows, c->d_rows, c->capacity, pitch, bp.w, box_rows);
+        // with reserved address ranges the map covers the whole range once: tiles beyond the committed rows are never touched
+        // (TMA coordinates are signed 32-bit: a row dimension beyond 2^31 makes the copy an illegal instruction)
+        rc = make_u8_map(&c->map_rows, c->d_rows, std::min<uint64_t>(c->use_vmm ? c->reserved_rows : c->capacity, kBatchMaxRows), pitch, bp.w, box_rows);
         if (rc != PBX_OK) return rc;
         c->map_rows_gen = c->rows_generation; c->map_rows_box = box_rows;
     }
@@ -1123,6 +1353,8 @@ extern "C" int pbx_search_device(pbx_corpus* c, const uint8_t* d_queries, uint32
     if (rc != PBX_OK) return rc;
     if (nq == 0) return PBX_OK;
     if (!d_hits || !d_count) return fail(PBX_E_INVALID, "NULL output");
+    rc = flush_pending(c);                          // coalesced appends become visible before the search (append lock only)
+    if (rc != PBX_OK) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
     CU_TRY(cudaSetDevice(c->device));
     cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->stream;
@@ -1135,6 +1367,8 @@ extern "C" int pbx_search_hits(pbx_corpus* c, const uint8_t* queries, uint32_t n
     if (rc != PBX_OK) return rc;
     if (nq == 0) return PBX_OK;
     if (!out_hits || !out_count) return fail(PBX_E_INVALID, "NULL output");
+    rc = flush_pending(c);                          // coalesced appends become visible before the search (append lock only)
+    if (rc != PBX_OK) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
     CU_TRY(cudaSetDevice(c->device));
     const uint32_t batch_max = 1024;
@@ -1381,6 +1615,8 @@ extern "C" int pbx_exchange_search_hits(pbx_exchange* x, pbx_corpus* c, const ui
     if (!out_hits || !out_count) return fail(PBX_E_INVALID, "NULL output");
     if (!x->connected) return fail(PBX_E_INVALID, "exchange is not connected");
     if (x->device != c->device) return fail(PBX_E_INVALID, "exchange and corpus live on different devices");
+    rc = flush_pending(c);
+    if (rc != PBX_OK) return rc;
     if ((uint64_t)nq * k > x->max_records || nq > x->max_queries || nq > 1024)
         return fail(PBX_E_INVALID, "exchange sized for %u records / %u queries per call, got %u x %u", x->max_records, x->max_queries, nq, k);
     std::lock_guard<std::mutex> lk(c->mu);
@@ -1528,6 +1764,16 @@ extern "C" int pbx_quantize(int device, const float* embeddings, uint64_t n, uin
     return PBX_OK;
 }
 
+extern "C" int pbx_quantize_device(int device, const float* d_embeddings, uint64_t n, uint8_t* d_out, void* cuda_stream) {
+    if (n == 0) return PBX_OK;
+    if (!d_embeddings || !d_out) return fail(PBX_E_INVALID, "NULL argument");
+    if (pbx_device_count() == 0) return fail(PBX_E_NO_DEVICE, "no sm_100 device: pixelbox_b200 has no CPU fallback");
+    CU_TRY(cudaSetDevice(device));
+    quantize_kernel<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 65535), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(d_embeddings, n, d_out);
+    CU_TRY(cudaGetLastError());
+    return PBX_OK;
+}
+
 extern "C" int pbx_int8_peak(int device, double* out_tops) {
     if (!out_tops) return fail(PBX_E_INVALID, "out_tops is NULL");
     if (pbx_device_count() == 0) return fail(PBX_E_NO_DEVICE, "no sm_100 device: pixelbox_b200 has no CPU fallback");
@@ -1573,8 +1819,9 @@ extern "C" int pbx_get_stats(const pbx_corpus* cc, pbx_stats* out) {
     if (!c || !out) return fail(PBX_E_INVALID, "NULL argument");
     std::lock_guard<std::mutex> lk(c->mu);
     memset(out, 0, sizeof(*out));
-    out->rows = c->n.load();
+    out->rows = c->n.load() + c->pending.load();
     out->capacity_rows = c->capacity;
+    out->reserved = c->use_vmm ? 1 : 0;             // 1: the arrays grow by mapping memory into reserved address ranges
     out->dim = c->dim;
     out->row_pitch = c->pitch;
     out->queries = c->queries;

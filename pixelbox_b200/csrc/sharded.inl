@@ -184,7 +184,7 @@ extern "C" int pbx_sharded_shard(pbx_sharded* s, uint32_t index, pbx_corpus** ou
 extern "C" int pbx_sharded_size(const pbx_sharded* s, uint64_t* n_rows) {
     if (!s || !n_rows) return fail(PBX_E_INVALID, "NULL argument");
     uint64_t t = 0;
-    for (auto& sh : s->shards) t += sh->c->n.load();
+    for (auto& sh : s->shards) t += sh->c->n.load() + sh->c->pending.load();
     *n_rows = t;
     return PBX_OK;
 }
@@ -210,7 +210,7 @@ extern "C" int pbx_sharded_append(pbx_sharded* s, const int64_t* image_ids, cons
     if (!image_ids || !hashes) return fail(PBX_E_INVALID, "NULL ids or hashes with n > 0");
     pbx_sharded::Shard* best = s->shards[0].get();
     for (auto& sh : s->shards)
-        if (sh->c->n.load() < best->c->n.load()) best = sh.get();
+        if (sh->c->n.load() + sh->c->pending.load() < best->c->n.load() + best->c->pending.load()) best = sh.get();
     return pbx_corpus_append(best->c, image_ids, hashes, n);
 }
 
