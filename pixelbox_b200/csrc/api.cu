@@ -135,7 +135,7 @@ struct pbx_corpus {
     int sm_count = 0;
     uint32_t dim = 0, pitch = 0, pitch16 = 0;
     std::atomic<uint64_t> n{0};       // committed rows (searches see a prefix)
-    uint64_t capacity = 0;            // allocated rows, multiple of kTileRows
+    std::atomic<uint64_t> capacity{0};  // allocated (mapped) rows, multiple of kTileRows
     uint8_t* d_rows = nullptr;
     float* d_inv = nullptr;
     int* d_rsum = nullptr;            // sum of the raw bytes of each row (batched tensor-core path)
@@ -181,11 +181,14 @@ struct pbx_corpus {
     size_t h_queries_cap = 0;
     pbx_hit* h_hits = nullptr;
     size_t h_hits_cap = 0;
-    uint8_t* h_stage = nullptr;       // append staging
-    size_t h_stage_cap = 0;
+    uint8_t* h_stage = nullptr;       // append staging: two slots of stage_rows rows + ids
+    size_t h_stage_cap = 0, stage_rows = 0;
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};
 
     std::mutex mu;                    // searches and structural changes
     std::mutex append_mu;             // appends among themselves
+    std::mutex grow_mu;               // growth steps among themselves (mapped growth runs outside append_mu)
+    cudaStream_t grow_stream = nullptr;   // zero fill of freshly mapped memory
 
     uint32_t slack = 0;               // 0 = default
     uint32_t ctas_per_sm = 0;         // 0 = default
@@ -210,13 +213,16 @@ struct pbx_corpus {
     CUtensorMap map_rows, map_q;
     uint64_t map_rows_gen = ~0ull;
     uint32_t map_q_pad = 0, map_q_box = 0, map_rows_box = 0;
-    uint32_t batch_cg = 2;            // CTAs per cluster of the batched kernel: 2 = cta_group::2 pairs; PBX_BATCH_CG=1: single CTAs
+    uint32_t batch_cg = 0;            // CTAs per cluster of the batched kernel: 0 = by batch size; PBX_BATCH_CG=1 / 2 forces single CTAs / pairs
 
     uint32_t batch_min = 2;           // calls with at least this many queries use the tensor-core path
     uint64_t batched_queries = 0;
     bool scan_timed = false;          // ev_s0/ev_s1 were recorded by the last enqueue
     bool profiling = false;           // record CUDA events around the search / the scan (pbx_set_profiling)
 };
+
+constexpr size_t kStageMinRows = 2048;              // pinned upload staging: covers the coalesced blocks (kAppendBlock + kAppendCoalesceBelow rows)
+static int ensure_stage(pbx_corpus* c, size_t rows_per_slot);
 
 static uint32_t default_keep(uint32_t k, uint32_t slack) {
     uint32_t s = slack ? slack : std::max<uint32_t>(156u, k / 4u);
@@ -256,7 +262,7 @@ static int free_corpus_buffers(pbx_corpus* c) {
 
 // (re)allocates row storage for at least `rows` rows, keeping the committed prefix.  Caller holds mu.
 // Growth on reserved address ranges: map more memory behind the arrays, zero it, done.  Pointers and committed rows stay
-// where they are, so no search has to be kept out.  Caller holds append_mu (appends among themselves).
+// where they are, so no search has to be kept out.  Caller holds grow_mu.
 static int reserve_rows_vmm(pbx_corpus* c, uint64_t want) {
     struct Arr { VmmArray* a; size_t elem; } arrs[5] = {{&c->v_rows, (size_t)c->pitch}, {&c->v_inv, sizeof(float)}, {&c->v_rsum, sizeof(int)},
                                                         {&c->v_ids, sizeof(int64_t)}, {&c->v_bmeta, sizeof(float4)}};
@@ -266,9 +272,9 @@ static int reserve_rows_vmm(pbx_corpus* c, uint64_t want) {
         int rc = vmm_grow(*arrs[i].a, c->device, need, &from, &to);
         if (rc != PBX_OK) return rc;
         // rows beyond the committed prefix are read (and ignored) by whole-tile loads: keep them defined
-        if (to > from) CU_TRY(cudaMemsetAsync(reinterpret_cast<void*>(arrs[i].a->base + from), 0, to - from, c->copy_stream));
+        if (to > from) CU_TRY(cudaMemsetAsync(reinterpret_cast<void*>(arrs[i].a->base + from), 0, to - from, c->grow_stream));
     }
-    CU_TRY(cudaStreamSynchronize(c->copy_stream));
+    CU_TRY(cudaStreamSynchronize(c->grow_stream));
     c->capacity = want;
     return PBX_OK;
 }
@@ -276,7 +282,11 @@ static int reserve_rows_vmm(pbx_corpus* c, uint64_t want) {
 static int reserve_rows(pbx_corpus* c, uint64_t rows) {
     if (rows <= c->capacity) return PBX_OK;
     if (rows > PBX_MAX_ROWS) return fail(PBX_E_CAPACITY, "shard would hold %llu rows (max %llu)", (unsigned long long)rows, (unsigned long long)PBX_MAX_ROWS);
-    uint64_t want = std::max<uint64_t>(rows, c->capacity + c->capacity / 2);
+    // x1.5, and never less than 32 MB of rows per step once the shard exists: a growth step costs five driver mappings
+    // plus a zero fill whatever its size, and an appender holds the append lock while it runs
+    const uint64_t cap_now = c->capacity.load();
+    uint64_t want = std::max<uint64_t>(rows, cap_now + cap_now / 2);
+    if (cap_now) want = std::max<uint64_t>(want, cap_now + (32u << 20) / c->pitch);
     want = (want + kTileRows - 1) / kTileRows * kTileRows;
     if (c->use_vmm) {
         want = std::min<uint64_t>(want, c->reserved_rows);
@@ -338,6 +348,14 @@ static int reserve_rows(pbx_corpus* c, uint64_t rows) {
     c->rows_generation++;                           // device pointers moved: tensor maps must be rebuilt
     c->capacity = want;
     return PBX_OK;
+}
+
+// Mapped growth (reserved address ranges) to at least `rows` rows; needs neither mu nor append_mu.
+static int grow_mapped(pbx_corpus* c, uint64_t rows) {
+    std::lock_guard<std::mutex> g(c->grow_mu);
+    if (rows <= c->capacity.load()) return PBX_OK;
+    CU_TRY(cudaSetDevice(c->device));
+    return reserve_rows(c, rows);
 }
 
 static int ensure_query_scratch(pbx_corpus* c, uint32_t nq) {
@@ -464,17 +482,20 @@ extern "C" int pbx_corpus_create(uint32_t dim, uint64_t capacity_hint, int devic
     c->dim = dim;
     c->split_finalize = getenv("PBX_NO_SPLIT_FINALIZE") == nullptr;
     if (const char* e = getenv("PBX_SPLIT_MIN_BYTES")) c->split_min_bytes = (size_t)atoll(e);
-    if (const char* e = getenv("PBX_BATCH_CG")) c->batch_cg = atoi(e) == 1 ? 1u : 2u;       // experiments / fallback
+    if (const char* e = getenv("PBX_BATCH_CG")) c->batch_cg = atoi(e) == 1 ? 1u : (atoi(e) == 2 ? 2u : 0u);   // experiments
     c->pitch = (dim + 15u) & ~15u;
     c->pitch16 = c->pitch / 16u;
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->grow_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_chain, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_t0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_t1);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_s0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_s1);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_stage[0], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_stage[1], cudaEventDisableTiming);
     if (e == cudaSuccess) e = init_kernel_attributes();
     // Device-side (tail) launches of the exact pass: up to 2 per query of a 1024-query batch are queued by ONE finalize
     // grid.  The default pool holds 2048 pending launches; leave room for back-to-back batches.
@@ -516,6 +537,7 @@ extern "C" int pbx_corpus_create(uint32_t dim, uint64_t capacity_hint, int devic
     {
         std::lock_guard<std::mutex> lk(c->mu);
         int rc = reserve_rows(c, std::max<uint64_t>(capacity_hint, 1));
+        if (rc == PBX_OK) rc = ensure_stage(c, kStageMinRows);
         if (rc != PBX_OK) { pbx_corpus_destroy(c); return rc; }
     }
     *out = c;
@@ -537,8 +559,11 @@ extern "C" void pbx_corpus_destroy(pbx_corpus* c) {
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     if (c->ev_s0) cudaEventDestroy(c->ev_s0);
     if (c->ev_s1) cudaEventDestroy(c->ev_s1);
+    if (c->ev_stage[0]) cudaEventDestroy(c->ev_stage[0]);
+    if (c->ev_stage[1]) cudaEventDestroy(c->ev_stage[1]);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->grow_stream) cudaStreamDestroy(c->grow_stream);
     cudaGetLastError();
     delete c;
 }
@@ -560,18 +585,33 @@ extern "C" int pbx_corpus_dim(const pbx_corpus* c, uint32_t* dim) {
     return PBX_OK;
 }
 
+// Pinned staging of the uploads: two slots of rows_per_slot rows + ids.  Pinned allocations take milliseconds (and the
+// searcher may be waiting for the append lock meanwhile): one at create sized for the coalesced blocks, larger ones only
+// when a bulk load asks for them.
+static int ensure_stage(pbx_corpus* c, size_t rows_per_slot) {
+    const size_t per_row = (size_t)c->pitch + sizeof(int64_t);
+    const size_t need = rows_per_slot * per_row * 2;
+    if (c->h_stage_cap >= need) return PBX_OK;
+    CU_TRY(cudaStreamSynchronize(c->copy_stream));
+    cudaFreeHost(c->h_stage); c->h_stage = nullptr; c->h_stage_cap = 0; c->stage_rows = 0;
+    CU_TRY(cudaMallocHost(&c->h_stage, need));
+    c->h_stage_cap = need;
+    c->stage_rows = rows_per_slot;
+    return PBX_OK;
+}
+
 // copies n host rows to device rows [at, at+n) through pinned staging and computes their metadata
 static int upload_rows(pbx_corpus* c, uint64_t at, const int64_t* ids, const uint8_t* hashes, uint64_t n) {
-    const size_t stage_rows = std::max<size_t>(1, (size_t)(8u << 20) / c->pitch);
+    const size_t max_stage_rows = std::max<size_t>(kStageMinRows, (size_t)(8u << 20) / c->pitch);
     const size_t per_row = (size_t)c->pitch + sizeof(int64_t);
-    if (c->h_stage_cap < stage_rows * per_row * 2) {
-        cudaFreeHost(c->h_stage); c->h_stage = nullptr; c->h_stage_cap = 0;
-        CU_TRY(cudaMallocHost(&c->h_stage, stage_rows * per_row * 2));
-        c->h_stage_cap = stage_rows * per_row * 2;
+    {
+        size_t want = kStageMinRows;
+        while (want < n && want < max_stage_rows) want *= 2;
+        int rc0 = ensure_stage(c, std::min(want, max_stage_rows));
+        if (rc0 != PBX_OK) return rc0;
     }
-    cudaEvent_t done[2];
-    CU_TRY(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
-    CU_TRY(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
+    const size_t stage_rows = c->stage_rows;
+    cudaEvent_t* done = c->ev_stage;
     int rc = PBX_OK;
     uint64_t off = 0;
     int slot = 0;
@@ -612,8 +652,6 @@ static int upload_rows(pbx_corpus* c, uint64_t at, const int64_t* ids, const uin
     }
     cudaError_t e = cudaStreamSynchronize(c->copy_stream);
     if (rc == PBX_OK && e != cudaSuccess) rc = fail(PBX_E_CUDA, "row upload failed: %s", cudaGetErrorString(e));
-    cudaEventDestroy(done[0]);
-    cudaEventDestroy(done[1]);
     return rc;
 }
 
@@ -624,7 +662,7 @@ static int append_locked(pbx_corpus* c, const int64_t* image_ids, const uint8_t*
     if (at + n > c->capacity) {
         int rc;
         if (c->use_vmm) {
-            rc = reserve_rows(c, at + n);               // maps more memory behind the arrays: searches keep running
+            rc = grow_mapped(c, at + n);                // maps more memory behind the arrays: searches keep running
         } else {
             std::lock_guard<std::mutex> lk(c->mu);      // growth moves the buffers: no search may be running
             rc = reserve_rows(c, at + n);
@@ -663,6 +701,13 @@ extern "C" int pbx_corpus_append(pbx_corpus* c, const int64_t* image_ids, const 
     if (!c) return fail(PBX_E_INVALID, "corpus is NULL");
     if (n == 0) return PBX_OK;
     if (!image_ids || !hashes) return fail(PBX_E_INVALID, "NULL ids or hashes with n > 0");
+    if (c->use_vmm) {
+        // Grow AHEAD of need and outside the append lock: a searcher that has to flush pending rows waits for that lock,
+        // and a growth step (five driver mappings + a zero fill) takes about a millisecond.  Failure here is not an error
+        // yet: the rows may still fit, and append_locked reports it if they do not.
+        const uint64_t soon = c->n.load() + c->pending.load(std::memory_order_acquire) + n + 4 * kAppendBlock;
+        if (soon > c->capacity.load() && soon <= c->reserved_rows) { if (grow_mapped(c, soon) != PBX_OK) g_err[0] = 0; }
+    }
     std::lock_guard<std::mutex> alk(c->append_mu);
     if (n < kAppendCoalesceBelow) {
         try {
@@ -696,7 +741,7 @@ extern "C" int pbx_corpus_append_device(pbx_corpus* c, const int64_t* d_image_id
     const uint64_t at = c->n.load();
     if (at + n > c->capacity) {
         if (c->use_vmm) {
-            rc = reserve_rows(c, at + n);
+            rc = grow_mapped(c, at + n);
         } else {
             std::lock_guard<std::mutex> lk(c->mu);
             rc = reserve_rows(c, at + n);
@@ -738,7 +783,7 @@ extern "C" int pbx_corpus_fill_synthetic(pbx_corpus* c, uint64_t n, uint64_t see
     CU_TRY(cudaDeviceSynchronize());
     c->n.store(0);
     c->pend_ids.clear(); c->pend_rows.clear(); c->pending.store(0);
-    int rc = reserve_rows(c, std::max<uint64_t>(n, 1));
+    int rc = c->use_vmm ? grow_mapped(c, std::max<uint64_t>(n, 1)) : reserve_rows(c, std::max<uint64_t>(n, 1));
     if (rc != PBX_OK) return rc;
     if (n == 0) return PBX_OK;
     const uint64_t step = 1ull << 24;               // rows per launch
@@ -904,11 +949,11 @@ struct BatchPlan {
     int grid;
 };
 
-static bool batch_plan(const pbx_corpus* c, uint32_t nq, BatchPlan* out) {
+static bool batch_plan(const pbx_corpus* c, uint32_t nq, uint32_t cg, BatchPlan* out) {
     BatchPlan bp;
     const uint32_t pitch = c->pitch;
     if (pitch % 32 != 0 || pitch > 1024) return false;
-    bp.cg = c->batch_cg;
+    bp.cg = cg;
     bp.tn = bp.cg == 2 ? 256u : 128u;                // pairs: 256-row tiles, 128 rows per CTA; single CTAs: 128-row tiles
     bp.w = pitch % 128 == 0 ? 128u : (pitch % 64 == 0 ? 64u : 32u);
     bp.kc = pitch / bp.w;
@@ -948,15 +993,32 @@ static void batch_seed_geometry(uint32_t n, uint32_t tn, uint32_t* n_tiles, uint
     *step = *n_tiles ? full / *n_tiles : 1u;
 }
 
+// The launch shape of a batch of nq (<= 1024) queries over n rows with `keep` candidates per query, or false if the
+// batched path cannot take it.  CTA pairs on 256-row tiles hold a whole batch of 1024 queries and stream the corpus once;
+// up to 128 queries fit one CTA, and single CTAs on 128-row tiles then keep twice as many independent tiles in flight
+// (measured at 10M x 256: 8 queries 0.57 ms against 0.63, 128 queries 0.61 against 0.70).  The other grouping is the
+// fallback when the preferred one has no shape or too few sample blocks for the seed pass.
+static bool batch_choose(const pbx_corpus* c, uint32_t nq, uint32_t n, uint32_t keep, BatchPlan* out) {
+    const uint32_t first = c->batch_cg ? c->batch_cg : (nq <= 128u ? 1u : 2u);
+    const uint32_t order[2] = {first, 3u - first};
+    for (int i = 0; i < (c->batch_cg ? 1 : 2); ++i) {
+        BatchPlan bp;
+        if (!batch_plan(c, nq, order[i], &bp)) continue;
+        uint32_t seed_tiles, seed_step;
+        batch_seed_geometry(n, bp.tn, &seed_tiles, &seed_step);
+        if (seed_tiles * (bp.tn / 32u) < keep + keep / 2u) continue;
+        *out = bp;
+        return true;
+    }
+    return false;
+}
+
 static bool batch_eligible(const pbx_corpus* c, uint32_t nq, uint32_t n, uint32_t k) {
     // per-query candidate buffers hold kBatchCap keys and are cut back to keep = k + slack at the end: the scheme
     // needs keep well below the capacity, larger k loops over the single-query scan
     const uint32_t keep = batch_keep(k, c->slack);
     BatchPlan bp;
-    if (nq < c->batch_min || keep * 8u > kBatchCapLarge || n > kBatchMaxRows || !batch_plan(c, std::min<uint32_t>(nq, 1024u), &bp)) return false;
-    uint32_t seed_tiles, seed_step;
-    batch_seed_geometry(n, bp.tn, &seed_tiles, &seed_step);
-    return seed_tiles * (bp.tn / 32u) >= keep + keep / 2u;
+    return nq >= c->batch_min && keep * 8u <= kBatchCapLarge && n <= kBatchMaxRows && batch_choose(c, std::min<uint32_t>(nq, 1024u), n, keep, &bp);
 }
 
 static int ensure_batch_scratch(pbx_corpus* c, uint32_t nq_pad, uint32_t cap) {
@@ -1054,10 +1116,10 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
                                   uint32_t* d_count, cudaStream_t s, uint32_t n) {
     const uint32_t pitch = c->pitch;
     BatchPlan bp;
-    if (!batch_plan(c, nq, &bp)) return fail(PBX_E_INTERNAL, "batched path: no launch shape for pitch %u", pitch);
+    const uint32_t keep = batch_keep(k, c->slack);
+    if (!batch_choose(c, nq, n, keep, &bp)) return fail(PBX_E_INTERNAL, "batched path: no launch shape for pitch %u", pitch);
     int rc = ensure_query_scratch(c, nq);
     if (rc != PBX_OK) return rc;
-    const uint32_t keep = batch_keep(k, c->slack);
     const uint32_t cap = batch_cap_for(keep);
     rc = ensure_batch_scratch(c, bp.nq_pad, cap);
     if (rc != PBX_OK) return rc;
@@ -1065,7 +1127,7 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
     if (c->map_rows_gen != c->rows_generation || c->map_rows_box != box_rows) {
         // with reserved address ranges the map covers the whole range once: tiles beyond the committed rows are never touched
         // (TMA coordinates are signed 32-bit: a row dimension beyond 2^31 makes the copy an illegal instruction)
-        rc = make_u8_map(&c->map_rows, c->d_rows, std::min<uint64_t>(c->use_vmm ? c->reserved_rows : c->capacity, kBatchMaxRows), pitch, bp.w, box_rows);
+        rc = make_u8_map(&c->map_rows, c->d_rows, std::min<uint64_t>(c->use_vmm ? c->reserved_rows : c->capacity.load(), kBatchMaxRows), pitch, bp.w, box_rows);
         if (rc != PBX_OK) return rc;
         c->map_rows_gen = c->rows_generation; c->map_rows_box = box_rows;
     }
@@ -1093,6 +1155,11 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
     mp.bhist = c->d_bhist; mp.inv_q = c->d_binvq; mp.thr_live = c->d_thr; mp.keep = keep; mp.cap = cap;
     mp.n = n; mp.dim = c->dim; mp.w = bp.w; mp.kc = bp.kc; mp.qg = bp.qg; mp.groups = bp.groups; mp.stages = bp.stages; mp.tn = bp.tn;
     mp.seed_lb = c->d_seedlb; mp.nq_pad = bp.nq_pad;
+    // L2 prefetch ahead of the shared-memory ring: measured counter-productive (10M x 256, 8 queries: 0.55 ms without, 0.56 /
+    // 0.73 / 0.78 ms at 6 / 12 / 24 tiles ahead) -- the small-batch pass is bound by the MMA thread's serial
+    // wait -> issue -> commit loop per 128-row tile, not by the stream.  Kept as an experiment knob, off.
+    mp.prefetch_tiles = getenv("PBX_BATCH_PREFETCH") ? (uint32_t)atoi(getenv("PBX_BATCH_PREFETCH")) : 0u;
+    mp.exp_flags = getenv("PBX_BATCH_EXPFLAGS") ? (uint32_t)atoi(getenv("PBX_BATCH_EXPFLAGS")) : 0u;
     BatchTightenParams tp;
     tp.cand = c->d_bcand; tp.cand_cnt = c->d_bcnt; tp.thr = c->d_thr; tp.keep = keep; tp.nq = nq; tp.cap = cap;
 
@@ -1820,7 +1887,7 @@ extern "C" int pbx_get_stats(const pbx_corpus* cc, pbx_stats* out) {
     std::lock_guard<std::mutex> lk(c->mu);
     memset(out, 0, sizeof(*out));
     out->rows = c->n.load() + c->pending.load();
-    out->capacity_rows = c->capacity;
+    out->capacity_rows = c->capacity.load();
     out->reserved = c->use_vmm ? 1 : 0;             // 1: the arrays grow by mapping memory into reserved address ranges
     out->dim = c->dim;
     out->row_pitch = c->pitch;

@@ -100,6 +100,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
         asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                      ::"r"(smem_u32(dst)), "l"(map), "r"(bar_addr), "r"(x), "r"(y) : "memory");
 }
+// L2 prefetch of one box of a tensor map: no shared memory, no barrier.  The ring in shared memory holds 4-5 tiles per SM
+// (128-160 KB); a stream at HBM speed needs ~200 KB in flight per SM, the rest waits in L2.
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int x, int y) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
+}
 // plain (non-tensor) bulk copy global -> this CTA's shared memory, completing on one of its own barriers
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -311,6 +316,8 @@ struct BatchMmaParams {
     uint32_t tn;                // corpus rows per tile = UMMA N (128 or 256)
     uint32_t n_tiles;           // tiles of this launch: tile index = tile_step * i, i < n_tiles
     uint32_t tile_step;         // 1: every tile (MAIN); > 1: a strided sample (SEED)
+    uint32_t prefetch_tiles;    // tiles the producer prefetches into L2 ahead of the shared-memory ring (0: none)
+    uint32_t exp_flags;         // experiment builds (PBX_BATCH_PROF) only
 };
 
 #ifdef PBX_BATCH_PROF
@@ -427,8 +434,17 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                 for (uint32_t h = 0; h < QG; h += qbox)
                     if (lane == 0) tma_load_2d<CG>(sQ + ((size_t)kc * QG + h) * W, &p.map_q, qfull_l, (int)(kc * W), (int)(qbase + h));
             uint32_t st = 0, ph = 0, ti = 0;
+            const uint32_t pf = p.prefetch_tiles;
+            if (lane == 0)
+                for (uint32_t d = 0; d < pf; ++d)
+                    if (ci + d * cstride < p.n_tiles)
+                        for (uint32_t kc = 0; kc < KC; ++kc)
+                            tma_prefetch_2d(&p.map_rows, (int)(kc * W), (int)((ci + d * cstride) * p.tile_step * TN + rank * NB));
             for (uint32_t i = ci; i < p.n_tiles; i += cstride, ++ti) {
                 const uint32_t t = i * p.tile_step;
+                if (pf && lane == 0 && i + pf * cstride < p.n_tiles)
+                    for (uint32_t kc = 0; kc < KC; ++kc)
+                        tma_prefetch_2d(&p.map_rows, (int)(kc * W), (int)((i + pf * cstride) * p.tile_step * TN + rank * NB));
                 {
                     // inv_norm / row_sum / block metadata of the tile's TN rows (every CTA of a pair sees all of them):
                     // plain bulk copies into a small ring the epilogue reads in place
@@ -449,8 +465,15 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                     PBX_BP_ADD(0, tp1);
                     const uint32_t full_l = CG == 1 ? smem_u32(&a_full[st]) : mapa_u32(smem_u32(&a_full[st]), 0);
                     if (lane == 0) {
-                        mbar_expect_tx_at(full_l, stage_bytes);
-                        tma_load_2d<CG>(sA + (size_t)st * stage_bytes, &p.map_rows, full_l, (int)(kc * W), (int)(t * TN + rank * NB));
+#ifdef PBX_BATCH_PROF
+                        if ((p.exp_flags & 1u) && ti >= 8u) {        // experiment: the MMAs run on stale tiles, nothing is streamed
+                            mbar_arrive_at(full_l);
+                        } else
+#endif
+                        {
+                            mbar_expect_tx_at(full_l, stage_bytes);
+                            tma_load_2d<CG>(sA + (size_t)st * stage_bytes, &p.map_rows, full_l, (int)(kc * W), (int)(t * TN + rank * NB));
+                        }
                     }
                     if (++st == STAGES) { st = 0; ph ^= 1u; }
                 }
@@ -491,9 +514,13 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                         }
                         const uint64_t da = da0 + (uint64_t)(kc * a_kc + mb * a_mb), db = db0 + (uint64_t)(st * b_st);
                         if (lane == 0) {
+                            const long long tm9 = PBX_BP_T();
                             for (uint32_t ks = 0; ks < ksteps; ++ks)
                                 umma_i8<CG>(d_tmem, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, (kc | ks) ? 1u : 0u);
+                            PBX_BP_ADD(0, tm9);
+                            const long long tm10 = PBX_BP_T();
                             if (mb == MB - 1) umma_commit<CG>(&a_empty[st]);       // the stage is free once these MMAs retire
+                            PBX_BP_ADD(1, tm10);
                         }
                         __syncwarp();
                         if (++st == STAGES) { st = 0; ph ^= 1u; }
@@ -505,7 +532,8 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
             }
             PBX_BP_ADD(4, tm_all);
 #ifdef PBX_BATCH_PROF
-            if (lane == 0) { g_batch_prof[blockIdx.x][2] += bp_acc[2]; g_batch_prof[blockIdx.x][3] += bp_acc[3]; g_batch_prof[blockIdx.x][4] += bp_acc[4]; }
+            if (lane == 0) { g_batch_prof[blockIdx.x][2] += bp_acc[2]; g_batch_prof[blockIdx.x][3] += bp_acc[3]; g_batch_prof[blockIdx.x][4] += bp_acc[4];
+                             g_batch_prof[blockIdx.x][11] += bp_acc[0]; g_batch_prof[blockIdx.x][10] += bp_acc[1] << 32; }
 #endif
         }
     } else {
@@ -728,6 +756,15 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                 if (threadIdx.x == 0) { PBX_BP_ADD(5, te5); g_prof_stage(); }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t taddr = tmem + ((quarter * 32u) << 16) + ab * TN + col_base;
+                // A lane quarter that holds only padding queries (small batches: 8 queries occupy one quarter of one block)
+                // has nothing to look at: it hands the accumulator straight back.  With one to four live warps per tile
+                // instead of sixteen the pass is bound by the corpus stream, not by the epilogue's issue rate.
+                if (!__any_sync(0xFFFFFFFFu, s_invq[j] > 0.0f)) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_at(acc_empty0 + ab * 8u);
+                    continue;
+                }
                 int deferred = 0;                                      // dumped survivors of an earlier step, not tested yet
 #pragma unroll 1
                 for (uint32_t hf = 0; hf < STEPS; ++hf) {              // WIDTH columns = one or two 32-row blocks at a time

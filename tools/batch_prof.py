@@ -34,11 +34,14 @@ L.pbx_debug_batch_profile(None, 1)
 c.search_device(dq.data_ptr(), nq, k, 1e3, dh.data_ptr(), dc.data_ptr(), s.cuda_stream)
 torch.cuda.synchronize()
 L.pbx_debug_batch_profile(ctypes.c_void_p(buf.ctypes.data), 0)
+commit = (buf[:148, 10] >> np.uint64(32)).astype(np.float64)      # MMA role: cycles in the per-stage commits (high half of column 10)
+buf[:, 10] &= np.uint64(0xFFFFFFFF)
 b = buf[:148].astype(np.float64)
 names = ["prod wait a_empty", "prod wait m_empty", "mma wait acc_empty", "mma wait a_full", "mma total", "epi wait acc_full", "epi ld+arrive",
-         "epi process", "epi wait m_full", "epi total", "stages"]
+         "epi process", "epi wait m_full", "epi total", "stages", "mma issue (UTCIMMA)"]
 lead = b[0::2]
 print("per CTA means (cycles), seed + main pass of one search; leaders only for the mma rows")
 for i, nme in enumerate(names):
     src = lead if nme.startswith("mma") else b
     print(f"  {nme:22s} {src[:, i].mean():14.0f}   per stage {src[:, i].mean() / max(1.0, b[:, 10].mean()):8.1f}")
+print(f"  {'mma a_empty commits':22s} {commit[commit > 0].mean():14.0f}   per stage {commit[commit > 0].mean() / max(1.0, b[:, 10].mean()):8.1f}")
