@@ -954,7 +954,7 @@ static bool batch_plan(const pbx_corpus* c, uint32_t nq, uint32_t cg, BatchPlan*
     const uint32_t pitch = c->pitch;
     if (pitch % 32 != 0 || pitch > 1024) return false;
     bp.cg = cg;
-    bp.tn = bp.cg == 2 ? 256u : 128u;                // pairs: 256-row tiles, 128 rows per CTA; single CTAs: 128-row tiles
+    bp.tn = 256u;                                    // 256-row tiles: 128 rows per CTA of a pair, all 256 in a single CTA
     bp.w = pitch % 128 == 0 ? 128u : (pitch % 64 == 0 ? 64u : 32u);
     bp.kc = pitch / bp.w;
     const uint32_t stage_bytes = (bp.tn / bp.cg) * bp.w;
@@ -994,16 +994,19 @@ static void batch_seed_geometry(uint32_t n, uint32_t tn, uint32_t* n_tiles, uint
 }
 
 // The launch shape of a batch of nq (<= 1024) queries over n rows with `keep` candidates per query, or false if the
-// batched path cannot take it.  CTA pairs on 256-row tiles hold a whole batch of 1024 queries and stream the corpus once;
-// up to 128 queries fit one CTA, and single CTAs on 128-row tiles then keep twice as many independent tiles in flight
-// (measured at 10M x 256: 8 queries 0.57 ms against 0.63, 128 queries 0.61 against 0.70).  The other grouping is the
-// fallback when the preferred one has no shape or too few sample blocks for the seed pass.
+// batched path cannot take it.  CTA pairs hold a whole batch of 1024 queries and stream the corpus once; up to 128
+// queries fit one CTA, and single CTAs then run twice as many independent tile pipelines (a small batch is bound by the
+// per-tile hand-offs between the TMA, MMA and epilogue roles, not by the tensor pipe).  The other grouping is the fallback
+// when the preferred one has no shape or too few sample blocks for the seed pass.
 static bool batch_choose(const pbx_corpus* c, uint32_t nq, uint32_t n, uint32_t keep, BatchPlan* out) {
     const uint32_t first = c->batch_cg ? c->batch_cg : (nq <= 128u ? 1u : 2u);
     const uint32_t order[2] = {first, 3u - first};
     for (int i = 0; i < (c->batch_cg ? 1 : 2); ++i) {
         BatchPlan bp;
         if (!batch_plan(c, nq, order[i], &bp)) continue;
+        // single CTAs hold whole 256-row K-chunks (32 KB at 128-byte chunks): with fewer than four of them in the ring the
+        // stream stalls on every tile -- long rows stay on pairs
+        if (!c->batch_cg && i == 0 && order[i] == 1u && bp.stages < 4u) continue;
         uint32_t seed_tiles, seed_step;
         batch_seed_geometry(n, bp.tn, &seed_tiles, &seed_step);
         if (seed_tiles * (bp.tn / 32u) < keep + keep / 2u) continue;

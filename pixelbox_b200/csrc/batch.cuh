@@ -356,8 +356,8 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
     // the swizzle of TMA and UMMA is a function of the shared-memory address: tiles must sit on 1024-byte boundaries,
     // and dynamic shared memory only starts after the static variables (the host adds 1 KB of slack)
     uint8_t* bsm = bsm_raw + ((1024u - (smem_u32(bsm_raw) & 1023u)) & 1023u);
-    constexpr uint32_t TN = CG == 2 ? 256u : 128u;      // corpus rows per tile = UMMA N: pairs take 256-row tiles (p.tn agrees)
-    constexpr uint32_t NB = TN / CG;                    // corpus rows of a tile in THIS CTA's shared memory (128)
+    constexpr uint32_t TN = 256u;                       // corpus rows per tile = UMMA N (p.tn agrees): at N = 128 the MMA runs at 77 % of the N = 256 rate
+    constexpr uint32_t NB = TN / CG;                    // corpus rows of a tile in THIS CTA's shared memory: 128 per CTA of a pair, 256 for a single CTA
     constexpr uint32_t AS = 512u / TN;                  // TMEM accumulator ring: 2 x 256 or 4 x 128 columns
     constexpr uint32_t AS_LOG = AS == 2 ? 1u : 2u;
     constexpr uint32_t CPS = TN / 128u;                 // 32-column blocks per epilogue warp and accumulator
