@@ -224,10 +224,15 @@ finalize_exact_kernel(const FinalizeExactParams p) {
         }
         p.hits[c] = h;
     }
+    __syncthreads();
     if (threadIdx.x == 0) {
         *p.count = nc;
         *p.tile_counter = 0;
         atomicAdd(p.exact_passes, 1ull);
+        if (p.done_flag) {
+            __threadfence_system();
+            *reinterpret_cast<volatile uint32_t*>(p.done_flag) = p.done_seq;
+        }
     }
 }
 

@@ -31,6 +31,8 @@ struct FinalizeExactParams {
     const SearchStatus* status;
     uint32_t* tile_counter;
     unsigned long long* exact_passes;
+    uint32_t* done_flag;        // host-mapped word (or NULL): receives done_seq after the hits, with a system-scope fence between
+    uint32_t done_seq;
 };
 __global__ void finalize_exact_kernel(const FinalizeExactParams p);     // finalize.cuh
 
@@ -81,6 +83,11 @@ struct FinalizeParams {
     uint32_t* count;            // this query
     SearchStatus* status;       // this query
     uint32_t* tile_counter;     // reset for the next scan
+    // Zero-copy completion (pbx_search_hits, one query): hits / count point into host-mapped memory and the host polls this
+    // word instead of waiting for a copy and a stream synchronisation.  Written by whichever kernel produces the final
+    // answer: this one, or finalize_exact_kernel when the exact pass runs.  NULL: not used.
+    uint32_t* done_flag;
+    uint32_t done_seq;
     // batched path (finalize_kernel<true>, one CTA per query; the per-query pointers above are those of query 0)
     const u64* bcand;           // [nq][kBatchCapacity] candidate keys (kappa' = dot_i * inv_norm_r, row)
     const uint32_t* bcnt;       // [nq]
@@ -804,9 +811,14 @@ finalize_kernel(const FinalizeParams p) {
         if constexpr (!BATCH) {
             p.tile_counter[0] = 0;                        // chunk scheduler
             p.tile_counter[32] = 0;                       // global bin threshold of the scan
+            bool exact_follows = st.need_exact != 0;          // (without device-side launches the host has enqueued it already)
 #ifdef PBX_USE_CDP
-            if (st.need_exact) { __threadfence(); if (!launch_exact_tail(p.x)) *count_g = PBX_COUNT_EXACT_LAUNCH_FAILED; }
+            if (st.need_exact) { __threadfence(); if (!launch_exact_tail(p.x)) { *count_g = PBX_COUNT_EXACT_LAUNCH_FAILED; exact_follows = false; } }
 #endif
+            if (p.done_flag && !exact_follows) {              // every hit was written before the barrier above
+                __threadfence_system();
+                *reinterpret_cast<volatile uint32_t*>(p.done_flag) = p.done_seq;
+            }
         } else {
             // the last CTA to finish tail-launches the exact pass of every query that needs one, one after the
             // other (they share the scan scratch), from a single thread so that their order is well defined
