@@ -1642,6 +1642,12 @@ struct pbx_exchange {
     pbx_hit* d_out = nullptr;                      // merged result of pbx_exchange_search_hits: [max_records] records, then [max_queries] counts
     pbx_hit* h_out = nullptr;                      // pinned
     size_t out_records = 0;
+    uint32_t* h_flag = nullptr;                    // pinned: [0] completion sequence number, [1] the shard's own count (zero-copy completion)
+    uint32_t flag_seq = 0;
+    // set around the launch by pbx_exchange_search_hits for a one-query call (see ExchangeParams)
+    const uint32_t* zc_local_count = nullptr;
+    uint32_t* zc_local_count_out = nullptr;
+    uint32_t* zc_flag = nullptr;
 };
 
 extern "C" int pbx_exchange_create(int device, uint32_t rank, uint32_t world, uint32_t max_records, uint32_t max_queries, pbx_exchange** out) {
@@ -1718,6 +1724,7 @@ extern "C" int pbx_exchange_allgather_merge(pbx_exchange* x, const pbx_hit* d_lo
     p.seq = x->seq + 1; p.slot = p.seq & 1u;
     p.slot_records = x->slot_records; p.slot_flags = x->slot_flags;
     p.stage_bytes = merge_smem_bytes(x->world, k);
+    if (x->zc_flag && nq == 1) { p.local_count = x->zc_local_count; p.local_count_out = x->zc_local_count_out; p.done_flag = x->zc_flag; p.done_seq = x->flag_seq; }
     exchange_merge_kernel<<<nq, kMergeThreads, p.stage_bytes, static_cast<cudaStream_t>(cuda_stream)>>>(p);
     CU_TRY(cudaGetLastError());
     x->seq = p.seq;                                 // only a launched call consumes a sequence number (the ranks stay in step)
@@ -1763,14 +1770,46 @@ extern "C" int pbx_exchange_search_hits(pbx_exchange* x, pbx_corpus* c, const ui
     uint32_t* d_cnt_local = reinterpret_cast<uint32_t*>(c->d_hits + (size_t)nq * k);
     rc = enqueue_search(c, c->d_queries, nq, k, max_dist, c->d_hits, d_cnt_local, c->stream, false);
     if (rc != PBX_OK) return rc;
-    uint32_t* d_cnt_out = reinterpret_cast<uint32_t*>(x->d_out + (size_t)nq * k);
-    rc = pbx_exchange_allgather_merge(x, c->d_hits, nq, k, x->d_out, d_cnt_out, c->stream);
+    // one query: the merge kernel writes the merged records, both counts and a sequence number into pinned memory and this
+    // thread polls it (as pbx_search_hits does on one device); otherwise two copies back and a synchronisation
+    pbx_hit* out_dev = x->d_out;
+    uint32_t* flag_dev = nullptr;
+    uint32_t* local_out_dev = nullptr;
+    if (c->zero_copy && nq == 1) {
+        if (!x->h_flag) { CU_TRY(cudaMallocHost(&x->h_flag, 64)); x->h_flag[0] = 0; }
+        void *dh = nullptr, *df = nullptr;
+        if (cudaHostGetDevicePointer(&dh, x->h_out, 0) == cudaSuccess && cudaHostGetDevicePointer(&df, x->h_flag, 0) == cudaSuccess) {
+            out_dev = static_cast<pbx_hit*>(dh);
+            flag_dev = static_cast<uint32_t*>(df);
+            local_out_dev = flag_dev + 1;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    uint32_t* d_cnt_out = reinterpret_cast<uint32_t*>(out_dev + (size_t)nq * k);
+    if (flag_dev) { ++x->flag_seq; x->zc_flag = flag_dev; x->zc_local_count = d_cnt_local; x->zc_local_count_out = local_out_dev; }
+    rc = pbx_exchange_allgather_merge(x, c->d_hits, nq, k, out_dev, d_cnt_out, c->stream);
+    x->zc_flag = nullptr;
     if (rc != PBX_OK) return rc;
     const size_t out_bytes = (size_t)nq * k * sizeof(pbx_hit) + (size_t)nq * sizeof(uint32_t);
-    CU_TRY(cudaMemcpyAsync(x->h_out, x->d_out, out_bytes, cudaMemcpyDeviceToHost, c->stream));
-    // the local counts too: a refused device-side exact launch shows there (PBX_COUNT_EXACT_LAUNCH_FAILED)
-    CU_TRY(cudaMemcpyAsync(c->h_hits, d_cnt_local, (size_t)nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    CU_TRY(cudaStreamSynchronize(c->stream));
+    if (flag_dev) {
+        volatile uint32_t* flag = x->h_flag;
+        for (uint32_t spins = 1; *flag != x->flag_seq; ++spins) {
+            if ((spins & 0xFFFFu) == 0) {
+                const cudaError_t qe = cudaStreamQuery(c->stream);
+                if (qe == cudaSuccess) break;
+                if (qe != cudaErrorNotReady) return fail(PBX_E_CUDA, "sharded search failed: %s", cudaGetErrorString(qe));
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        if (*flag != x->flag_seq) return fail(PBX_E_INTERNAL, "sharded search finished without publishing its result");
+        reinterpret_cast<uint32_t*>(c->h_hits)[0] = x->h_flag[1];
+    } else {
+        CU_TRY(cudaMemcpyAsync(x->h_out, x->d_out, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+        // the local counts too: a refused device-side exact launch shows there (PBX_COUNT_EXACT_LAUNCH_FAILED)
+        CU_TRY(cudaMemcpyAsync(c->h_hits, d_cnt_local, (size_t)nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+    }
     const uint32_t* h_cnt = reinterpret_cast<const uint32_t*>(x->h_out + (size_t)nq * k);
     const uint32_t* h_local = reinterpret_cast<const uint32_t*>(c->h_hits);
     for (uint32_t q = 0; q < nq; ++q) {
@@ -1786,7 +1825,7 @@ extern "C" void pbx_exchange_destroy(pbx_exchange* x) {
     if (!x) return;
     cudaSetDevice(x->device);
     cudaDeviceSynchronize();
-    cudaFree(x->d_out); cudaFreeHost(x->h_out);
+    cudaFree(x->d_out); cudaFreeHost(x->h_out); cudaFreeHost(x->h_flag);
     for (uint32_t r = 0; r < x->world; ++r)
         if (r != x->rank && x->peer_base[r]) cudaIpcCloseMemHandle(x->peer_base[r]);
     cudaFree(x->base);

@@ -377,6 +377,12 @@ struct ExchangeParams {
     uint32_t slot_records;                // records per mailbox slot
     uint32_t slot_flags;                  // flags per slot (max_queries * world)
     uint32_t stage_bytes;                 // dynamic shared memory for the merge keys (0: probe through L2)
+    // zero-copy completion of a one-query host call (NULL otherwise): out / out_count are host-mapped, the shard's own
+    // count (which may carry an error marker) is copied next to them, and done_seq is published last
+    const uint32_t* local_count;
+    uint32_t* local_count_out;
+    uint32_t* done_flag;
+    uint32_t done_seq;
 };
 
 __global__ void __launch_bounds__(kMergeThreads)
@@ -416,7 +422,14 @@ exchange_merge_kernel(const __grid_constant__ ExchangeParams p) {
     merge_hits_block(p.peer_mail[p.rank] + (size_t)p.slot * p.slot_records, nullptr, p.world, p.nq, p.k, q, p.out, p.out_count,
                      p.stage_bytes ? merge_stage : nullptr);
     __syncthreads();
-    if (threadIdx.x == 0 && s_timeout) p.out_count[q] = 0xFFFFFFFFu;          // "exchange timed out" marker for the host
+    if (threadIdx.x == 0) {
+        if (s_timeout) p.out_count[q] = 0xFFFFFFFFu;                          // "exchange timed out" marker for the host
+        if (p.done_flag) {                                                    // (one query = one CTA: no counting needed)
+            p.local_count_out[q] = p.local_count[q];
+            __threadfence_system();
+            *reinterpret_cast<volatile uint32_t*>(p.done_flag) = p.done_seq;
+        }
+    }
 }
 
 // ---- the ingest quantizer (src/image_hashes/efficientnet.rs:39), SURVEY.md 8f N3 --------------------------
