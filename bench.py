@@ -40,6 +40,7 @@ SEED = 42
 NQ = 64          # distinct queries cycled through
 PLANT_IDS = (3_000_000_003, 3_000_000_005)      # two identical planted rows (one on the first, one on the last shard)
 NORTHSTAR_ROWS = 1_000_000_000
+SWEEP_ROWS = 100_000_000
 
 
 def parse():
@@ -57,6 +58,9 @@ def parse():
     ap.add_argument("--no-northstar", action="store_true", help="skip the 1B-row section of a multi-GPU run")
     ap.add_argument("--northstar-rows", type=int, default=NORTHSTAR_ROWS)
     ap.add_argument("--no-c1", action="store_true", help="skip the configs[0] SQLite comparison of a 1-GPU run")
+    ap.add_argument("--sweep", action="store_true", help="run the configs[4] d x k sweep at N = 1 too (always on for N >= 2)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the configs[4] sweep of a multi-GPU run")
+    ap.add_argument("--sweep-rows", type=int, default=SWEEP_ROWS)
     return ap.parse_args()
 
 
@@ -385,7 +389,7 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return [float(x) for x in t]
 
-    def make_corpus(rows):
+    def make_corpus(rows, dim=args.dim):
         """Row-sharded synthetic corpus of `rows` rows per GPU + the two planted identical rows."""
         if world > 1:
             sc = ShardedCorpus(dim, capacity_hint=rows + 1024, device=local_rank, use_peer_exchange=os.environ.get("PBX_NO_PEER_EXCHANGE") is None)
@@ -599,6 +603,73 @@ def run_ours(args):
                      "parity_check": ns_check, "batched": ns_batched}
         sc.close()
 
+    # =========================================================================================
+    # configs[4]: 100M rows in total x d in {64, 256, 1024} x k in {10, 100, 1000}, row-sharded over the N GPUs
+    # =========================================================================================
+    sweep = None
+    if (world > 1 or args.sweep) and not args.no_sweep:
+        d_bq = d_bh = d_bc = None
+        if world > 1 and northstar is None:
+            sc.close()
+        if world == 1:
+            corpus.close()
+        torch.cuda.empty_cache()
+        barrier()
+        sw_rows = args.sweep_rows // world
+        sw_total = sw_rows * world
+        cells = []
+        for sd in (64, 256, 1024):
+            s_sc, s_corpus = make_corpus(sw_rows, sd)
+            sq = synth.synth_queries(13, 8, sd, sw_total, SEED)
+            sbq = synth.synth_queries(17, nqb, sd, sw_total, SEED)
+            d_sq, d_sbq = torch.from_numpy(sq).cuda(), torch.from_numpy(sbq).cuda()
+            for sk in (10, 100, 1000):
+                d_sh = torch.zeros(nqb * sk * 24, dtype=torch.uint8, device="cuda")
+                d_scn = torch.zeros(nqb, dtype=torch.int32, device="cuda")
+
+                def sw_step(q, nq, src):
+                    if s_sc is None:
+                        s_corpus.search_device(src.data_ptr() + q * sd, nq, sk, 1e3, d_sh.data_ptr(), d_scn.data_ptr(), stream.cuda_stream)
+                        return d_sh, d_scn
+                    return s_sc.search_device(src[q:q + nq].reshape(-1), nq, sk, 1e3)
+
+                it = [0]
+
+                def one():
+                    it[0] += 1
+                    return sw_step(it[0] % 8, 1, d_sq)
+
+                s_ms, _ = time_batch(one, 1, 20)
+                with torch.cuda.stream(stream):
+                    h1, c1 = sw_step(0, 1, d_sq)
+                    torch.cuda.synchronize()
+                r1 = h1.cpu().numpy()[:sk * 24].view(nat.HIT_DTYPE)[:int(c1.cpu()[0])]
+                b_ms, (hb, cb) = time_batch(lambda: sw_step(0, nqb, d_sbq), nqb, 2)
+                rb = hb.cpu().numpy()[:nqb * sk * 24].view(nat.HIT_DTYPE).reshape(nqb, sk)[3][:int(cb.cpu()[3])]
+                cell_check = "skipped"
+                if rank == 0:
+                    ok1, det1 = completeness_check(r1["image_id"], r1["dist"], sq[0], sk, sd, world, sw_rows, stripe_rows=50_000, seed=sk)
+                    ok2, det2 = completeness_check(rb["image_id"], rb["dist"], sbq[3], sk, sd, world, sw_rows, stripe_rows=50_000, seed=sk + 1)
+                    cell_check = "ok" if ok1 and ok2 else f"MISMATCH (single: {det1}; batched: {det2})"
+                gbs = sw_total * sd / (s_ms * 1e-3) / 1e9
+                cells.append({"dim": sd, "k": sk, "ms_per_query": s_ms, "queries_per_sec": 1e3 / s_ms, "aggregate_GB_per_s": gbs,
+                              "frac_of_measured_hbm_peak": gbs / (peak * world), "batch1024_ms": b_ms,
+                              "batch1024_queries_per_sec": nqb / (b_ms * 1e-3),
+                              "batch1024_int8_tops": 2.0 * sw_total * nqb * sd / (b_ms * 1e-3) / 1e12, "parity_check": cell_check})
+                d_sh = d_scn = None
+            if s_sc is not None:
+                s_sc.close()
+            else:
+                s_corpus.close()
+            d_sq = d_sbq = None
+            torch.cuda.empty_cache()
+            barrier()
+        sweep = {"workload": f"{sw_total} rows row-sharded over {world} B200 ({sw_rows} per GPU), d x k grid, single query (20 steps, 8 distinct "
+                             f"queries) and a batch of {nqb} (BASELINE configs[4])",
+                 "parity_check": "per cell: one single query and one query of the batch: returned rows re-ranked by the oracle + a 50k-row "
+                                 "stripe of every shard",
+                 "cells": cells}
+
     if rank == 0:
         ms_step = ms / args.steps
         bytes_step = total_rows * dim
@@ -631,6 +702,8 @@ def run_ours(args):
             line["batched"] = batched
         if northstar is not None:
             line["northstar"] = northstar
+        if sweep is not None:
+            line["sweep"] = sweep
         if world == 1:
             # free the 10M-row corpus before the small-table comparison and the CPU baseline
             corpus.close()

@@ -42,6 +42,13 @@ namespace pbx {
 constexpr int kBatchEpiWarps = PBX_BATCH_EPI_WARPS;   // 16: four per TMEM lane quarter, a quarter of an accumulator's columns each, read 32
                                                       // at a time (<= 96 registers); 8: two per quarter, 64 at a time (up to 168 registers).
                                                       // Measured at 10M x 256 x 1024: 2.44 ms with 16 warps, 2.64 ms with 8.
+#ifndef PBX_BATCH_EPI_GROUPS
+#define PBX_BATCH_EPI_GROUPS 1
+#endif
+// Epilogue warp groups: with G groups, group g drains the accumulator stages s = g (mod G) alone -- its warps read G times as
+// many columns of G times fewer stages, the fixed cost per stage and warp is paid G times less often, and an accumulator
+// goes back to the MMA thread when kBatchEpiWarps / G warps (not all of them) have read it.
+constexpr int kBatchEpiGroups = PBX_BATCH_EPI_GROUPS;
 constexpr int kBatchThreads = 64 + 32 * kBatchEpiWarps;   // warps 0..7 epilogue, warp 8 TMA producer, warp 9 MMA issuer
 // The two single-thread roles sit on the HIGHEST warp ids: the warp scheduler prefers high warp ids among eligible
 // warps, and an MMA issuer that shares its scheduler with four polling epilogue warps of higher priority starves.
@@ -91,6 +98,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "bra PBX_WAIT;\n\t"
         "PBX_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// ... on a barrier given by its shared::cta address (hoisted out of the loops: the address of a __shared__ object is
+// re-derived from the CTA's shared window at every use otherwise)
+__device__ __forceinline__ void mbar_wait_at(uint32_t bar_addr, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "PBX_WAITA:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra PBX_DONEA;\n\t"
+        "bra PBX_WAITA;\n\t"
+        "PBX_DONEA:\n\t}" ::"r"(bar_addr), "r"(parity) : "memory");
+}
+// Pure polling (test_wait never suspends the thread): for the two accumulator hand-off waits when PBX_BATCH_SPIN is set
+// (bit 0: the MMA thread's wait for the epilogue, bit 1: the epilogue's wait for the MMAs)
+__device__ __forceinline__ void mbar_spin_at(uint32_t bar_addr, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "PBX_SPIN:\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra PBX_SPUN;\n\t"
+        "bra PBX_SPIN;\n\t"
+        "PBX_SPUN:\n\t}" ::"r"(bar_addr), "r"(parity) : "memory");
+}
+#ifndef PBX_BATCH_SPIN
+#define PBX_BATCH_SPIN 0
+#endif
 template <int CG>
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint32_t bar_addr, int x, int y) {
     if constexpr (CG == 1)
@@ -224,7 +256,7 @@ __global__ void block_meta_kernel(const float* __restrict__ inv_norm, const int*
         float4 m;
         m.x = inv_hi > 0.0f ? __fdiv_rn(1.0f, inv_hi) : 0.0f;          // smallest norm of the block
         m.y = inv_hi > 0.0f ? __fdiv_rn(1.0f, inv_lo) : 0.0f;          // largest
-        m.z = __int_as_float(rt_max);
+        m.z = 0.25f * (float)rt_max;                                   // exact: |rowterm| < 2^24 (the epilogue's bound subtracts it as is)
         m.w = __int_as_float(rt_min);
         blk[b] = m;
     }
@@ -287,6 +319,24 @@ batch_prep_kernel(const BatchPrepParams p) {
     for (uint32_t i = threadIdx.x; i < kBatchHistBins; i += blockDim.x) p.bhist[(size_t)q * kBatchHistBins + i] = 0;
 }
 
+// The epilogue's bound, split so that one step costs a select, an FMA, an add and a conversion.  A score passes when
+// fl(fl(dot_i) * inv_r) >= thr with dot_i = 4 S + rowterm + colterm.  With norm = 1 / inv_r inside [norm_lo, norm_hi] and
+// rowterm <= rt_max over the 32 rows of a block, passing implies (in real numbers, up to the roundings of the test itself:
+// relative 3 * 2^-24 of thr * norm)
+//     S >= (thr * (thr >= 0 ? norm_lo : norm_hi) - colterm - rt_max) / 4.
+// Evaluated as  v = floor(fma(t4, norm_sel, cq) - rq)  with
+//     t4 = thr / 4, pushed 5e-6 (relative) towards -inf: covers the roundings of the exact test, of norm_lo / norm_hi (one
+//          rounded division each) and of the product;
+//     cq = -colterm / 4 - (1e-6 |colterm| + 8): colterm can exceed 2^24 (conversion error < 2^-24 |colterm|), the FMA and
+//          the subtraction round once each at magnitudes below 2^26 (errors <= 4 each, in units of S / 4 ... <= 2 in v);
+//     rq = rt_max / 4, exact in float (block metadata z).
+// The float -> int conversion saturates, so the clamped +-1e30 thresholds become INT_MIN / INT_MAX.
+__host__ __device__ inline float batch_bound_t4(const float thr) { return 0.25f * thr * (thr >= 0.0f ? 1.0f - 5.0e-6f : 1.0f + 5.0e-6f); }
+__host__ __device__ inline float batch_bound_cq(const int ct) {
+    const float c = (float)ct;
+    return -0.25f * c - (1.0e-6f * fabsf(c) + 8.0f);
+}
+
 // ---- the contraction + selection kernel ---------------------------------------------------------------------
 struct BatchMmaParams {
     CUtensorMap map_rows;       // corpus [capacity][pitch] u8, box {w bytes, tn / CG rows}, w-byte swizzle
@@ -338,7 +388,7 @@ constexpr uint32_t kBatchScrSlots = 4;       // per epilogue warp: two for a def
 
 // Dynamic shared memory of batch_mma_kernel after the 1024-byte alignment fix-up; the host sizes the ring with it.
 __host__ __device__ inline size_t batch_smem_fixed(uint32_t qg, uint32_t tn) {
-    return (size_t)qg * 12                                            // s_colterm, s_thr, s_invq
+    return (size_t)qg * 20                                            // s_colterm, s_thr, s_invq, s_t4, s_cq
            + (size_t)kBatchMetaSlots * (tn * 8 + tn / 2)              // metadata ring: inv_norm, row_sum, 16 B per 32 rows
            + (size_t)kBatchEpiWarps * kBatchScrSlots * kBatchScrWords * 4   // survivor scratch
            + (size_t)kBatchEpiWarps * kBatchStage * 12;               // staged candidates (key + query)
@@ -376,6 +426,8 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
     int* s_colterm = reinterpret_cast<int*>(st_q + kBatchEpiWarps * kBatchStage);
     float* s_thr = reinterpret_cast<float*>(s_colterm + QG);
     float* s_invq = s_thr + QG;
+    float* s_t4 = s_invq + QG;          // threshold term of the epilogue's bound (batch_bound_t4)
+    float* s_cq = s_t4 + QG;            // per-query constant of the bound (batch_bound_cq)
     __shared__ uint32_t st_cnt[kBatchEpiWarps];
     __shared__ __align__(8) uint64_t q_full, a_full[kBatchMaxStages], a_empty[kBatchMaxStages], acc_full[4], acc_empty[4];
     __shared__ __align__(8) uint64_t m_full[kBatchMetaSlots], m_empty[kBatchMetaSlots];
@@ -407,14 +459,18 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
         // barriers that collect from both CTAs of a pair live in the leader and count CG arrivals
         mbar_init(&q_full, CG);
         for (int i = 0; i < kBatchMaxStages; ++i) { mbar_init(&a_full[i], CG); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < 4; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], CG * kBatchEpiWarps); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], CG * kBatchEpiWarps / kBatchEpiGroups); }
         for (uint32_t i = 0; i < kBatchMetaSlots; ++i) { mbar_init(&m_full[i], 1); mbar_init(&m_empty[i], kBatchEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (uint32_t i = threadIdx.x; i < QG; i += blockDim.x) {
-        s_colterm[i] = p.colterm[qbase + i];
-        s_thr[i] = p.thr[qbase + i];
+        const int ct = p.colterm[qbase + i];
+        const float th = fminf(fmaxf(p.thr[qbase + i], -1.0e30f), 1.0e30f);    // -inf: no bound known, +inf: padding query
+        s_colterm[i] = ct;
+        s_thr[i] = th;
         s_invq[i] = p.inv_q[qbase + i];
+        s_t4[i] = batch_bound_t4(th);
+        s_cq[i] = batch_bound_cq(ct);
     }
     if (threadIdx.x < kBatchEpiWarps) st_cnt[threadIdx.x] = 0;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -493,30 +549,39 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t st0 = 0, ph0 = 0, acc_it = 0;
             const uint64_t da0 = umma_desc_k(sQ, W), db0 = umma_desc_k(sA, W);
+            // Only the start-address field (the low word) of a descriptor changes from MMA to MMA, and everything the first
+            // MMAs of a stage need is computed BEFORE the wait for the accumulator: between the epilogue's last arrival and
+            // the first MMA lies nothing but the fence and the issue itself (the accumulator hand-off is a latency chain:
+            // arrive -> wait -> issue -> MMA -> commit -> wait -> tcgen05.ld -> arrive, two of them in flight).
+            const uint32_t da_lo = (uint32_t)da0, da_hi = (uint32_t)(da0 >> 32), db_lo = (uint32_t)db0, db_hi = (uint32_t)(db0 >> 32);
             const uint32_t a_kc = (QG * W) >> 4, a_mb = (128u * W) >> 4, b_st = stage_bytes >> 4;    // descriptor steps (16-byte units)
+            const uint32_t acc_empty_l = smem_u32(&acc_empty[0]), a_full_l = smem_u32(&a_full[0]);
             const long long tm_all = PBX_BP_T();
             for (uint32_t i = ci; i < p.n_tiles; i += cstride) {
                 uint32_t st = st0, ph = ph0;
                 for (uint32_t mb = 0; mb < MB; ++mb, ++acc_it) {
                     const uint32_t ab = acc_it & (AS - 1u), par = (acc_it >> AS_LOG) & 1u;
-                    const long long tm0 = PBX_BP_T();
-                    mbar_wait(&acc_empty[ab], par ^ 1u);                          // the epilogues have drained its previous use
-                    PBX_BP_ADD(2, tm0);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t d_tmem = tmem + ab * TN;
                     st = st0; ph = ph0;
+                    uint32_t a_lo = da_lo + mb * a_mb, b_lo = db_lo + st * b_st;
+                    asm volatile("" ::"r"(a_lo), "r"(b_lo), "r"(d_tmem), "r"(acc_empty_l + ab * 8u));
+                    const long long tm0 = PBX_BP_T();
+                    if (PBX_BATCH_SPIN & 1) mbar_spin_at(acc_empty_l + ab * 8u, par ^ 1u);
+                    else mbar_wait_at(acc_empty_l + ab * 8u, par ^ 1u);           // the epilogues have drained its previous use
+                    PBX_BP_ADD(2, tm0);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     for (uint32_t kc = 0; kc < KC; ++kc) {
                         if (mb == 0) {
                             const long long tm1 = PBX_BP_T();
-                            mbar_wait(&a_full[st], ph);
+                            mbar_wait_at(a_full_l + st * 8u, ph);
                             PBX_BP_ADD(3, tm1);
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         }
-                        const uint64_t da = da0 + (uint64_t)(kc * a_kc + mb * a_mb), db = db0 + (uint64_t)(st * b_st);
                         if (lane == 0) {
                             const long long tm9 = PBX_BP_T();
                             for (uint32_t ks = 0; ks < ksteps; ++ks)
-                                umma_i8<CG>(d_tmem, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, (kc | ks) ? 1u : 0u);
+                                umma_i8<CG>(d_tmem, ((uint64_t)da_hi << 32) | (uint64_t)(a_lo + ks * 2u), ((uint64_t)db_hi << 32) | (uint64_t)(b_lo + ks * 2u),
+                                            idesc, (kc | ks) ? 1u : 0u);
                             PBX_BP_ADD(0, tm9);
                             const long long tm10 = PBX_BP_T();
                             if (mb == MB - 1) umma_commit<CG>(&a_empty[st]);       // the stage is free once these MMAs retire
@@ -524,6 +589,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                         }
                         __syncwarp();
                         if (++st == STAGES) { st = 0; ph ^= 1u; }
+                        a_lo += a_kc; b_lo = db_lo + st * b_st;
                     }
                     if (lane == 0) umma_commit<CG>(&acc_full[ab]);
                     __syncwarp();
@@ -544,9 +610,13 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
         // is the few KB the shared-memory carve-out leaves). =====
         const uint32_t e = (uint32_t)warp;
         const uint32_t quarter = (uint32_t)warp & 3u;
-        const uint32_t slice = e >> 2;
-        constexpr uint32_t cols_per_slice = TN / (kBatchEpiWarps / 4);     // columns of this warp in every accumulator
-        constexpr uint32_t WIDTH = kBatchEpiWarps == 8 ? 64u : 32u;        // columns per tcgen05.ld (the live score registers)
+        constexpr uint32_t SLICES = kBatchEpiWarps / 4 / kBatchEpiGroups;  // warps that share a lane quarter of one accumulator
+        const uint32_t slice = (e >> 2) % SLICES, group = (e >> 2) / SLICES;
+        constexpr uint32_t cols_per_slice = TN / SLICES;                   // columns of this warp in every accumulator of its group
+#ifndef PBX_BATCH_WIDTH
+#define PBX_BATCH_WIDTH (kBatchEpiWarps == 8 ? 64u : 32u)
+#endif
+        constexpr uint32_t WIDTH = PBX_BATCH_WIDTH;                        // columns per tcgen05.ld (the live score registers)
         constexpr uint32_t STEPS = cols_per_slice / WIDTH;
         static_assert(cols_per_slice % WIDTH == 0 && STEPS >= 1, "epilogue column split");
         const uint32_t col_base = slice * cols_per_slice;
@@ -652,7 +722,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
             asm volatile("bar.sync 1, %0;" ::"r"(32 * kBatchEpiWarps) : "memory");       // the epilogue warps only
             for (uint32_t j = (uint32_t)threadIdx.x; j < QG; j += 32u * kBatchEpiWarps) {
                 const float live = *reinterpret_cast<volatile float*>(p.thr_live + qbase + j);
-                if (live > s_thr[j]) s_thr[j] = live;
+                if (live > s_thr[j]) { s_thr[j] = fminf(live, 1.0e30f); s_t4[j] = batch_bound_t4(fminf(live, 1.0e30f)); }
             }
             asm volatile("bar.sync 1, %0;" ::"r"(32 * kBatchEpiWarps) : "memory");
         };
@@ -666,20 +736,9 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
             const int u0 = max3(t[0], t[1], t[2]), u1 = max3(t[3], t[4], t[5]), u2 = max3(t[6], t[7], t[8]), u3 = max(t[9], t[10]);
             return max(max3(u0, u1, u2), u3);
         };
-        // A score passes when fl(fl(dot_i) * inv_r) >= thr with dot_i = 4 S + rowterm + colterm.  With norm = 1 / inv_r inside
-        // [norm_lo, norm_hi] and rowterm <= rt_max over the 32 rows of a block, passing implies
-        //     S >= (thr * (thr >= 0 ? norm_lo : norm_hi) - colterm - rt_max - slack) / 4 =: v
-        // (slack covers every rounding; the float -> int conversion saturates, so the clamped +-1e30 thresholds -- -inf: no
-        // bound known, +inf: padding query -- become INT_MIN / INT_MAX).  rowterm = 2 sum r - 255 d moves little from row to
-        // row, so the bound loses almost nothing to rt_max; what it loses to the norm spread of 32 rows is the price of one
-        // compare per 32 scores.
-        auto bound = [](const float thr, const int ct, const float4 bm) {
-            const float rt_f = (float)__float_as_int(bm.z);             // |rowterm| < 2^24: exact
-            const float ctf = (float)ct;
-            const float tt = thr * (thr >= 0.0f ? bm.x : bm.y);
-            const float y = (tt - ctf) - rt_f;
-            const float m = fabsf(tt) + fabsf(ctf) + fabsf(rt_f);       // every rounding above is relative to one of these
-            return __float2int_rd(0.25f * (fmaf(m, -4.0e-6f, y) - 8.0f));
+        // one bound per query and 32-row block: see batch_bound_t4 / batch_bound_cq
+        auto bound = [](const float t4, const float cq, const float4 bm) {
+            return __float2int_rd(fmaf(t4, t4 >= 0.0f ? bm.x : bm.y, cq) - bm.z);
         };
         // Rare: some lanes (queries) may have a hit among the 32 rows [row0, row0 + 32) whose scores they hold in r.  Such a
         // lane dumps its scores and {bound, threshold, colterm, query, first row, first column} into one of the warp's
@@ -737,38 +796,40 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
 #else
         auto g_prof_stage = []() {};
 #endif
+        // 128-query blocks of this CTA in which this warp's lane quarter holds real queries (small batches: 8 queries occupy one
+        // quarter of one block).  A quarter of padding queries has nothing to look at: it hands the accumulator straight back.
+        uint32_t live_mb = 0;
+        for (uint32_t mb = 0; mb < MB; ++mb)
+            if (__any_sync(0xFFFFFFFFu, s_invq[mb * 128u + quarter * 32u + (uint32_t)lane] > 0.0f)) live_mb |= 1u << mb;
+        const uint32_t acc_full0 = smem_u32(&acc_full[0]), m_full0 = smem_u32(&m_full[0]), m_empty0 = smem_u32(&m_empty[0]);
         for (uint32_t i = ci; i < p.n_tiles; i += cstride, ++tile_iter) {
             const uint32_t t = i * p.tile_step;
             // refresh points: every tile at first (the starting thresholds are loose), then ever more rarely
             if (!SEED && tile_iter >= 1 && (tile_iter <= 8 || (tile_iter & (tile_iter - 1)) == 0 || (tile_iter & 31u) == 0)) refresh();
             const uint32_t ms = tile_iter & (kBatchMetaSlots - 1u);
             const long long te8 = PBX_BP_T();
-            mbar_wait(&m_full[ms], (tile_iter >> 2) & 1u);             // this tile's row / block metadata has landed
+            mbar_wait_at(m_full0 + ms * 8u, (tile_iter >> 2) & 1u);    // this tile's row / block metadata has landed
             if (threadIdx.x == 0) PBX_BP_ADD(8, te8);
+            const float4* bmp = s_mblk + ms * (TN / 32u) + (col_base >> 5);
             for (uint32_t mb = 0; mb < MB; ++mb, ++acc_it) {
+                if (kBatchEpiGroups > 1 && (acc_it % (uint32_t)kBatchEpiGroups) != group) continue;    // another group's stage
                 const uint32_t ab = acc_it & (AS - 1u);
                 const uint32_t j = mb * 128u + quarter * 32u + (uint32_t)lane;      // this lane's query in the block
-                const uint32_t qi = qbase + j;
-                const float thr = fminf(fmaxf(s_thr[j], -1.0e30f), 1.0e30f);
-                const int ct = s_colterm[j];
+                const float t4 = s_t4[j], cq = s_cq[j];
                 const long long te5 = PBX_BP_T();
-                mbar_wait(&acc_full[ab], (acc_it >> AS_LOG) & 1u);
+                if (PBX_BATCH_SPIN & 2) mbar_spin_at(acc_full0 + ab * 8u, (acc_it >> AS_LOG) & 1u);
+                else mbar_wait_at(acc_full0 + ab * 8u, (acc_it >> AS_LOG) & 1u);
                 if (threadIdx.x == 0) { PBX_BP_ADD(5, te5); g_prof_stage(); }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t taddr = tmem + ((quarter * 32u) << 16) + ab * TN + col_base;
-                // A lane quarter that holds only padding queries (small batches: 8 queries occupy one quarter of one block)
-                // has nothing to look at: it hands the accumulator straight back.  With one to four live warps per tile
-                // instead of sixteen the pass is bound by the corpus stream, not by the epilogue's issue rate.
-                if (!__any_sync(0xFFFFFFFFu, s_invq[j] > 0.0f)) {
+                if (!((live_mb >> mb) & 1u)) {
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive_at(acc_empty0 + ab * 8u);
                     continue;
                 }
-                int deferred = 0;                                      // dumped survivors of an earlier step, not tested yet
-#pragma unroll 1
+#pragma unroll
                 for (uint32_t hf = 0; hf < STEPS; ++hf) {              // WIDTH columns = one or two 32-row blocks at a time
-                    const uint32_t col0 = col_base + WIDTH * hf, row0 = t * TN + col0;
                     uint32_t r[WIDTH];
                     const long long te6b = PBX_BP_T();
                     tmem_ld_issue(taddr + WIDTH * hf, r);
@@ -781,13 +842,23 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                     }
                     if (threadIdx.x == 0) PBX_BP_ADD(6, te6b);
                     const long long te7 = PBX_BP_T();
-                    const float4 bm0 = s_mblk[ms * (TN / 32u) + (col0 >> 5)];
-                    const float4 bm1 = WIDTH == 64 ? s_mblk[ms * (TN / 32u) + (col0 >> 5) + 1u] : bm0;
+                    const float4 bm0 = bmp[hf * (WIDTH / 32u)];
+                    const float4 bm1 = WIDTH == 64 ? bmp[hf * (WIDTH / 32u) + 1u] : bm0;
                     const int mx0 = max32(r), mx1 = WIDTH == 64 ? max32(r + WIDTH - 32) : mx0;
                     if constexpr (SEED) {
+#ifdef PBX_BATCH_EXPSKIP      // timing experiments on the bare pass (PBX_BATCH_EXP=1: seed_lb == nullptr): 2 = max trees only, 3 = loads only
+                        if (p.seed_lb == nullptr) {
+                            if (PBX_BATCH_EXPSKIP == 2) { if (mx0 == 0x7FFFFFF1 || mx1 == 0x7FFFFFF1) p.overflow[0] = 1u; }
+                            else { if (r[0] == 0x7FFFFFF1u && r[WIDTH - 1] == 0x7FFFFFF1u) p.overflow[0] = 1u; }
+                            continue;
+                        }
+#endif
                         // The block's best raw score belongs to a real row r* with dot_i = 4 S + rowterm + colterm >= 4 mx + rt_min
                         // + ct =: d and kappa' = fl(fl(dot_i) * inv_r), 1 / norm_hi <= inv_r <= 1 / norm_lo: kappa'(r*) >= d / norm_hi
                         // for d >= 0 and >= d / norm_lo otherwise (minus the roundings: relative 4e-6 and an absolute crumb).
+                        const uint32_t col0 = col_base + WIDTH * hf;
+                        const uint32_t qi = qbase + j;
+                        const int ct = s_colterm[j];
                         const size_t blk = (size_t)((i * TN + col0) >> 5);
                         const float d0 = (float)(4 * mx0 + __float_as_int(bm0.w) + ct);
                         const float lb0 = d0 >= 0.0f ? __fdiv_rn(d0, bm0.y) : __fdiv_rn(d0, bm0.x);
@@ -798,48 +869,31 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                             if (p.seed_lb) p.seed_lb[(blk + 1) * p.nq_pad + qi] = lb1 - fabsf(lb1) * 4.0e-6f - 1.0e-3f;
                         }
                     } else {
-                        // one bound for the WIDTH rows from the union of the blocks' ranges
-                        float4 bm;
-                        bm.x = fminf(bm0.x, bm1.x); bm.y = fmaxf(bm0.y, bm1.y);
-                        bm.z = __int_as_float(max(__float_as_int(bm0.z), __float_as_int(bm1.z))); bm.w = 0.0f;
-                        const int v = bound(thr, ct, bm);
-                        const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, mx0 >= v);
-                        if constexpr (WIDTH == 32) {
-#ifdef PBX_BATCH_DEFER        // measured: 2.42 ms instead of 2.23 at 10M x 256 x 1024, 3.29 instead of 2.66 at 12.5M x 64 -- off
-                            if (hf + 1 < STEPS) {
-#else
-                            if (false) {
-#endif
-                                // Experiment (PBX_BATCH_DEFER): in the steps before the last, one or two survivors are only dumped
-                                // and tested after the accumulator has been handed back.  Slower in every shape but dim 1024.
-                                if (m0) {
-                                    if (__popc(m0) <= 2) {
-                                        if (mx0 >= v) dump_lane(r, __popc(m0 & ((1u << lane) - 1u)), v, thr, ct, qi, row0, col0);
-                                        deferred = __popc(m0);
-                                    } else {
-                                        resolve_now(r, m0, v, thr, ct, qi, row0, col0, ms);
-                                    }
-                                }
-                            } else {
-                                if (deferred) { test_slots(0, deferred, ms); deferred = 0; }
-                                if (m0) resolve_now(r, m0, v, thr, ct, qi, row0, col0, ms);
+                        const int v0 = bound(t4, cq, bm0);
+                        const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, mx0 >= v0);
+                        if (m0) {                                            // rare: fetch what only the survivor path needs
+                            const uint32_t col0 = col_base + WIDTH * hf;
+                            resolve_now(r, m0, v0, s_thr[j], s_colterm[j], qbase + j, t * TN + col0, col0, ms);
+                        }
+                        if constexpr (WIDTH == 64) {
+                            const int v1 = bound(t4, cq, bm1);
+                            const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, mx1 >= v1);
+                            if (m1) {
+                                const uint32_t col0 = col_base + WIDTH * hf + 32u;
+                                resolve_now(r + WIDTH - 32, m1, v1, s_thr[j], s_colterm[j], qbase + j, t * TN + col0, col0, ms);
                             }
-                        } else {
-                            const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, mx1 >= v);
-                            if (m0) resolve_now(r, m0, v, thr, ct, qi, row0, col0, ms);
-                            if (m1) resolve_now(r + WIDTH - 32, m1, v, thr, ct, qi, row0 + 32u, col0 + 32u, ms);
                         }
                     }
                     if (threadIdx.x == 0) PBX_BP_ADD(7, te7);
                 }
-                if constexpr (!SEED) {
-                    // staged candidates: complete the flush issued a stage ago, issue the next one when enough are waiting
-                    __syncwarp();
-                    if (*reinterpret_cast<volatile uint32_t*>(my_cnt) >= kBatchStage / 2) { flush_complete(); flush_issue(); }
-                }
+            }
+            if constexpr (!SEED) {
+                // staged candidates: complete the flush issued a tile ago, issue the next one when enough are waiting
+                __syncwarp();
+                if (*reinterpret_cast<volatile uint32_t*>(my_cnt) >= kBatchStage / 2) { flush_complete(); flush_issue(); }
             }
             __syncwarp();                                            // done with this tile's metadata
-            if (lane == 0) mbar_arrive_at(smem_u32(&m_empty[ms]));
+            if (lane == 0) mbar_arrive_at(m_empty0 + ms * 8u);
         }
         if (!SEED) flush();
 #ifdef PBX_BATCH_PROF
