@@ -20,15 +20,23 @@
 // hold both a whole batch of queries and two corpus tiles; a CTA pair splits the tile (128 rows each, fetched by the
 // hardware from both shared memories) and holds 2 x 512 queries, so the corpus is streamed once per batch of 1024.
 //
-// Warp roles per CTA: warp 8 streams corpus K-chunks with TMA into an mbarrier ring; one thread of warp 9 (leader CTA
-// only) issues the MMAs into a ring of TMEM accumulators (2 x 256 columns); warps 0..7 are the epilogue: warp w owns
-// TMEM lanes 32 (w % 4) .. +31 (queries) and half of the columns (rows) of every accumulator, read 64 at a time.  Survivors of the
-// bound take the exact float test; the few that beat the threshold are staged per warp and pushed to the per-query
-// candidate buffers.  Starting thresholds come from a seed pass of the same kernel over a strided sample of tiles (one
-// bound per query and 32-row block, nothing pushed; batch_seed_select_kernel takes each query's keep-th largest); inside
-// the main pass the thresholds tighten from per-query histograms of the accepted keys; batch_tighten_kernel cuts the
-// buffers back to `keep` at the end.  The final candidates go through the same bit-exact re-rank and certificate as the
-// single-query path (batch_finalize_kernel).
+// Warp roles per CTA (576 threads): warp 16 streams corpus K-chunks (and the tile's row / block metadata) with TMA into
+// mbarrier rings; warp 17 of the pair leader issues the MMAs into a ring of two TMEM accumulators (2 x 256 columns): its
+// descriptors are ready before it waits for an accumulator, so that nothing but the issue itself follows the epilogue's
+// last arrival; warps 0..15 are the epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31 (queries) and a quarter of the
+// columns (rows) of every accumulator, read 32 at a time.  Per 32 x 32 scores the common case is one tcgen05.ld, 16
+// three-input maxima, one bound (select + FMA + add + conversion against per-query terms precomputed in shared memory)
+// and one vote.  Survivors of the bound take the exact float test; the few that beat the threshold are staged per warp
+// and pushed to the per-query candidate buffers.  Starting thresholds come from a seed pass of the same kernel over a
+// strided sample of tiles (one bound per query and 32-row block, nothing pushed; batch_seed_select_kernel takes each
+// query's keep-th largest); inside the main pass the thresholds tighten from per-query histograms of the accepted keys;
+// batch_tighten_kernel cuts the buffers back to `keep` at the end.  The final candidates go through the same bit-exact
+// re-rank and certificate as the single-query path (batch_finalize_kernel).
+//
+// What bounds the main pass (measured, profiles/README.md round 2c): with an epilogue that only loads the accumulators and
+// hands them back a 128 x 256 stage still takes ~760 cycles at K = 64 (MMA: 256) and ~1380 at K = 256 (MMA: 1024) -- the
+// hand-off is a latency chain (commit -> wait -> tcgen05.ld -> arrive -> wait -> issue -> MMA) and two accumulators are
+// all the 512 TMEM columns hold.  The epilogue's own instructions come on top (IPC 0.4-0.6 per scheduler).
 #pragma once
 #include <cuda.h>
 #include <cstdio>
@@ -49,7 +57,7 @@ constexpr int kBatchEpiWarps = PBX_BATCH_EPI_WARPS;   // 16: four per TMEM lane 
 // many columns of G times fewer stages, the fixed cost per stage and warp is paid G times less often, and an accumulator
 // goes back to the MMA thread when kBatchEpiWarps / G warps (not all of them) have read it.
 constexpr int kBatchEpiGroups = PBX_BATCH_EPI_GROUPS;
-constexpr int kBatchThreads = 64 + 32 * kBatchEpiWarps;   // warps 0..7 epilogue, warp 8 TMA producer, warp 9 MMA issuer
+constexpr int kBatchThreads = 64 + 32 * kBatchEpiWarps;   // epilogue warps, then the TMA producer warp, then the MMA issuer warp
 // The two single-thread roles sit on the HIGHEST warp ids: the warp scheduler prefers high warp ids among eligible
 // warps, and an MMA issuer that shares its scheduler with four polling epilogue warps of higher priority starves.
 constexpr int kBatchTmaWarp = kBatchEpiWarps, kBatchMmaWarp = kBatchEpiWarps + 1;
