@@ -570,10 +570,13 @@ def run_ours(args):
             n1.record(stream)
             barrier()
         ns_ms = allmax([n0.elapsed_time(n1) / ns_steps])[0]
+        for i in range(3):                                   # the host-buffer path's own first-call set-up stays outside
+            sc.search(nsq[i % 8], k, 1e3)
+        barrier()
         t0 = time.perf_counter()
-        for i in range(8):
+        for i in range(16):
             res_ns = sc.search(nsq[i % 8], k, 1e3)[0]
-        ns_e2e = allmax([(time.perf_counter() - t0) / 8 * 1e3])[0]
+        ns_e2e = allmax([(time.perf_counter() - t0) / 16 * 1e3])[0]
         res_q0 = sc.search(nsq[0], k, 1e3)[0]
         ns_check = "skipped"
         if rank == 0:

@@ -35,7 +35,7 @@ __device__ __forceinline__ void ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 // EPI epilogue warps (multiple of 4), then one MMA warp.  NT = 256, K = 256 bytes.
-template <int CG, int EPI>
+template <int CG, int EPI, int KS>      // KS = K / 32 MMAs per stage: 8 = K 256, 2 = K 64
 __global__ void __launch_bounds__(32 * (EPI + 1)) pipe_kernel(int iters, unsigned long long* cycles, unsigned* sink) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -65,9 +65,9 @@ __global__ void __launch_bounds__(32 * (EPI + 1)) pipe_kernel(int iters, unsigne
                 const int s = it & 1;
                 mbar_wait(&acc_empty[s], ((it >> 1) & 1) ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                for (int kc = 0; kc < 2; ++kc) {
+                for (int kc = 0; kc < (KS + 3) / 4; ++kc) {
                     const uint64_t da = make_desc_sw128(sa + kc * 128 * 128), db = make_desc_sw128(sb + kc * NB * 128);
-                    for (int ks = 0; ks < 4; ++ks) umma_i8<CG>(tmem + s * NT, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, (kc | ks) ? 1u : 0u);
+                    for (int ks = 0; ks < (KS < 4 ? KS : 4); ++ks) umma_i8<CG>(tmem + s * NT, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, (kc | ks) ? 1u : 0u);
                 }
                 umma_commit<CG>(&acc_full[s]);
             }
@@ -103,9 +103,9 @@ __global__ void __launch_bounds__(32 * (EPI + 1)) pipe_kernel(int iters, unsigne
         else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
     }
 }
-template <int CG, int EPI> static void run(int iters) {
+template <int CG, int EPI, int KS = 8> static void run(int iters) {
     const size_t smem = (size_t)2 * (128 + 256 / CG) * 128 + 1024;
-    auto kern = pipe_kernel<CG, EPI>;
+    auto kern = pipe_kernel<CG, EPI, KS>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned long long* dcyc; unsigned* dsink;
     CK(cudaMalloc(&dcyc, 8 * 148)); CK(cudaMalloc(&dsink, 4)); CK(cudaMemset(dcyc, 0, 8 * 148));
@@ -116,12 +116,14 @@ template <int CG, int EPI> static void run(int iters) {
     cfg.attrs = attr; cfg.numAttrs = 1;
     for (int rep = 0; rep < 2; ++rep) { CK(cudaLaunchKernelEx(&cfg, kern, iters, dcyc, dsink)); CK(cudaDeviceSynchronize()); }
     unsigned long long cyc = 0; CK(cudaMemcpy(&cyc, dcyc, 8, cudaMemcpyDeviceToHost));
-    printf("{\"cta_group\": %d, \"epilogue_warps\": %d, \"cycles_per_stage\": %.1f}\n", CG, EPI, (double)cyc / iters); fflush(stdout);
+    printf("{\"cta_group\": %d, \"epilogue_warps\": %d, \"K\": %d, \"cycles_per_stage\": %.1f}\n", CG, EPI, KS * 32, (double)cyc / iters); fflush(stdout);
     cudaFree(dcyc); cudaFree(dsink);
 }
 int main() {
     CK(cudaSetDevice(0));
     run<1, 4>(20000); run<1, 8>(20000); run<1, 16>(20000);
     run<2, 4>(20000); run<2, 8>(20000); run<2, 16>(20000);
+    run<1, 16, 2>(20000); run<2, 4, 2>(20000); run<2, 8, 2>(20000); run<2, 16, 2>(20000);     // K = 64: the hand-off chain itself
+    run<2, 16, 1>(20000); run<2, 16, 4>(20000);
     return 0;
 }
