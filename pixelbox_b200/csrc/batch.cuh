@@ -70,6 +70,9 @@ constexpr uint32_t kBatchStage = 32;         // staged candidates per epilogue w
 
 // ---- PTX helpers -------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// A value the compiler must keep in a register: without this it re-derives the address of a __shared__ object from
+// SR_CgaCtaId (an S2UR with a long latency) at every use, also right behind a barrier wait on the hand-off's critical path.
+__device__ __forceinline__ uint32_t keep_u32(uint32_t v) { uint32_t r; asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; }
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {        // shared::cluster address of `addr` in CTA `rank`
     uint32_t r;
@@ -563,7 +566,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
             // arrive -> wait -> issue -> MMA -> commit -> wait -> tcgen05.ld -> arrive, two of them in flight).
             const uint32_t da_lo = (uint32_t)da0, da_hi = (uint32_t)(da0 >> 32), db_lo = (uint32_t)db0, db_hi = (uint32_t)(db0 >> 32);
             const uint32_t a_kc = (QG * W) >> 4, a_mb = (128u * W) >> 4, b_st = stage_bytes >> 4;    // descriptor steps (16-byte units)
-            const uint32_t acc_empty_l = smem_u32(&acc_empty[0]), a_full_l = smem_u32(&a_full[0]);
+            const uint32_t acc_empty_l = keep_u32(smem_u32(&acc_empty[0])), a_full_l = keep_u32(smem_u32(&a_full[0]));
             const long long tm_all = PBX_BP_T();
             for (uint32_t i = ci; i < p.n_tiles; i += cstride) {
                 uint32_t st = st0, ph = ph0;
@@ -572,7 +575,8 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                     const uint32_t d_tmem = tmem + ab * TN;
                     st = st0; ph = ph0;
                     uint32_t a_lo = da_lo + mb * a_mb, b_lo = db_lo + st * b_st;
-                    asm volatile("" ::"r"(a_lo), "r"(b_lo), "r"(d_tmem), "r"(acc_empty_l + ab * 8u));
+                    uint64_t a_d = ((uint64_t)da_hi << 32) | (uint64_t)a_lo, b_d = ((uint64_t)db_hi << 32) | (uint64_t)b_lo;
+                    asm volatile("" ::"l"(a_d), "l"(b_d), "r"(d_tmem), "r"(acc_empty_l + ab * 8u), "r"(idesc));
                     const long long tm0 = PBX_BP_T();
                     if (PBX_BATCH_SPIN & 1) mbar_spin_at(acc_empty_l + ab * 8u, par ^ 1u);
                     else mbar_wait_at(acc_empty_l + ab * 8u, par ^ 1u);           // the epilogues have drained its previous use
@@ -588,8 +592,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                         if (lane == 0) {
                             const long long tm9 = PBX_BP_T();
                             for (uint32_t ks = 0; ks < ksteps; ++ks)
-                                umma_i8<CG>(d_tmem, ((uint64_t)da_hi << 32) | (uint64_t)(a_lo + ks * 2u), ((uint64_t)db_hi << 32) | (uint64_t)(b_lo + ks * 2u),
-                                            idesc, (kc | ks) ? 1u : 0u);
+                                umma_i8<CG>(d_tmem, a_d + (uint64_t)(ks * 2u), b_d + (uint64_t)(ks * 2u), idesc, (kc | ks) ? 1u : 0u);
                             PBX_BP_ADD(0, tm9);
                             const long long tm10 = PBX_BP_T();
                             if (mb == MB - 1) umma_commit<CG>(&a_empty[st]);       // the stage is free once these MMAs retire
@@ -598,6 +601,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                         __syncwarp();
                         if (++st == STAGES) { st = 0; ph ^= 1u; }
                         a_lo += a_kc; b_lo = db_lo + st * b_st;
+                        a_d = ((uint64_t)da_hi << 32) | (uint64_t)a_lo; b_d = ((uint64_t)db_hi << 32) | (uint64_t)b_lo;
                     }
                     if (lane == 0) umma_commit<CG>(&acc_full[ab]);
                     __syncwarp();
@@ -634,7 +638,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
         uint32_t* my_q = st_q + e * kBatchStage;
         uint32_t* my_cnt = &st_cnt[e];
         int* my_scr = s_scr + e * (kBatchScrSlots * kBatchScrWords);   // survivor slots: 32 scores + {v, thr, ct, qi, row0, col0}
-        const uint32_t acc_empty0 = CG == 1 ? smem_u32(&acc_empty[0]) : mapa_u32(smem_u32(&acc_empty[0]), 0);
+        const uint32_t acc_empty0 = keep_u32(CG == 1 ? smem_u32(&acc_empty[0]) : mapa_u32(smem_u32(&acc_empty[0]), 0));
 
         // Accepted candidates are staged per warp in shared memory and leave in two steps that never wait for each other
         // inside one accumulator stage: `flush_issue` sends the slot atomics of up to 32 staged records (their results stay
@@ -809,7 +813,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
         uint32_t live_mb = 0;
         for (uint32_t mb = 0; mb < MB; ++mb)
             if (__any_sync(0xFFFFFFFFu, s_invq[mb * 128u + quarter * 32u + (uint32_t)lane] > 0.0f)) live_mb |= 1u << mb;
-        const uint32_t acc_full0 = smem_u32(&acc_full[0]), m_full0 = smem_u32(&m_full[0]), m_empty0 = smem_u32(&m_empty[0]);
+        const uint32_t acc_full0 = keep_u32(smem_u32(&acc_full[0])), m_full0 = keep_u32(smem_u32(&m_full[0])), m_empty0 = keep_u32(smem_u32(&m_empty[0]));
         for (uint32_t i = ci; i < p.n_tiles; i += cstride, ++tile_iter) {
             const uint32_t t = i * p.tile_step;
             // refresh points: every tile at first (the starting thresholds are loose), then ever more rarely
