@@ -89,3 +89,33 @@ def test_batched_k1000_large_buffers_on_a_bigger_corpus():
             assert list(got[qi].ids) == list(o_ids), qi
             assert np.array_equal(np.asarray(got[qi].dist).view(np.uint32), o_dist.view(np.uint32)), qi
             assert np.array_equal(got[qi].dot, o_dot) and np.array_equal(got[qi].norm2, o_n2)
+
+
+@pytest.mark.parametrize("d,n", [(64, 40_000), (256, 30_000), (32, 50_000), (1024, 8_000)])
+def test_batched_bound_with_wild_norm_spread_and_negative_thresholds(d, n):
+    """The epilogue tests max(32 raw scores) against ONE bound per query and 32-row block, built from the block's norm
+    range, its largest row term and the query's threshold (batch_bound_t4 / batch_bound_cq).  A bound that is too tight
+    loses a true neighbour silently (the certificate only sees candidates that were found), so: blocks that mix rows of
+    almost no norm (bytes 127 / 128), of maximal norm (bytes 0 / 255) and ordinary rows; queries of all three kinds and
+    their complements (all cosines negative: negative thresholds); every query checked against the oracle."""
+    rng = np.random.default_rng(1000 + d)
+    kind = rng.integers(0, 4, size=n)
+    corpus = rng.integers(0, 256, size=(n, d), dtype=np.uint8)
+    tiny = rng.integers(127, 129, size=(n, d), dtype=np.uint8)
+    huge = (rng.integers(0, 2, size=(n, d), dtype=np.uint8) * 255).astype(np.uint8)
+    dark = rng.integers(0, 40, size=(n, d), dtype=np.uint8)             # large norm, large negative row term
+    corpus[kind == 1] = tiny[kind == 1]
+    corpus[kind == 2] = huge[kind == 2]
+    corpus[kind == 3] = dark[kind == 3]
+    ids = rng.permutation(np.arange(1, n + 1)).astype(np.int64)
+    base = corpus[rng.integers(0, n, 24)].astype(int)
+    near = np.clip(base + rng.integers(-3, 4, size=base.shape), 0, 255).astype(np.uint8)
+    queries = np.concatenate([near, (255 - near).astype(np.uint8), rng.integers(0, 256, size=(8, d), dtype=np.uint8),
+                              np.full((1, d), 128, np.uint8), np.full((1, d), 0, np.uint8), np.full((1, d), 255, np.uint8)])
+    with Corpus(d) as c:
+        c.load(ids, corpus)
+        for k, md in ((100, 1e7), (10, 1e3), (300, 1e7)):
+            before = c.stats().batched_queries
+            check(corpus, ids, queries, k, md, c)
+            # (k = 300 needs 562 sampled 32-row blocks for its seed: the smallest corpus here answers it query by query)
+            assert k > 100 or c.stats().batched_queries == before + len(queries), "the tensor-core path did not run"
