@@ -40,6 +40,7 @@
 #pragma once
 #include <cuda.h>
 #include <cstdio>
+#include <type_traits>
 #include "rerank.cuh"
 
 namespace pbx {
@@ -568,46 +569,61 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
             const uint32_t a_kc = (QG * W) >> 4, a_mb = (128u * W) >> 4, b_st = stage_bytes >> 4;    // descriptor steps (16-byte units)
             const uint32_t acc_empty_l = keep_u32(smem_u32(&acc_empty[0])), a_full_l = keep_u32(smem_u32(&a_full[0]));
             const long long tm_all = PBX_BP_T();
-            for (uint32_t i = ci; i < p.n_tiles; i += cstride) {
-                uint32_t st = st0, ph = ph0;
-                for (uint32_t mb = 0; mb < MB; ++mb, ++acc_it) {
-                    const uint32_t ab = acc_it & (AS - 1u), par = (acc_it >> AS_LOG) & 1u;
-                    const uint32_t d_tmem = tmem + ab * TN;
-                    st = st0; ph = ph0;
-                    uint32_t a_lo = da_lo + mb * a_mb, b_lo = db_lo + st * b_st;
-                    uint64_t a_d = ((uint64_t)da_hi << 32) | (uint64_t)a_lo, b_d = ((uint64_t)db_hi << 32) | (uint64_t)b_lo;
-                    asm volatile("" ::"l"(a_d), "l"(b_d), "r"(d_tmem), "r"(acc_empty_l + ab * 8u), "r"(idesc));
-                    const long long tm0 = PBX_BP_T();
-                    if (PBX_BATCH_SPIN & 1) mbar_spin_at(acc_empty_l + ab * 8u, par ^ 1u);
-                    else mbar_wait_at(acc_empty_l + ab * 8u, par ^ 1u);           // the epilogues have drained its previous use
-                    PBX_BP_ADD(2, tm0);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    for (uint32_t kc = 0; kc < KC; ++kc) {
-                        if (mb == 0) {
-                            const long long tm1 = PBX_BP_T();
-                            mbar_wait_at(a_full_l + st * 8u, ph);
-                            PBX_BP_ADD(3, tm1);
-                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // one copy of the loop per K-chunk width: the MMAs of a chunk are then straight-line code with immediate offsets
+            auto issue_all = [&](auto ks_c, auto kc_c) {
+                constexpr uint32_t KS = decltype(ks_c)::value;          // MMAs (K = 32) per K-chunk = W / 32
+                constexpr uint32_t KCC = decltype(kc_c)::value;         // K-chunks per row when known at compile time (0: p.kc)
+                const uint32_t KCN = KCC ? KCC : KC;
+                for (uint32_t i = ci; i < p.n_tiles; i += cstride) {
+                    uint32_t st = st0, ph = ph0;
+                    for (uint32_t mb = 0; mb < MB; ++mb, ++acc_it) {
+                        const uint32_t ab = acc_it & (AS - 1u), par = (acc_it >> AS_LOG) & 1u;
+                        const uint32_t d_tmem = tmem + ab * TN;
+                        st = st0; ph = ph0;
+                        uint32_t a_lo = da_lo + mb * a_mb, b_lo = db_lo + st * b_st;
+                        uint64_t a_d = ((uint64_t)da_hi << 32) | (uint64_t)a_lo, b_d = ((uint64_t)db_hi << 32) | (uint64_t)b_lo;
+                        asm volatile("" ::"l"(a_d), "l"(b_d), "r"(d_tmem), "r"(acc_empty_l + ab * 8u), "r"(idesc));
+                        const long long tm0 = PBX_BP_T();
+                        if (PBX_BATCH_SPIN & 1) mbar_spin_at(acc_empty_l + ab * 8u, par ^ 1u);
+                        else mbar_wait_at(acc_empty_l + ab * 8u, par ^ 1u);           // the epilogues have drained its previous use
+                        PBX_BP_ADD(2, tm0);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                        for (uint32_t kc = 0; kc < KCN; ++kc) {
+                            if (mb == 0) {
+                                const long long tm1 = PBX_BP_T();
+                                mbar_wait_at(a_full_l + st * 8u, ph);
+                                PBX_BP_ADD(3, tm1);
+                                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            }
+                            if (lane == 0) {
+                                const long long tm9 = PBX_BP_T();
+    #pragma unroll
+                                for (uint32_t ks = 0; ks < KS; ++ks)
+                                    umma_i8<CG>(d_tmem, a_d + (uint64_t)(ks * 2u), b_d + (uint64_t)(ks * 2u), idesc, (kc | ks) ? 1u : 0u);
+                                PBX_BP_ADD(0, tm9);
+                                const long long tm10 = PBX_BP_T();
+                                if (mb == MB - 1) umma_commit<CG>(&a_empty[st]);       // the stage is free once these MMAs retire
+                                PBX_BP_ADD(1, tm10);
+                            }
+                            __syncwarp();
+                            if (++st == STAGES) { st = 0; ph ^= 1u; }
+                            a_lo += a_kc; b_lo = db_lo + st * b_st;
+                            a_d = ((uint64_t)da_hi << 32) | (uint64_t)a_lo; b_d = ((uint64_t)db_hi << 32) | (uint64_t)b_lo;
                         }
-                        if (lane == 0) {
-                            const long long tm9 = PBX_BP_T();
-                            for (uint32_t ks = 0; ks < ksteps; ++ks)
-                                umma_i8<CG>(d_tmem, a_d + (uint64_t)(ks * 2u), b_d + (uint64_t)(ks * 2u), idesc, (kc | ks) ? 1u : 0u);
-                            PBX_BP_ADD(0, tm9);
-                            const long long tm10 = PBX_BP_T();
-                            if (mb == MB - 1) umma_commit<CG>(&a_empty[st]);       // the stage is free once these MMAs retire
-                            PBX_BP_ADD(1, tm10);
-                        }
+                        if (lane == 0) umma_commit<CG>(&acc_full[ab]);
                         __syncwarp();
-                        if (++st == STAGES) { st = 0; ph ^= 1u; }
-                        a_lo += a_kc; b_lo = db_lo + st * b_st;
-                        a_d = ((uint64_t)da_hi << 32) | (uint64_t)a_lo; b_d = ((uint64_t)db_hi << 32) | (uint64_t)b_lo;
                     }
-                    if (lane == 0) umma_commit<CG>(&acc_full[ab]);
-                    __syncwarp();
+                    st0 = st; ph0 = ph;
                 }
-                st0 = st; ph0 = ph;
-            }
+            };
+            using std::integral_constant;
+            if (ksteps == 4u && KC == 2u) issue_all(integral_constant<uint32_t, 4>{}, integral_constant<uint32_t, 2>{});         // dim 256
+            else if (ksteps == 4u && KC == 1u) issue_all(integral_constant<uint32_t, 4>{}, integral_constant<uint32_t, 1>{});    // dim 128
+            else if (ksteps == 2u && KC == 1u) issue_all(integral_constant<uint32_t, 2>{}, integral_constant<uint32_t, 1>{});    // dim 64
+            else if (ksteps == 4u) issue_all(integral_constant<uint32_t, 4>{}, integral_constant<uint32_t, 0>{});
+            else if (ksteps == 2u) issue_all(integral_constant<uint32_t, 2>{}, integral_constant<uint32_t, 0>{});
+            else issue_all(integral_constant<uint32_t, 1>{}, integral_constant<uint32_t, 0>{});
             PBX_BP_ADD(4, tm_all);
 #ifdef PBX_BATCH_PROF
             if (lane == 0) { g_batch_prof[blockIdx.x][2] += bp_acc[2]; g_batch_prof[blockIdx.x][3] += bp_acc[3]; g_batch_prof[blockIdx.x][4] += bp_acc[4];
