@@ -135,6 +135,9 @@ __device__ __forceinline__ void mbar_spin_at(uint32_t bar_addr, uint32_t parity)
 #ifndef PBX_BATCH_SPIN
 #define PBX_BATCH_SPIN 0
 #endif
+#ifndef PBX_BATCH_LDPIPE       // experiment: second tcgen05.ld of a stage in flight while the first half is processed.  Measured
+#define PBX_BATCH_LDPIPE 0     // slower (2.10 instead of 2.01 ms at 10M x 256, 2.69 instead of 2.47 ms at 12.5M x 64; 96 registers): off
+#endif
 template <int CG>
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint32_t bar_addr, int x, int y) {
     if constexpr (CG == 1)
@@ -861,20 +864,8 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                     if (lane == 0) mbar_arrive_at(acc_empty0 + ab * 8u);
                     continue;
                 }
-#pragma unroll
-                for (uint32_t hf = 0; hf < STEPS; ++hf) {              // WIDTH columns = one or two 32-row blocks at a time
-                    uint32_t r[WIDTH];
-                    const long long te6b = PBX_BP_T();
-                    tmem_ld_issue(taddr + WIDTH * hf, r);
-                    tmem_ld_done(r);
-                    if (hf == STEPS - 1) {
-                        // the last scores are in registers: hand the accumulator back to the MMA thread before looking at them
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_at(acc_empty0 + ab * 8u);
-                    }
-                    if (threadIdx.x == 0) PBX_BP_ADD(6, te6b);
-                    const long long te7 = PBX_BP_T();
+                // what is done with WIDTH scores of this lane's query (block(s) hf of the warp's column slice)
+                auto process = [&](const uint32_t* r, const uint32_t hf) {
                     const float4 bm0 = bmp[hf * (WIDTH / 32u)];
                     const float4 bm1 = WIDTH == 64 ? bmp[hf * (WIDTH / 32u) + 1u] : bm0;
                     const int mx0 = max32(r), mx1 = WIDTH == 64 ? max32(r + WIDTH - 32) : mx0;
@@ -883,7 +874,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                         if (p.seed_lb == nullptr) {
                             if (PBX_BATCH_EXPSKIP == 2) { if (mx0 == 0x7FFFFFF1 || mx1 == 0x7FFFFFF1) p.overflow[0] = 1u; }
                             else { if (r[0] == 0x7FFFFFF1u && r[WIDTH - 1] == 0x7FFFFFF1u) p.overflow[0] = 1u; }
-                            continue;
+                            return;
                         }
 #endif
                         // The block's best raw score belongs to a real row r* with dot_i = 4 S + rowterm + colterm >= 4 mx + rt_min
@@ -917,7 +908,34 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                             }
                         }
                     }
-                    if (threadIdx.x == 0) PBX_BP_ADD(7, te7);
+                };
+                auto hand_back = [&]() {                                 // the last scores are in registers: the MMA thread may reuse the accumulator
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_at(acc_empty0 + ab * 8u);
+                };
+                const long long te6b = PBX_BP_T();
+                if constexpr (STEPS == 2 && PBX_BATCH_LDPIPE) {
+                    // the second load is in flight while the first 32 columns are looked at: only one tcgen05.ld round trip is
+                    // exposed per stage, and the accumulator goes back before the second half is looked at
+                    uint32_t ra[WIDTH], rb[WIDTH];
+                    tmem_ld_issue(taddr, ra);
+                    tmem_ld_done(ra);
+                    tmem_ld_issue(taddr + WIDTH, rb);
+                    process(ra, 0u);
+                    tmem_ld_done(rb);
+                    hand_back();
+                    if (threadIdx.x == 0) PBX_BP_ADD(6, te6b);
+                    process(rb, 1u);
+                } else {
+#pragma unroll
+                    for (uint32_t hf = 0; hf < STEPS; ++hf) {          // WIDTH columns = one or two 32-row blocks at a time
+                        uint32_t r[WIDTH];
+                        tmem_ld_issue(taddr + WIDTH * hf, r);
+                        tmem_ld_done(r);
+                        if (hf == STEPS - 1) hand_back();
+                        process(r, hf);
+                    }
                 }
             }
             if constexpr (!SEED) {
