@@ -156,7 +156,13 @@ PBX_API int pbx_search_hits(pbx_corpus* c, const uint8_t* queries, uint32_t nq, 
  * are DEVICE pointers on the corpus' device; the work is enqueued on `cuda_stream` (a
  * cudaStream_t; NULL = the corpus' own stream) and the call returns without waiting.  This is
  * what a pipeline (or the multi-GPU driver, which all-gathers d_hits with NCCL on the same
- * stream) uses; no host synchronisation happens inside. */
+ * stream) uses; no host synchronisation happens inside.
+ * Stream-ordering contract: the first kernel of a call is launched with programmatic stream
+ * serialisation and reads d_queries in its prologue.  d_queries must therefore be complete in
+ * stream order in the ordinary sense: written by copies, by kernels that have finished, or by a
+ * preceding kernel on `cuda_stream` that does NOT trigger its dependents early
+ * (cudaTriggerProgrammaticLaunchCompletion / griddepcontrol.launch_dependents) before its last
+ * write to d_queries.  The library's own kernels never trigger early. */
 PBX_API int pbx_search_device(pbx_corpus* c, const uint8_t* d_queries, uint32_t nq, uint32_t k, double max_dist,
                               pbx_hit* d_hits, uint32_t* d_count, void* cuda_stream);
 
