@@ -119,3 +119,46 @@ def test_batched_bound_with_wild_norm_spread_and_negative_thresholds(d, n):
             check(corpus, ids, queries, k, md, c)
             # (k = 300 needs 562 sampled 32-row blocks for its seed: the smallest corpus here answers it query by query)
             assert k > 100 or c.stats().batched_queries == before + len(queries), "the tensor-core path did not run"
+
+
+def test_full_size_10m_batch_of_1024_properties():
+    """BASELINE configs[2] at full size (10M x 256, 1024 queries, top-100) through the tensor-core path: too big for an oracle pass
+    over the corpus, so size-independent properties on a spread of the queries: planted self-matches lead with the reference's
+    self-distance, the returned rows re-rank identically under the oracle (ids, order, distance bits, integer terms), and in
+    a random 100k-row stripe per checked query no row beats the k-th hit without being in the answer (nothing was missed);
+    the same 16 queries through the single-query path give the same answers."""
+    n, d, k, nq, seed = 10_000_000, 256, 100, 1024, 42
+    with Corpus(d, capacity_hint=n) as c:
+        c.fill_synthetic(n, seed, 0)
+        queries = synth.synth_queries(43, nq, d, n, seed)
+        probes = {0: 17, 500: 5_000_000, 1023: n - 1}
+        for qi, row in probes.items():
+            queries[qi] = synth.synth_rows(seed, row, 1, d)[0]
+        before = c.stats().batched_queries
+        res = c.search(queries, k)
+        assert c.stats().batched_queries == before + nq, "the tensor-core path did not run"
+        rng = np.random.default_rng(8)
+        checked = sorted(set(probes) | set(int(x) for x in rng.integers(0, nq, 13)))
+        for qi in checked:
+            r = res[qi]
+            assert len(r.ids) == k
+            rows = np.concatenate([synth.synth_rows(seed, int(i) - 1, 1, d) for i in r.ids])
+            o_ids, o_dist, o_dot, o_n2 = oracle.topk(rows, r.ids, queries[qi], k, 1e3)
+            assert list(r.ids) == list(o_ids) and np.array_equal(bits(r.dist), bits(o_dist)), f"q{qi}: returned rows re-rank differently"
+            assert np.array_equal(r.dot, o_dot) and np.array_equal(r.norm2, o_n2)
+            if qi in probes:
+                assert r.ids[0] == probes[qi] + 1
+                assert bits(r.dist[0]) == bits(oracle.cosine_distance(queries[qi], queries[qi]))
+            s0 = int(rng.integers(0, n - 100_000))
+            stripe = synth.synth_rows(seed, s0, 100_000, d)
+            s_ids = np.arange(s0 + 1, s0 + 100_001, dtype=np.int64)
+            t_ids, t_dist, _, _ = oracle.topk(stripe, s_ids, queries[qi], k, 1e3, threads=oracle.max_threads())
+            kth, have = (float(r.dist[-1]), int(r.ids[-1])), set(int(x) for x in r.ids)
+            for i, dd in zip(t_ids, t_dist):
+                assert not ((float(dd), int(i)) < kth) or int(i) in have, f"stripe row {i} (dist {dd}) missing from q{qi}"
+        c.set_batch_min(0xFFFFFFFF)
+        single = c.search(queries[checked], k)
+        for qi, b in zip(checked, single):
+            a = res[qi]
+            assert list(a.ids) == list(b.ids) and np.array_equal(bits(a.dist), bits(b.dist)), f"q{qi}: single-query path differs"
+        assert c.stats().batched_queries == before + nq
