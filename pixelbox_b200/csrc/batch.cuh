@@ -848,13 +848,8 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                 const uint32_t j = mb * 128u + quarter * 32u + (uint32_t)lane;      // this lane's query in the block
                 const float t4 = s_t4[j], cq = s_cq[j];
                 const long long te5 = PBX_BP_T();
-#ifdef PBX_BATCH_ONEWAIT   // experiment: one epilogue warp polls the mbarrier, the others sleep in a named barrier
-                if (warp == 0) mbar_wait_at(acc_full0 + ab * 8u, (acc_it >> AS_LOG) & 1u);
-                asm volatile("bar.sync 2, %0;" ::"r"(32 * kBatchEpiWarps) : "memory");
-#else
                 if (PBX_BATCH_SPIN & 2) mbar_spin_at(acc_full0 + ab * 8u, (acc_it >> AS_LOG) & 1u);
                 else mbar_wait_at(acc_full0 + ab * 8u, (acc_it >> AS_LOG) & 1u);
-#endif
                 if (threadIdx.x == 0) { PBX_BP_ADD(5, te5); g_prof_stage(); }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t taddr = tmem + ((quarter * 32u) << 16) + ab * TN + col_base;
