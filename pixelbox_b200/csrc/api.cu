@@ -416,6 +416,7 @@ static cudaError_t allow_smem(Kern kern, size_t bytes) {
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 constexpr uint64_t kBatchMaxRows = 0x7FFFF000ull;    // rows the batched path can address (TMA row coordinate is a signed 32-bit int)
+constexpr uint32_t kBatchSegTilesLarge = 98304;      // main-pass segment (25M rows) between cut-backs when keep > 512
 constexpr uint32_t kBatchSeedTiles = 256;            // sample tiles of the batched path's seed pass
 constexpr size_t kBatchSmemLimit = 232448 - 1024;   // 227 KB per CTA minus the kernel's static shared memory
 static cudaError_t init_kernel_attributes() {
@@ -1180,7 +1181,7 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
     // 1. seed pass over a strided sample of complete tiles: one bound per (query, 32-row block), nothing is pushed
     uint32_t seed_tiles, seed_step;
     batch_seed_geometry(n, bp.tn, &seed_tiles, &seed_step);
-    mp.n_tiles = seed_tiles; mp.tile_step = seed_step;
+    mp.n_tiles = seed_tiles; mp.tile_step = seed_step; mp.tile_base = 0;
     CU_TRY((bp.cg == 2 ? launch_batch_mma<2, true>(bp, mp, s) : launch_batch_mma<1, true>(bp, mp, s)));
     // 2. starting threshold of every query = its keep-th largest bound
     BatchSeedSelectParams sp;
@@ -1190,15 +1191,26 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
     if (getenv("PBX_BATCH_EXP")) {
         // experiment: the bare pipeline (TMA, MMA, TMEM loads, max trees; nothing stored) over every tile
         BatchMmaParams xp = mp;
-        xp.seed_lb = nullptr; xp.n_tiles = (n + bp.tn - 1) / bp.tn; xp.tile_step = 1;
+        xp.seed_lb = nullptr; xp.n_tiles = (n + bp.tn - 1) / bp.tn; xp.tile_step = 1; xp.tile_base = 0;
         CU_TRY((bp.cg == 2 ? launch_batch_mma<2, true>(bp, xp, s) : launch_batch_mma<1, true>(bp, xp, s)));
     }
-    // 3. the main pass over every tile; thresholds keep tightening from the per-query histograms of accepted keys
-    mp.n_tiles = (n + bp.tn - 1) / bp.tn; mp.tile_step = 1;
-    CU_TRY((bp.cg == 2 ? launch_batch_mma<2, false>(bp, mp, s) : launch_batch_mma<1, false>(bp, mp, s)));
-    // 4. cut every buffer back to keep: the finalize kernels take at most `keep` candidates per query
-    batch_tighten_kernel<<<nq, 256, (size_t)cap * sizeof(u64), s>>>(tp);
-    CU_TRY(cudaGetLastError());
+    // 3. the main pass over every tile; thresholds keep tightening from the per-query histograms of accepted keys.
+    // 4. cut every buffer back to keep: the finalize kernels take at most `keep` candidates per query.
+    // A query accepts about keep * (1 + ln(rows / sample rows)) keys over a pass (more while a threshold lags): with the large
+    // candidate sets of k ~ 1000 that outgrows the 16384-entry buffers somewhere near 100M rows, and an overflowed buffer
+    // costs its query an exact pass over the whole shard (100M x 256, k = 1000: 7.5 s per 1024 queries instead of 75 ms).
+    // So long shards run the pass in segments with the cut-back in between: the buffers start every segment at `keep`
+    // entries, the thresholds carry over.
+    const uint32_t all_tiles = (n + bp.tn - 1) / bp.tn;
+    uint32_t seg_tiles = keep > 512u ? kBatchSegTilesLarge : all_tiles;
+    if (const char* e = getenv("PBX_BATCH_SEG_TILES")) seg_tiles = std::max<uint32_t>(1u, (uint32_t)atoll(e));    // tests: segments on small shards
+    mp.tile_step = 1;
+    for (uint32_t t0 = 0; t0 < all_tiles; t0 += seg_tiles) {
+        mp.tile_base = t0; mp.n_tiles = std::min<uint32_t>(seg_tiles, all_tiles - t0);
+        CU_TRY((bp.cg == 2 ? launch_batch_mma<2, false>(bp, mp, s) : launch_batch_mma<1, false>(bp, mp, s)));
+        batch_tighten_kernel<<<nq, 256, (size_t)cap * sizeof(u64), s>>>(tp);
+        CU_TRY(cudaGetLastError());
+    }
 
     // per-query finalize: bit-exact re-rank, certificate; exact passes are tail-launched by its last CTA
     const ExactSetup xs = exact_setup(c, 0, k, max_dist, n, d_hits, d_count);       // template of query 0

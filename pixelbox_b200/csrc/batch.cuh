@@ -381,6 +381,7 @@ struct BatchMmaParams {
     uint32_t tn;                // corpus rows per tile = UMMA N (128 or 256)
     uint32_t n_tiles;           // tiles of this launch: tile index = tile_step * i, i < n_tiles
     uint32_t tile_step;         // 1: every tile (MAIN); > 1: a strided sample (SEED)
+    uint32_t tile_base;         // first tile of this launch (MAIN passes over a long shard run in segments; 0 otherwise)
     uint32_t prefetch_tiles;    // tiles the producer prefetches into L2 ahead of the shared-memory ring (0: none)
     uint32_t exp_flags;         // experiment builds (PBX_BATCH_PROF) only
 };
@@ -510,12 +511,12 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
                 for (uint32_t d = 0; d < pf; ++d)
                     if (ci + d * cstride < p.n_tiles)
                         for (uint32_t kc = 0; kc < KC; ++kc)
-                            tma_prefetch_2d(&p.map_rows, (int)(kc * W), (int)((ci + d * cstride) * p.tile_step * TN + rank * NB));
+                            tma_prefetch_2d(&p.map_rows, (int)(kc * W), (int)((p.tile_base + (ci + d * cstride) * p.tile_step) * TN + rank * NB));
             for (uint32_t i = ci; i < p.n_tiles; i += cstride, ++ti) {
-                const uint32_t t = i * p.tile_step;
+                const uint32_t t = p.tile_base + i * p.tile_step;
                 if (pf && lane == 0 && i + pf * cstride < p.n_tiles)
                     for (uint32_t kc = 0; kc < KC; ++kc)
-                        tma_prefetch_2d(&p.map_rows, (int)(kc * W), (int)((i + pf * cstride) * p.tile_step * TN + rank * NB));
+                        tma_prefetch_2d(&p.map_rows, (int)(kc * W), (int)((p.tile_base + (i + pf * cstride) * p.tile_step) * TN + rank * NB));
                 {
                     // inv_norm / row_sum / block metadata of the tile's TN rows (every CTA of a pair sees all of them):
                     // plain bulk copies into a small ring the epilogue reads in place
@@ -834,7 +835,7 @@ batch_mma_kernel(const __grid_constant__ BatchMmaParams p) {
             if (__any_sync(0xFFFFFFFFu, s_invq[mb * 128u + quarter * 32u + (uint32_t)lane] > 0.0f)) live_mb |= 1u << mb;
         const uint32_t acc_full0 = keep_u32(smem_u32(&acc_full[0])), m_full0 = keep_u32(smem_u32(&m_full[0])), m_empty0 = keep_u32(smem_u32(&m_empty[0]));
         for (uint32_t i = ci; i < p.n_tiles; i += cstride, ++tile_iter) {
-            const uint32_t t = i * p.tile_step;
+            const uint32_t t = p.tile_base + i * p.tile_step;
             // refresh points: every tile at first (the starting thresholds are loose), then ever more rarely
             if (!SEED && tile_iter >= 1 && (tile_iter <= 8 || (tile_iter & (tile_iter - 1)) == 0 || (tile_iter & 31u) == 0)) refresh();
             const uint32_t ms = tile_iter & (kBatchMetaSlots - 1u);

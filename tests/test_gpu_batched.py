@@ -162,3 +162,22 @@ def test_full_size_10m_batch_of_1024_properties():
             a = res[qi]
             assert list(a.ids) == list(b.ids) and np.array_equal(bits(a.dist), bits(b.dist)), f"q{qi}: single-query path differs"
         assert c.stats().batched_queries == before + nq
+
+
+def test_main_pass_in_segments_gives_the_same_answers(monkeypatch):
+    """Long shards with large candidate sets run the main pass in segments with a cut-back of the candidate buffers in
+    between (a buffer that overflows costs its query an exact pass).  Forced here on a small shard (PBX_BATCH_SEG_TILES):
+    thresholds and candidates carry over from segment to segment, the answers are the oracle's."""
+    monkeypatch.setenv("PBX_BATCH_SEG_TILES", "37")
+    n, d, nq = 150_000, 256, 48
+    rng = np.random.default_rng(77)
+    corpus = rng.integers(0, 256, size=(n, d), dtype=np.uint8)
+    ids = rng.permutation(np.arange(1, n + 1)).astype(np.int64)
+    queries = rng.integers(0, 256, size=(nq, d), dtype=np.uint8)
+    queries[:16] = corpus[rng.integers(0, n, 16)]
+    with Corpus(d) as c:
+        c.load(ids, corpus)
+        for k in (100, 400):
+            before = c.stats().batched_queries
+            check(corpus, ids, queries, k, 1e3, c, oracle_every=3)
+            assert c.stats().batched_queries == before + nq, "the tensor-core path did not run"
