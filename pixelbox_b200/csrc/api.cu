@@ -1202,14 +1202,28 @@ static int enqueue_search_batched(pbx_corpus* c, const uint8_t* d_queries, uint3
     // So long shards run the pass in segments with the cut-back in between: the buffers start every segment at `keep`
     // entries, the thresholds carry over.
     const uint32_t all_tiles = (n + bp.tn - 1) / bp.tn;
-    uint32_t seg_tiles = keep > 512u ? kBatchSegTilesLarge : all_tiles;
-    if (const char* e = getenv("PBX_BATCH_SEG_TILES")) seg_tiles = std::max<uint32_t>(1u, (uint32_t)atoll(e));    // tests: segments on small shards
+    // Segment lengths for keep > 512, from what a buffer can take: a segment may add room = (cap - keep) / (1.5 keep) times
+    // keep keys per query (1.5: thresholds lag behind the rows).  The first segment starts from the seed thresholds (the
+    // keep-th best of the sample): keep * (1 + ln(rows / sample rows)) keys; a later one from exact thresholds over the rows
+    // so far: keep * ln(rows after / rows before).  keep = 1250: the 25M-row cap decides; keep = 2000: 2.9M rows first.
+    const double room = (double)(cap - std::min(cap, keep)) / (1.5 * (double)keep);
+    const double first_tiles = (double)std::max<uint32_t>(seed_tiles, 1u) * std::exp(std::max(0.0, std::min(room - 1.0, 20.0)));
+    const double growth = std::exp(std::min(room, 20.0)) - 1.0;
+    uint32_t forced_seg = 0;
+    if (const char* e = getenv("PBX_BATCH_SEG_TILES")) forced_seg = std::max<uint32_t>(1u, (uint32_t)atoll(e));    // tests: segments on small shards
     mp.tile_step = 1;
-    for (uint32_t t0 = 0; t0 < all_tiles; t0 += seg_tiles) {
-        mp.tile_base = t0; mp.n_tiles = std::min<uint32_t>(seg_tiles, all_tiles - t0);
+    for (uint32_t t0 = 0; t0 < all_tiles;) {
+        uint32_t seg = all_tiles - t0;
+        if (forced_seg) seg = std::min(seg, forced_seg);
+        else if (keep > 512u) {
+            const double lim = t0 == 0 ? first_tiles : (double)t0 * growth;
+            seg = std::min<uint32_t>(seg, (uint32_t)std::max(256.0, std::min(lim, (double)kBatchSegTilesLarge)));
+        }
+        mp.tile_base = t0; mp.n_tiles = seg;
         CU_TRY((bp.cg == 2 ? launch_batch_mma<2, false>(bp, mp, s) : launch_batch_mma<1, false>(bp, mp, s)));
         batch_tighten_kernel<<<nq, 256, (size_t)cap * sizeof(u64), s>>>(tp);
         CU_TRY(cudaGetLastError());
+        t0 += seg;
     }
 
     // per-query finalize: bit-exact re-rank, certificate; exact passes are tail-launched by its last CTA
