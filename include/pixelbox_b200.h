@@ -274,7 +274,7 @@ PBX_API int pbx_set_profiling(pbx_corpus* c, int enabled);
 /* Calls with at least `min_queries` queries take the tensor-core path (tcgen05 kind::i8 contraction with the top-k
  * fused into the epilogue) when the shape allows it (row pitch a multiple of 32 bytes, <= 1024; enough rows to seed the
  * thresholds); fewer queries, or other shapes, loop over the single-query scan.  0 restores the default (2: one
- * streaming pass over the corpus serves all queries of the call, 2 queries cost ~1.5x one); UINT32_MAX disables the
+ * streaming pass over the corpus serves all queries of the call, 2 to 128 queries cost ~1.15x one); UINT32_MAX disables the
  * batched path.  Results are identical either way. */
 PBX_API int pbx_set_batch_min(pbx_corpus* c, uint32_t min_queries);
 /* CTAs per SM of the persistent scan kernel (0 = default). */
